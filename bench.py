@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""CrossCLR fwd+bwd throughput benchmark (BASELINE.json metric: pairs/s at [B, D]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c4|c5]
+
+One step = one forward + one backward of the criterion over one synthetic [B, D] video/text batch
+(a "pair" = one (video_i, text_i) row pair).  N > 1 is launched by torchrun, one rank
+per GPU; the GLOBAL batch is sharded by rows (strong scaling: the global workload is fixed).
+
+Workloads (BASELINE.json `configs`; tau = 0.03, w = 0.8):
+    c2  B=4096   D=512   bf16   (configs[1], default at N = 1)
+    c3  B=16384  D=1024  bf16   (configs[2])
+    c4  B=65536  D=512   bf16   (configs[3], default at N > 1; global batch)
+    c5  B=131072 D=1024  bf16   (configs[4]; global batch)
+
+Printed JSON keys follow the bench contract: value (device-resident), e2e (pinned host buffers, H2D of the
+features and D2H of the loss inside the timed region), roofline (dominant kernel, per-kernel CUDA events from the
+library's timing hooks), cpu_baseline (the reference criterion on this box's host cores), clocks, gpu_launches.
+
+`--impl reference` times the reference's own CPU implementation (baseline/_ref/trainer/loss.py, an untracked
+verbatim copy, when present; else the numpy oracle port) on the host cores; nothing of the product runs there.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(B=4096, D=512, desc="BASELINE configs[1]: B=4096 D=512 bf16"),
+    "c3": dict(B=16384, D=1024, desc="BASELINE configs[2]: B=16384 D=1024 bf16"),
+    "c4": dict(B=65536, D=512, desc="BASELINE configs[3]: global B=65536 D=512 bf16"),
+    "c5": dict(B=131072, D=1024, desc="BASELINE configs[4]: global B=131072 D=1024 bf16"),
+}
+TAU, W = 0.03, 0.8
+METRIC = "crossclr_fwd_bwd_pairs_per_sec"
+UNIT = "pairs/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops"]), float(p["bf16_tflops_sustained"]), "measured"
+    except Exception:
+        return 1590.0, 1400.0, "fallback"
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference criterion on the host cores
+def _reference_runner():
+    """Returns (kind, fn(v, t) -> loss) running fwd+bwd on CPU fp32 tensors."""
+    import torch
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.exists(os.path.join(ref_dir, "trainer", "loss.py")):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_crossclr_reference_loss", os.path.join(ref_dir, "trainer", "loss.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        crit = mod.CrossCLR_onlyIntraModality(temperature=TAU, negative_weight=W)
+
+        def step(v, t):
+            # placement shim only: the reference hard-codes .cuda() (trainer/loss.py:66,103,104)
+            import torch as _t
+            orig = _t.Tensor.cuda
+            _t.Tensor.cuda = lambda self, *a, **k: self
+            try:
+                v = v.detach().requires_grad_()
+                t = t.detach().requires_grad_()
+                loss = crit(v, t)
+                loss.backward()
+                return float(loss)
+            finally:
+                _t.Tensor.cuda = orig
+        return "reference", step
+
+    from oracle import crossclr_oracle as O
+
+    def step(v, t):
+        loss, _, _ = O.loss_and_grads(v.numpy(), t.numpy(), TAU, W)
+        return loss
+    return "port", step
+
+
+def time_reference(B, D, steps, warmup, max_seconds=150.0):
+    """pairs/s of the reference criterion on the host cores (all threads), fp32, bounded by max_seconds."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, step = _reference_runner()
+    # bound the sample: the reference materialises ~216*B^2 bytes and takes ~1.8 s at B=4096 on 8 cores
+    Bs = min(B, 4096)
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(Bs, D, generator=g)
+    t = torch.randn(Bs, D, generator=g)
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step(v, t)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > max_seconds and len(times) >= 1:
+            break
+    best = min(times)
+    mean = sum(times) / len(times)
+    sample = (f"{len(times)} timed fwd+bwd steps of B={Bs} D={D} fp32 on {cores} threads ({cpu_model()}); "
+              f"mean {mean * 1e3:.1f} ms, best {best * 1e3:.1f} ms"
+              + ("" if Bs == B else f"; batch capped at {Bs} of {B}: the reference needs ~216*B^2 bytes"))
+    return dict(value=Bs / mean, unit=UNIT, cores=cores, kind=kind, sample=sample), mean, len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    cb, mean, n = time_reference(wl["B"], wl["D"], args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']} (reference CPU path, fp32 features)", "B": wl["B"],
+                   "D": wl["D"], "temperature": TAU, "negative_weight": W},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    import crossmodal_contrastive_learning_b200 as M
+    from crossmodal_contrastive_learning_b200 import _native as NAT
+    M.load_native()
+
+    wl = WORKLOADS[args.workload]
+    Bg, D = wl["B"], wl["D"]
+    assert Bg % world == 0
+    Bl = Bg // world
+    g = torch.Generator().manual_seed(0)
+    lo, hi = rank * Bl, (rank + 1) * Bl
+    # same seed on every rank; rank r keeps its rows.  Generated in row chunks.
+    v_host = torch.empty(Bl, D, dtype=torch.bfloat16).pin_memory()
+    t_host = torch.empty(Bl, D, dtype=torch.bfloat16).pin_memory()
+    chunk = 8192
+    for name, dst in (("v", v_host), ("t", t_host)):
+        for r0 in range(0, Bg, chunk):
+            blk = torch.randn(min(chunk, Bg - r0), D, generator=g)
+            a, b = max(r0, lo), min(r0 + blk.shape[0], hi)
+            if a < b:
+                dst[a - lo:b - lo] = blk[a - r0:b - r0].to(torch.bfloat16)
+    loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+
+    crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group).to(dev)
+    v_dev = v_host.to(dev)
+    t_dev = t_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step_resident():
+        v = v_dev.detach().requires_grad_()
+        t = t_dev.detach().requires_grad_()
+        loss = crit(v, t)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        v_dev.copy_(v_host, non_blocking=True)
+        t_dev.copy_(t_host, non_blocking=True)
+        loss = step_resident()
+        loss_host.copy_(loss, non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Sum of per-step device times (CUDA events on the launching stream); L2 flushed between steps."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        tt = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    for _ in range(3):
+        step_e2e()
+    torch.cuda.synchronize()
+
+    n0 = M.launch_count()
+    with ClockSampler(local_rank) as clk:
+        total_ms = timed(step_resident, args.steps)
+    launches = M.launch_count() - n0
+    e2e_ms = timed(step_e2e, args.steps)
+    loss_val = float(loss_host)
+
+    # second pass with the library's per-kernel events on (its own stream-ordered cudaEvents)
+    NAT.timing_enable(True)
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        step_resident()
+    torch.cuda.synchronize()
+    NAT.timing_enable(False)
+    ktimes = NAT.timing_read()
+    barrier()
+
+    cb = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cb, _, _ = time_reference(Bg, D, steps=3, warmup=1, max_seconds=30.0)
+
+    if rank == 0:
+        burst, sustained, src = measured_peaks()
+        ms_step = total_ms / args.steps
+        # dominant kernel = backward similarity/gradient kernel: 4 products = 8 B^2 D algorithmic FLOPs per step,
+        # this rank computes 1/world of them (DESIGN.md "Roofline accounting")
+        fam = {k: (ms / max(n, 1), n) for k, (ms, n) in ktimes.items()}
+        bwd_ms, bwd_n = fam["bwd"]
+        fwd_ms, fwd_n = fam["fwd"]
+        alg_bwd = 8.0 * Bg * Bg * D / world
+        alg_fwd = 6.0 * Bg * Bg * D / world
+        achieved = alg_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": Bg / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (bf16 features in, bf16 grads out)",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "B_global": Bg, "B_per_gpu": Bl, "D": D,
+                       "temperature": TAU, "negative_weight": W, "l2": "flushed between steps (256 MiB write)",
+                       "parallelism": f"row-sharded x{world}, NCCL all-gather of features + row stats" if world > 1 else "single GPU",
+                       "loss": loss_val},
+            "e2e": {"value": Bg / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "bwd_tc_kernel", "achieved": achieved, "peak": burst,
+                         "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": None,
+                         "peak_source": f"{src} bf16_tflops (burst; kernel timed alone with CUDA events)",
+                         "algorithmic_flops_per_launch": alg_bwd, "avg_launch_ms": bwd_ms, "launches_timed": bwd_n,
+                         "fwd_kernel": {"avg_launch_ms": fwd_ms, "algorithmic_flops_per_launch": alg_fwd,
+                                        "achieved": (alg_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None)},
+                         "step": {"algorithmic_flops": 14.0 * Bg * Bg * D / world,
+                                  "achieved": 14.0 * Bg * Bg * D / world / (ms_step * 1e-3) / 1e12,
+                                  "frac_of_sustained": 14.0 * Bg * Bg * D / world / (ms_step * 1e-3) / 1e12 / sustained},
+                         "kernel_ms_per_step": {k: ms / args.steps for k, (ms, n) in ktimes.items()}},
+            "clocks": clk.summary(),
+        }
+        if cb is not None:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "c2" if args.gpus == 1 else "c4"
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

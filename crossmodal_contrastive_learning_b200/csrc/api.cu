@@ -1,0 +1,210 @@
+// extern "C" entry points of libcrossclr_b200 (see include/crossclr_b200.h for the contract).
+#include "common.cuh"
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace crossclr {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- per-kernel event timing ------------------------------------------------------------------------
+namespace {
+struct TimingRec { int kernel; cudaEvent_t a, b; };
+std::atomic<int> g_timing_on{0};
+std::mutex g_timing_mu;
+std::vector<TimingRec> g_timing;
+thread_local cudaEvent_t tl_start = nullptr;
+}  // namespace
+
+void timing_begin(int kernel, cudaStream_t st) {
+  (void)kernel;
+  if (!g_timing_on.load(std::memory_order_relaxed)) return;
+  cudaEventCreate(&tl_start);
+  cudaEventRecord(tl_start, st);
+}
+void timing_end(int kernel, cudaStream_t st) {
+  if (tl_start == nullptr) return;
+  TimingRec r{kernel, tl_start, nullptr};
+  tl_start = nullptr;
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.b, st);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timing.push_back(r);
+}
+
+int validate_problem(const crossclr_problem_t* p) {
+  CC_REQUIRE(p != nullptr, "problem is NULL");
+  CC_REQUIRE(p->nseg >= 2 && (p->nseg % 2) == 0, "nseg must be a positive even number (got %d)", p->nseg);
+  CC_REQUIRE(p->bseg >= 1 && p->dim >= 1, "bseg and dim must be >= 1 (got %d, %d)", p->bseg, p->dim);
+  CC_REQUIRE((int64_t)p->nseg * p->bseg < (int64_t)1 << 30, "too many stacked rows");
+  CC_REQUIRE(p->row_count == 2 * p->bseg && p->row_begin >= 0 && p->row_begin % (2 * p->bseg) == 0 &&
+                 p->row_begin + p->row_count <= p->nseg * p->bseg,
+             "owned rows must be one rank's [video; text] pair of segments (row_begin %d row_count %d)",
+             p->row_begin, p->row_count);
+  CC_REQUIRE(p->temperature > 0.f && std::isfinite(p->temperature), "temperature must be positive and finite");
+  CC_REQUIRE(std::isfinite(p->negative_weight), "negative_weight must be finite");
+  return CROSSCLR_OK;
+}
+
+static bool tc_shape_ok(const crossclr_problem_t* p) { return p->bseg % 128 == 0 && p->dim % 64 == 0; }
+
+static size_t dfhat_bytes(const crossclr_problem_t* p) {
+  return ((size_t)p->row_count * (size_t)p->dim * sizeof(float) + 255) & ~(size_t)255;
+}
+
+}  // namespace crossclr
+
+using namespace crossclr;
+
+extern "C" {
+
+int crossclr_version(void) { return CROSSCLR_VERSION; }
+
+const char* crossclr_last_error(void) { return g_err; }
+
+int crossclr_device_supported(int device) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e != cudaSuccess) {
+    set_error("cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    return CROSSCLR_ECUDA;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact) {
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  (void)in_dtype;
+  return (tc_shape_ok(p) && !exact) ? CROSSCLR_PATH_TC : CROSSCLR_PATH_SIMT;
+}
+
+int crossclr_feature_dtype(int path) {
+  if (path == CROSSCLR_PATH_SIMT) return CROSSCLR_F32;
+  if (path == CROSSCLR_PATH_TC) return CROSSCLR_F16;
+  set_error("crossclr_feature_dtype: path must be SIMT or TC");
+  return CROSSCLR_EINVAL;
+}
+
+size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {
+  (void)path;
+  if (validate_problem(p)) return 0;
+  return dfhat_bytes(p);
+}
+
+float crossclr_shift(const crossclr_problem_t* p) { return problem_shift(p); }
+
+int64_t crossclr_launch_count(void) { return g_launches.load(); }
+
+int crossclr_pack(const void* x, int in_dtype, int64_t x_row_stride, int32_t rows, int32_t dim, void* feat_out,
+                  int feat_dtype, float* rnorm_out, void* stream) {
+  CC_REQUIRE(x && feat_out && rnorm_out, "crossclr_pack: NULL pointer");
+  CC_REQUIRE(rows >= 0 && dim >= 1 && x_row_stride >= dim, "crossclr_pack: bad shape/stride");
+  return launch_pack(x, in_dtype, x_row_stride, rows, dim, feat_out, feat_dtype, rnorm_out, (cudaStream_t)stream);
+}
+
+int crossclr_fwd(const crossclr_problem_t* p, int path, const void* feat, float* stats, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  CC_REQUIRE(feat && stats, "crossclr_fwd: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geometry g = make_geometry(p);
+  // X accumulates with atomics across column ranges: zero the owned rows first
+  CC_CHECK_CUDA(cudaMemsetAsync(stats + 2 * (size_t)g.row_begin, 0, 2 * (size_t)g.row_count * sizeof(float), st));
+  if (path == CROSSCLR_PATH_TC) {
+    CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
+               p->bseg, p->dim);
+    return launch_fwd_tc(g, feat, stats, st);
+  }
+  CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_fwd: path must be SIMT or TC (got %d)", path);
+  return launch_fwd_simt(g, (const float*)feat, stats, st);
+}
+
+int crossclr_finalize(const crossclr_problem_t* p, const float* stats, float* coef, double* loss_out, float* scal,
+                      void* stream) {
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  CC_REQUIRE(stats && coef && loss_out && scal, "crossclr_finalize: NULL pointer");
+  return launch_finalize(make_geometry(p), stats, coef, loss_out, scal, (cudaStream_t)stream);
+}
+
+int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned, const float* coef,
+                 const float* scal, const double* grad_out, float grad_scale, void* dv, int64_t dv_row_stride,
+                 void* dt, int64_t dt_row_stride, int out_dtype, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  CC_REQUIRE(feat && rnorm_owned && coef && scal && dv && dt, "crossclr_bwd: NULL pointer");
+  CC_REQUIRE(dv_row_stride >= p->dim && dt_row_stride >= p->dim, "crossclr_bwd: output row stride < dim");
+  if (workspace == nullptr || workspace_bytes < dfhat_bytes(p)) {
+    set_error("crossclr_bwd: workspace too small (%zu < %zu)", workspace_bytes, dfhat_bytes(p));
+    return CROSSCLR_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Geometry g = make_geometry(p);
+  float* dfhat = (float*)workspace;
+  int feat_dtype;
+  bool use_sigma;
+  if (path == CROSSCLR_PATH_TC) {
+    CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
+               p->bseg, p->dim);
+    rc = launch_bwd_tc(g, feat, coef, scal, dfhat, st);
+    feat_dtype = CROSSCLR_F16;
+    use_sigma = true;
+  } else {
+    CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_bwd: path must be SIMT or TC (got %d)", path);
+    rc = launch_bwd_simt(g, (const float*)feat, coef, dfhat, st);
+    feat_dtype = CROSSCLR_F32;
+    use_sigma = false;
+  }
+  if (rc) return rc;
+  return launch_grad_finish(g, feat, feat_dtype, rnorm_owned, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
+                            dv_row_stride, dt, dt_row_stride, out_dtype, st);
+}
+
+int crossclr_timing_enable(int on) {
+  g_timing_on.store(on ? 1 : 0);
+  return CROSSCLR_OK;
+}
+
+int crossclr_timing_read(int kernel, double* total_ms, int64_t* launches) {
+  CC_REQUIRE(kernel >= 0 && kernel < CROSSCLR_K_COUNT && total_ms && launches, "crossclr_timing_read: bad argument");
+  double ms = 0.0;
+  int64_t n = 0;
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  std::vector<TimingRec> keep;
+  for (const TimingRec& r : g_timing) {
+    if (r.kernel != kernel) { keep.push_back(r); continue; }
+    float t = 0.f;
+    CC_CHECK_CUDA(cudaEventSynchronize(r.b));
+    CC_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    ms += t;
+    ++n;
+  }
+  g_timing.swap(keep);
+  *total_ms = ms;
+  *launches = n;
+  return CROSSCLR_OK;
+}
+
+int crossclr_selftest(int variant, const uint16_t* a_host, const uint16_t* b_host, float* out_host, int32_t n,
+                      int32_t k) {
+  CC_REQUIRE(a_host && b_host && out_host, "crossclr_selftest: NULL pointer");
+  return run_selftest(variant, a_host, b_host, out_host, n, k);
+}
+
+}  // extern "C"

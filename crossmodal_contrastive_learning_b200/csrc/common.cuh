@@ -1,0 +1,148 @@
+// Shared helpers for libcrossclr_b200 (host + device).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "crossclr_b200.h"
+
+namespace crossclr {
+
+constexpr float kEps = 1e-12f;              // F.normalize default eps (trainer/loss.py:79-80)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kShiftHeadroom = 96.0f;     // largest shifted log2-logit we allow: 2^96 * 2^19 rows < 2^127
+
+// ---- error reporting -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define CC_CHECK_CUDA(expr)                                                                        \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::crossclr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CROSSCLR_ECUDA;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define CC_REQUIRE(cond, ...)                                                                      \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      ::crossclr::set_error(__VA_ARGS__);                                                          \
+      return CROSSCLR_EINVAL;                                                                      \
+    }                                                                                              \
+  } while (0)
+
+// per-kernel event timing (api.cu); a no-op unless crossclr_timing_enable(1) was called
+void timing_begin(int kernel, cudaStream_t st);
+void timing_end(int kernel, cudaStream_t st);
+struct TimedLaunch {
+  int k; cudaStream_t st;
+  TimedLaunch(int k_, cudaStream_t st_) : k(k_), st(st_) { timing_begin(k, st); }
+  ~TimedLaunch() { timing_end(k, st); }
+};
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return CROSSCLR_ECUDA;
+  }
+  return CROSSCLR_OK;
+}
+
+// ---- problem geometry (shared by every kernel) -------------------------------------------------
+struct Geometry {
+  int nseg, bseg, dim, rows;       // rows = nseg * bseg
+  int row_begin, row_count;
+  float k_inter;                   // log2e / tau
+  float k_intra;                   // w * log2e / tau
+  float shift;                     // log2-domain shift
+  float inv_tau;
+  float w;
+};
+
+inline float problem_shift(const crossclr_problem_t* p) {
+  float wmax = fmaxf(1.0f, fabsf(p->negative_weight));
+  float lmax = kLog2e * wmax / p->temperature;
+  return fmaxf(0.0f, lmax - kShiftHeadroom);
+}
+
+inline Geometry make_geometry(const crossclr_problem_t* p) {
+  Geometry g;
+  g.nseg = p->nseg; g.bseg = p->bseg; g.dim = p->dim; g.rows = p->nseg * p->bseg;
+  g.row_begin = p->row_begin; g.row_count = p->row_count;
+  g.inv_tau = 1.0f / p->temperature;
+  g.k_inter = kLog2e / p->temperature;
+  g.k_intra = p->negative_weight * kLog2e / p->temperature;
+  g.shift = problem_shift(p);
+  g.w = p->negative_weight;
+  return g;
+}
+
+int validate_problem(const crossclr_problem_t* p);
+
+// modality (0 video / 1 text) and sample index of stacked row g
+__host__ __device__ __forceinline__ int row_modality(int g, int bseg) { return (g / bseg) & 1; }
+__host__ __device__ __forceinline__ int row_sample(int g, int bseg) {
+  int s = g / bseg;
+  return (s >> 1) * bseg + (g - s * bseg);
+}
+__host__ __device__ __forceinline__ int row_partner(int g, int bseg) {
+  return ((g / bseg) & 1) ? g - bseg : g + bseg;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ float to_float(T x);
+template <> __device__ __forceinline__ float to_float<float>(float x) { return x; }
+template <> __device__ __forceinline__ float to_float<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T> __device__ __forceinline__ T from_float(float x);
+template <> __device__ __forceinline__ float from_float<float>(float x) { return x; }
+template <> __device__ __forceinline__ __half from_float<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// ---- entry points implemented per translation unit --------------------------------------------
+// simt_kernels.cu
+int launch_pack(const void* x, int in_dtype, int64_t stride, int rows, int dim, void* out, int out_dtype,
+                float* rnorm, cudaStream_t st);
+int launch_fwd_simt(const Geometry& g, const float* feat, float* stats, cudaStream_t st);
+int launch_bwd_simt(const Geometry& g, const float* feat, const float* coef, float* dfhat, cudaStream_t st);
+int launch_finalize(const Geometry& g, const float* stats, float* coef, double* loss, float* scal, cudaStream_t st);
+int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm_owned,
+                       const float* coef, const float* scal, bool use_sigma, const double* grad_out,
+                       float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,
+                       int64_t dt_stride, int out_dtype, cudaStream_t st);
+// tc_kernels.cu
+int launch_fwd_tc(const Geometry& g, const void* feat_f16, float* stats, cudaStream_t st);
+int launch_bwd_tc(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
+                  cudaStream_t st);
+int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k);
+
+}  // namespace crossclr

@@ -1,0 +1,443 @@
+// CUDA-core (SIMT) kernels of libcrossclr_b200:
+//   * pack / rownorm / finalize / grad_finish -- the O(B*D) and O(B) stages shared by both paths
+//   * fwd_simt / bwd_simt -- exact-fp32 similarity kernels for any B, D (the generic path; also the
+//     on-device cross-check for the tcgen05 path).
+// Math follows trainer/loss.py:79-114 of the reference as restated in SURVEY.md App. A.
+#include "common.cuh"
+
+namespace crossclr {
+
+// ================================================================================================
+// pack: L2-normalise one modality block into its segment of the stacked matrix (trainer/loss.py:79-80,
+// F.normalize with eps 1e-12) and keep the reciprocal norms for the backward.  One warp per row.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ x, int64_t stride, int rows, int dim,
+                                                  Tout* __restrict__ out, float* __restrict__ rnorm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const Tin* src = x + (int64_t)row * stride;
+  Tout* dst = out + (int64_t)row * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    const float f = to_float<Tin>(src[d]);
+    ss = fmaf(f, f, ss);
+  }
+  ss = warp_sum(ss);
+  const float rn = 1.0f / fmaxf(sqrtf(ss), kEps);
+  for (int d = lane; d < dim; d += 32) dst[d] = from_float<Tout>(to_float<Tin>(src[d]) * rn);
+  if (lane == 0) rnorm[row] = rn;
+}
+
+// bf16 -> fp16 fast path: 16-byte vectors (requires dim % 8 == 0, 16B-aligned rows)
+__global__ void __launch_bounds__(256) pack_bf16_f16_vec_kernel(const uint4* __restrict__ x, int64_t stride_vec,
+                                                               int rows, int dim_vec, uint4* __restrict__ out,
+                                                               float* __restrict__ rnorm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* src = x + (int64_t)row * stride_vec;
+  uint4* dst = out + (int64_t)row * dim_vec;
+  float ss = 0.f;
+  for (int d = lane; d < dim_vec; d += 32) {
+    const uint4 u = __ldg(src + d);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      ss = fmaf(f.x, f.x, ss);
+      ss = fmaf(f.y, f.y, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float rn = 1.0f / fmaxf(sqrtf(ss), kEps);
+  for (int d = lane; d < dim_vec; d += 32) {
+    const uint4 u = __ldg(src + d);     // second pass hits L1/L2
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      oh[i] = __floats2half2_rn(f.x * rn, f.y * rn);
+    }
+    dst[d] = o;
+  }
+  if (lane == 0) rnorm[row] = rn;
+}
+
+template <typename Tin>
+static int pack_dispatch_out(const void* x, int64_t stride, int rows, int dim, void* out, int out_dtype,
+                             float* rnorm, cudaStream_t st) {
+  dim3 block(256), grid((rows + 7) / 8);
+  if (out_dtype == CROSSCLR_F32) {
+    pack_kernel<Tin, float><<<grid, block, 0, st>>>((const Tin*)x, stride, rows, dim, (float*)out, rnorm);
+  } else if (out_dtype == CROSSCLR_F16) {
+    pack_kernel<Tin, __half><<<grid, block, 0, st>>>((const Tin*)x, stride, rows, dim, (__half*)out, rnorm);
+  } else {
+    set_error("crossclr_pack: unsupported stacked dtype %d", out_dtype);
+    return CROSSCLR_EINVAL;
+  }
+  return check_launch("pack_kernel");
+}
+
+int launch_pack(const void* x, int in_dtype, int64_t stride, int rows, int dim, void* out, int out_dtype,
+                float* rnorm, cudaStream_t st) {
+  if (rows == 0) return CROSSCLR_OK;
+  TimedLaunch timed(CROSSCLR_K_PACK, st);
+  if (in_dtype == CROSSCLR_BF16 && out_dtype == CROSSCLR_F16 && dim % 8 == 0 && stride % 8 == 0 &&
+      ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
+    dim3 block(256), grid((rows + 7) / 8);
+    pack_bf16_f16_vec_kernel<<<grid, block, 0, st>>>((const uint4*)x, stride / 8, rows, dim / 8, (uint4*)out, rnorm);
+    return check_launch("pack_bf16_f16_vec_kernel");
+  }
+  switch (in_dtype) {
+    case CROSSCLR_F32: return pack_dispatch_out<float>(x, stride, rows, dim, out, out_dtype, rnorm, st);
+    case CROSSCLR_F16: return pack_dispatch_out<__half>(x, stride, rows, dim, out, out_dtype, rnorm, st);
+    case CROSSCLR_BF16: return pack_dispatch_out<__nv_bfloat16>(x, stride, rows, dim, out, out_dtype, rnorm, st);
+    default: set_error("crossclr_pack: unsupported input dtype %d", in_dtype); return CROSSCLR_EINVAL;
+  }
+}
+
+// ================================================================================================
+// fwd_simt: 64x64 similarity tiles on CUDA cores, fused scale / mask / exp2 / row-sum epilogue.
+// Replaces trainer/loss.py:83-100 + the row sums of :59-60 for the owned rows.
+constexpr int FT = 64;   // tile rows == tile cols
+constexpr int FK = 16;   // k chunk
+
+__global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* __restrict__ F,
+                                                      float* __restrict__ stats, int col_tiles_per_block) {
+  __shared__ float As[FK][FT + 4];
+  __shared__ float Bs[FK][FT + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row0 = g.row_begin + blockIdx.x * FT;
+  const int row_end = g.row_begin + g.row_count;
+  const int n_col_tiles = (g.rows + FT - 1) / FT;
+  const int ct0 = blockIdx.y * col_tiles_per_block;
+  const int ct1 = min(n_col_tiles, ct0 + col_tiles_per_block);
+
+  int gi[4], mod_i[4], samp_i[4];
+  float rsum[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    gi[r] = row0 + ty * 4 + r;
+    bool ok = gi[r] < row_end;
+    int gg = ok ? gi[r] : g.row_begin;
+    mod_i[r] = row_modality(gg, g.bseg);
+    samp_i[r] = row_sample(gg, g.bseg);
+    rsum[r] = 0.f;
+    if (!ok) gi[r] = -1;
+  }
+
+  for (int ct = ct0; ct < ct1; ++ct) {
+    const int col0 = ct * FT;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+    for (int k0 = 0; k0 < g.dim; k0 += FK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int e = threadIdx.x + 256 * i;
+        int rr = e >> 4, kk = e & 15;
+        int ga = row0 + rr, gb = col0 + rr, kd = k0 + kk;
+        As[kk][rr] = (ga < row_end && kd < g.dim) ? F[(int64_t)ga * g.dim + kd] : 0.f;
+        Bs[kk][rr] = (gb < g.rows && kd < g.dim) ? F[(int64_t)gb * g.dim + kd] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < FK; ++kk) {
+        float a[4], b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) b[c] = Bs[kk][tx * 4 + c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+      }
+      __syncthreads();
+    }
+
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = col0 + tx * 4 + c;
+      if (j >= g.rows) continue;
+      const int mod_j = row_modality(j, g.bseg);
+      const int samp_j = row_sample(j, g.bseg);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (gi[r] < 0) continue;
+        const bool same_mod = (mod_i[r] == mod_j);
+        const float k = same_mod ? g.k_intra : g.k_inter;
+        const float x = fmaf(acc[r][c], k, -g.shift);
+        if (samp_i[r] == samp_j) {
+          if (same_mod) rsum[r] += exp2f(-g.shift);   // masked intra-modal diagonal: logit 0 (loss.py:65,96-97)
+          else stats[2 * (int64_t)gi[r] + 1] = x;     // the positive logit a_ii (loss.py:102-109)
+        } else {
+          rsum[r] += exp2f(x);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float v = rsum[r];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (tx == 0 && gi[r] >= 0) atomicAdd(&stats[2 * (int64_t)gi[r]], v);
+  }
+}
+
+int launch_fwd_simt(const Geometry& g, const float* feat, float* stats, cudaStream_t st) {
+  TimedLaunch timed(CROSSCLR_K_FWD, st);
+  const int row_tiles = (g.row_count + FT - 1) / FT;
+  const int n_col_tiles = (g.rows + FT - 1) / FT;
+  int splits = max(1, min(n_col_tiles, (2 * 148 + row_tiles - 1) / row_tiles));
+  int per = (n_col_tiles + splits - 1) / splits;
+  splits = (n_col_tiles + per - 1) / per;
+  dim3 grid(row_tiles, splits), block(256);
+  fwd_simt_kernel<<<grid, block, 0, st>>>(g, feat, stats, per);
+  return check_launch("fwd_simt_kernel");
+}
+
+// ================================================================================================
+// bwd_simt: dFhat[g][d] = sum_j P_gj * F_j[d]  with
+//   P_gj = 2^(x_gj) * (1/Z_g + 1/Z_j) * kappa_gj   (0 for the same-sample pair), F = normalised rows
+// i.e. the un-normalised gradient w.r.t. the normalised row, without the positive-pair term (added in
+// grad_finish).  Block = 32 rows x one 256-wide slab of D; similarity tiles are recomputed per slab.
+constexpr int BR = 32, BJ = 32, BK = 32, BSLAB = 256;
+
+__global__ void __launch_bounds__(256) bwd_simt_kernel(Geometry g, const float* __restrict__ F,
+                                                      const float* __restrict__ coef, float* __restrict__ dfhat) {
+  __shared__ float As[BK][BR + 1];
+  __shared__ float Bs[BK][BJ + 1];
+  __shared__ float Ps[BR][BJ + 1];
+  const int t = threadIdx.x;
+  const int row0 = g.row_begin + blockIdx.x * BR;
+  const int row_end = g.row_begin + g.row_count;
+  const int d = blockIdx.y * BSLAB + t;
+  const int tys = t >> 5, txs = t & 31;
+
+  float acc[BR];
+#pragma unroll
+  for (int r = 0; r < BR; ++r) acc[r] = 0.f;
+
+  int gi[4], mod_i[4], samp_i[4];
+  float iz_i[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    gi[r] = row0 + tys * 4 + r;
+    bool ok = gi[r] < row_end;
+    int gg = ok ? gi[r] : g.row_begin;
+    mod_i[r] = row_modality(gg, g.bseg);
+    samp_i[r] = row_sample(gg, g.bseg);
+    iz_i[r] = coef[2 * (int64_t)gg];
+    if (!ok) gi[r] = -1;
+  }
+
+  for (int j0 = 0; j0 < g.rows; j0 += BJ) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < g.dim; k0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int e = t + 256 * i;
+        int rr = e >> 5, kk = e & 31;
+        int ga = row0 + rr, gb = j0 + rr, kd = k0 + kk;
+        As[kk][rr] = (ga < row_end && kd < g.dim) ? F[(int64_t)ga * g.dim + kd] : 0.f;
+        Bs[kk][rr] = (gb < g.rows && kd < g.dim) ? F[(int64_t)gb * g.dim + kd] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float b = Bs[kk][txs];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r] = fmaf(As[kk][tys * 4 + r], b, s[r]);
+      }
+      __syncthreads();
+    }
+    {
+      const int j = j0 + txs;
+      const bool jok = j < g.rows;
+      const int jj = jok ? j : 0;
+      const int mod_j = row_modality(jj, g.bseg);
+      const int samp_j = row_sample(jj, g.bseg);
+      const float iz_j = coef[2 * (int64_t)jj];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float p = 0.f;
+        if (jok && gi[r] >= 0 && samp_i[r] != samp_j) {
+          const bool same_mod = (mod_i[r] == mod_j);
+          const float k = same_mod ? g.k_intra : g.k_inter;
+          const float x = fmaf(s[r], k, -g.shift);
+          p = exp2f(x) * (iz_i[r] + iz_j) * (same_mod ? g.w : 1.0f);
+        }
+        Ps[tys * 4 + r][txs] = p;
+      }
+    }
+    __syncthreads();
+    if (d < g.dim) {
+      const int jn = min(BJ, g.rows - j0);
+      for (int jj = 0; jj < jn; ++jj) {
+        const float fj = F[(int64_t)(j0 + jj) * g.dim + d];
+#pragma unroll
+        for (int r = 0; r < BR; ++r) acc[r] = fmaf(Ps[r][jj], fj, acc[r]);
+      }
+    }
+    __syncthreads();
+  }
+  if (d < g.dim) {
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      int gr = row0 + r;
+      if (gr < row_end) dfhat[(int64_t)(gr - g.row_begin) * g.dim + d] = acc[r];
+    }
+  }
+}
+
+int launch_bwd_simt(const Geometry& g, const float* feat, const float* coef, float* dfhat, cudaStream_t st) {
+  TimedLaunch timed(CROSSCLR_K_BWD, st);
+  dim3 grid((g.row_count + BR - 1) / BR, (g.dim + BSLAB - 1) / BSLAB), block(256);
+  bwd_simt_kernel<<<grid, block, 0, st>>>(g, feat, coef, dfhat);
+  return check_launch("bwd_simt_kernel");
+}
+
+// ================================================================================================
+// finalize: loss (trainer/loss.py:60,:111-114) + backward coefficients from per-row statistics.
+// Single block; the cancellation-free form loss_g = log1p(X_g / 2^xpos_g) is evaluated in double.
+__global__ void __launch_bounds__(1024) finalize_kernel(Geometry g, const float* __restrict__ stats,
+                                                       float* __restrict__ coef, double* __restrict__ loss,
+                                                       float* __restrict__ scal) {
+  __shared__ double s_sum[32];
+  __shared__ float s_rho[32];
+  double lsum = 0.0;
+  float rho_max = 0.f;
+  for (int i = threadIdx.x; i < g.rows; i += blockDim.x) {
+    const float X = stats[2 * (int64_t)i], xp = stats[2 * (int64_t)i + 1];
+    const float e = exp2f(xp);
+    const float Z = X + e;
+    const float iz = 1.0f / Z;
+    const float rho = X / Z;
+    coef[2 * (int64_t)i] = iz;
+    coef[2 * (int64_t)i + 1] = rho;
+    lsum += log1p((double)X * exp2(-(double)xp));
+    rho_max = fmaxf(rho_max, rho);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  rho_max = warp_max(rho_max);
+  if (lane == 0) { s_sum[wid] = lsum; s_rho[wid] = rho_max; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    lsum = lane < nw ? s_sum[lane] : 0.0;
+    rho_max = lane < nw ? s_rho[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    rho_max = warp_max(rho_max);
+    if (lane == 0) {
+      loss[0] = lsum / (double)g.rows;
+      // fp16 probability tiles hold sigma * 2^x (1/Z_g + 1/Z_j) kappa <= sigma * 2 rho_max max(1,|w|)
+      const float bound = 2.0f * rho_max * fmaxf(1.0f, fabsf(g.w));
+      int ex = 0;
+      if (bound > 0.f && isfinite(bound)) ex = 14 - (int)ceilf(log2f(bound));
+      ex = max(-100, min(100, ex));
+      scal[0] = exp2f((float)ex);
+      scal[1] = exp2f((float)-ex);
+      scal[2] = rho_max;
+      scal[3] = 0.f;
+    }
+  }
+}
+
+int launch_finalize(const Geometry& g, const float* stats, float* coef, double* loss, float* scal,
+                    cudaStream_t st) {
+  TimedLaunch timed(CROSSCLR_K_FINALIZE, st);
+  finalize_kernel<<<1, 1024, 0, st>>>(g, stats, coef, loss, scal);
+  return check_launch("finalize_kernel");
+}
+
+// ================================================================================================
+// grad_finish: positive-pair term, F.normalize backward (projection + 1/norm), upstream scale, cast.
+//   dFhat_g  = (c/tau) [ acc_g / sigma - (rho_g + rho_partner) * Fhat_partner ]      c = 1/(2B)
+//   dF_g     = rnorm_g (dFhat_g - (dFhat_g . Fhat_g) Fhat_g)      (no projection if ||F_g|| < eps)
+// `F` holds the normalised rows (fp32 or fp16); `rn` the reciprocal norms of the owned rows.
+// One warp per owned row.
+template <typename TF, typename TO>
+__global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* __restrict__ F,
+                                                         const float* __restrict__ rn, const float* __restrict__ coef,
+                                                         const float* __restrict__ scal, bool use_sigma,
+                                                         const double* __restrict__ grad_out, float grad_scale,
+                                                         const float* __restrict__ dfhat, TO* __restrict__ dv,
+                                                         int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride) {
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (l >= g.row_count) return;
+  const int gr = g.row_begin + l;
+  const int pg = row_partner(gr, g.bseg);
+  const float rn_g = rn[l];                    // reciprocal norms of the OWNED rows only
+  const float acc_scale = use_sigma ? scal[1] : 1.0f;
+  const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]);
+  const TF* fg = F + (int64_t)gr * g.dim;
+  const TF* fp = F + (int64_t)pg * g.dim;
+  const float* dh = dfhat + (int64_t)l * g.dim;
+  float dot = 0.f;
+  for (int d = lane; d < g.dim; d += 32) {
+    const float h = dh[d] * acc_scale + pos_coef * to_float<TF>(fp[d]);
+    dot = fmaf(h, to_float<TF>(fg[d]), dot);
+  }
+  dot = warp_sum(dot);
+  if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
+  double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows;
+  if (grad_out != nullptr) m *= grad_out[0];
+  const float mult = (float)m * rn_g;
+  const int mod = row_modality(gr, g.bseg);
+  const int r = gr % g.bseg;
+  TO* out = mod == 0 ? dv + (int64_t)r * dv_stride : dt + (int64_t)r * dt_stride;
+  for (int d = lane; d < g.dim; d += 32) {
+    const float h = dh[d] * acc_scale + pos_coef * to_float<TF>(fp[d]);
+    out[d] = from_float<TO>(mult * (h - dot * to_float<TF>(fg[d])));
+  }
+}
+
+template <typename TF>
+static int grad_finish_out(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
+                           const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
+                           const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, int out_dtype,
+                           cudaStream_t st) {
+  dim3 block(256), grid((g.row_count + 7) / 8);
+#define CC_GF(TO)                                                                                             \
+  grad_finish_kernel<TF, TO><<<grid, block, 0, st>>>(g, (const TF*)feat, rnorm, coef, scal, use_sigma, grad_out, \
+                                                    grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
+  switch (out_dtype) {
+    case CROSSCLR_F32: CC_GF(float); break;
+    case CROSSCLR_F16: CC_GF(__half); break;
+    case CROSSCLR_BF16: CC_GF(__nv_bfloat16); break;
+    default: set_error("crossclr_bwd: unsupported output dtype %d", out_dtype); return CROSSCLR_EINVAL;
+  }
+#undef CC_GF
+  return check_launch("grad_finish_kernel");
+}
+
+int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm,
+                       const float* coef, const float* scal, bool use_sigma, const double* grad_out,
+                       float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,
+                       int64_t dt_stride, int out_dtype, cudaStream_t st) {
+  TimedLaunch timed(CROSSCLR_K_GRADFIN, st);
+  if (feat_dtype == CROSSCLR_F32)
+    return grad_finish_out<float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
+                                  dv_stride, dt, dt_stride, out_dtype, st);
+  if (feat_dtype == CROSSCLR_F16)
+    return grad_finish_out<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat,
+                                          dv, dv_stride, dt, dt_stride, out_dtype, st);
+  set_error("crossclr_bwd: unsupported stacked dtype %d", feat_dtype);
+  return CROSSCLR_EINVAL;
+}
+
+}  // namespace crossclr

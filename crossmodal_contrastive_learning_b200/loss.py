@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference criterion module for the CrossCLR hot path.
+
+`CrossCLR_onlyIntraModality` keeps the surface of the reference `nn.Module`
+(`trainer/loss.py:44-114`): same constructor `(temperature=0.03, negative_weight=0.8, logger=None)`
+(`:50`), same attributes (`temperature`, `negative_w`, `logger`, the dormant `logit_scale` Parameter and the
+unused `criterion` child, `:52-56`), same `forward(video_features, text_features)` (`:68`) returning a 0-dim
+float64 tensor on the inputs' device with gradients in the input dtype, and plain `RuntimeError` on shape /
+device mismatches.  Everything between the inputs and the loss runs in libcrossclr_b200.so (hand-written
+sm_100a kernels behind the C ABI of include/crossclr_b200.h); torch only owns device memory, the stream and,
+for more than one rank, the two NCCL all-gathers.
+
+There is no CPU / eager fallback: without the native library, or with CPU tensors, `forward` raises.
+
+Multi-GPU (keyword-only extension; the reference is single-device): rank r holds rows
+[r*B, (r+1)*B) of the global batch.  Normalised rows are all-gathered, every rank reduces the statistics of
+its own rows, the per-row statistics are all-gathered, and every rank returns the identical GLOBAL loss and
+the gradient of that global loss w.r.t. its own rows (times `grad_scale`) -- no gradient collective.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+_DTYPE_CODE = {torch.float32: N.F32, torch.float16: N.F16, torch.bfloat16: N.BF16}
+_FEAT_TORCH = {N.F32: torch.float32, N.F16: torch.float16}
+_PATH_CODE = {"auto": N.PATH_AUTO, "simt": N.PATH_SIMT, "tc": N.PATH_TC}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_inputs(v, t):
+    # The reference validates nothing itself; torch raises RuntimeError from inside its ops
+    # (trainer/loss.py:83 for ndim / D mismatch, :97 for B mismatch, :66 for CPU tensors).  Same class here.
+    if v.dim() != 2 or t.dim() != 2:
+        raise RuntimeError(f"CrossCLR expects 2-D [B, D] features, got {tuple(v.shape)} and {tuple(t.shape)}")
+    if v.shape[1] != t.shape[1]:
+        raise RuntimeError(f"feature dims differ: {v.shape[1]} vs {t.shape[1]} (mat1 and mat2 shapes cannot be multiplied)")
+    if v.shape[0] != t.shape[0]:
+        raise RuntimeError(f"batch sizes differ: {v.shape[0]} vs {t.shape[0]}")
+    if v.shape[0] < 1 or v.shape[1] < 1:
+        raise RuntimeError("CrossCLR needs at least one row and one feature")
+    if not (v.is_cuda and t.is_cuda):
+        raise RuntimeError("CrossCLR_onlyIntraModality (B200-native) needs CUDA tensors: the criterion has no CPU path")
+    if v.device != t.device:
+        raise RuntimeError(f"Expected all tensors to be on the same device, got {v.device} and {t.device}")
+    if v.dtype != t.dtype:
+        raise RuntimeError(f"expected video and text features of the same dtype, got {v.dtype} and {t.dtype}")
+    if v.dtype not in _DTYPE_CODE and v.dtype != torch.float64:
+        raise RuntimeError(f"unsupported feature dtype {v.dtype}")
+
+
+def _rowmajor(x):
+    return x if (x.stride(1) == 1 and x.stride(0) >= x.shape[1]) else x.contiguous()
+
+
+class _CrossCLRFunction(torch.autograd.Function):
+    """forward = pack -> [all-gather] -> fwd stats -> [all-gather] -> finalize; backward = bwd."""
+
+    @staticmethod
+    def forward(ctx, video, text, temperature, negative_weight, path, group, grad_scale):
+        lib = N.load()
+        _check_inputs(video, text)
+        in_dtype = video.dtype
+        if in_dtype == torch.float64:          # kernels compute in fp32; the reference's f64 inputs are down-cast
+            video, text = video.float(), text.float()
+        v, t = _rowmajor(video.detach()), _rowmajor(text.detach())
+        B, D = v.shape
+        dev = v.device
+        world, rank = 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        prob = N.Problem(2 * world, B, D, 2 * rank * B, 2 * B, float(temperature), float(negative_weight))
+        with torch.cuda.device(dev):
+            code = lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[v.dtype], 1 if path == "simt" else 0)
+            if code < 0:
+                N.check(code, "crossclr_choose_path")
+            if path == "tc" and code != N.PATH_TC:
+                raise RuntimeError(f"tensor-core path needs B % 128 == 0 and D % 64 == 0 (got B={B}, D={D})")
+            fdt = lib.crossclr_feature_dtype(code)
+            st = _stream()
+            rows = 2 * world * B
+            feat_all = torch.empty((2 * world, B, D), dtype=_FEAT_TORCH[fdt], device=dev)
+            feat_loc = feat_all[2 * rank:2 * rank + 2]
+            rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
+            N.check(lib.crossclr_pack(_ptr(v), _DTYPE_CODE[v.dtype], v.stride(0), B, D, _ptr(feat_loc[0]), fdt,
+                                      _ptr(rnorm), st), "crossclr_pack(video)")
+            N.check(lib.crossclr_pack(_ptr(t), _DTYPE_CODE[t.dtype], t.stride(0), B, D, _ptr(feat_loc[1]), fdt,
+                                      _ptr(rnorm[B:]), st), "crossclr_pack(text)")
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1).clone(), group=group)
+            stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+            N.check(lib.crossclr_fwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(stats), None, 0, st), "crossclr_fwd")
+            if world > 1:
+                import torch.distributed as dist
+                own = stats[2 * rank * B:2 * (rank + 1) * B].reshape(-1).clone()
+                dist.all_gather_into_tensor(stats.view(-1), own, group=group)
+            coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+            scal = torch.empty(4, dtype=torch.float32, device=dev)
+            loss = torch.empty((), dtype=torch.float64, device=dev)
+            N.check(lib.crossclr_finalize(ctypes.byref(prob), _ptr(stats), _ptr(coef), _ptr(loss), _ptr(scal), st),
+                    "crossclr_finalize")
+        ctx.save_for_backward(feat_all, rnorm, coef, scal)
+        ctx.prob, ctx.code, ctx.in_dtype, ctx.grad_scale = prob, code, in_dtype, float(grad_scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = N.load()
+        feat_all, rnorm, coef, scal = ctx.saved_tensors
+        prob = ctx.prob
+        B, D = prob.bseg, prob.dim
+        dev = feat_all.device
+        out_dtype = torch.float32 if ctx.in_dtype == torch.float64 else ctx.in_dtype
+        with torch.cuda.device(dev):
+            go = grad_out.detach().to(device=dev, dtype=torch.float64).contiguous()
+            dv = torch.empty((B, D), dtype=out_dtype, device=dev)
+            dt = torch.empty((B, D), dtype=out_dtype, device=dev)
+            ws_bytes = int(lib.crossclr_workspace_bytes(ctypes.byref(prob), ctx.code))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            N.check(lib.crossclr_bwd(ctypes.byref(prob), ctx.code, _ptr(feat_all), _ptr(rnorm), _ptr(coef), _ptr(scal),
+                                     _ptr(go), ctx.grad_scale, _ptr(dv), D, _ptr(dt), D, _DTYPE_CODE[out_dtype],
+                                     _ptr(ws), ws_bytes, _stream()), "crossclr_bwd")
+        if ctx.in_dtype == torch.float64:
+            dv, dt = dv.double(), dt.double()
+        return dv, dt, None, None, None, None, None
+
+
+class CrossCLR_onlyIntraModality(nn.Module):
+    """CrossCLR Loss between 2 groups of embeddings - Only Intra Modality alignment.
+
+    Drop-in for the reference module of the same name (`trainer/loss.py:44-114`).  Keyword-only extensions
+    (defaults reproduce the reference's single-device behaviour):
+      process_group  torch.distributed group whose ranks each hold a row shard of the global batch
+      grad_scale     multiplies the returned gradients (set to world_size under DDP's gradient averaging)
+      path           "auto" | "tc" (tcgen05 kernels) | "simt" (exact-fp32 CUDA-core kernels)
+    """
+
+    def __init__(self, temperature=0.03, negative_weight=0.8, logger=None, *, process_group=None, grad_scale=1.0,
+                 path="auto"):
+        super().__init__()
+        self.logit_scale = nn.Parameter(torch.ones([]))            # trainer/loss.py:52 (registered, never used)
+        self.criterion = torch.nn.CrossEntropyLoss(reduction='none')  # :53 (registered, never used)
+        self.temperature = temperature                             # :54
+        self.logger = logger                                       # :55
+        self.negative_w = negative_weight                          # :56 (attribute name differs from the arg)
+        if path not in _PATH_CODE:
+            raise ValueError(f"path must be one of {sorted(_PATH_CODE)}")
+        self.process_group = process_group
+        self.grad_scale = grad_scale
+        self.path = path
+
+    def forward(self, video_features, text_features):
+        """
+        Inputs shape (batch, embed_dim)
+        Args:
+            video_features: Video embeddings (batch, embed_dim)
+            text_features: Text embeddings (batch, embed_dim)
+        Returns: 0-dim float64 loss (trainer/loss.py:114)
+        """
+        # temperature / negative_w are read per call (trainer/loss.py:90-93, :99-100)
+        return _CrossCLRFunction.apply(video_features, text_features, self.temperature, self.negative_w, self.path,
+                                       self.process_group, self.grad_scale)
+
+
+def crossclr_loss(video_features, text_features, temperature=0.03, negative_weight=0.8, *, process_group=None,
+                  grad_scale=1.0, path="auto"):
+    """Functional form of `CrossCLR_onlyIntraModality.forward`."""
+    return _CrossCLRFunction.apply(video_features, text_features, temperature, negative_weight, path, process_group,
+                                   grad_scale)

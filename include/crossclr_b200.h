@@ -1,0 +1,162 @@
+/*
+ * crossclr_b200.h -- C ABI of the B200-native CrossCLR criterion (libcrossclr_b200.so).
+ *
+ * The reference (amazon-science/crossmodal-contrastive-learning) has no FFI layer: its boundary is the
+ * Python nn.Module `trainer/loss.py:44-114  CrossCLR_onlyIntraModality`.  The Python mirror of that
+ * module (crossmodal_contrastive_learning_b200/loss.py) keeps the module surface and calls the entry
+ * points below through ctypes.  Each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative CROSSCLR_E* code on failure; the message is
+ *     available from crossclr_last_error() (thread-local).
+ *   - all pointers are BORROWED DEVICE pointers (owned by the caller, e.g. torch's allocator) unless
+ *     a parameter says "host".  No allocation, no stream/device synchronisation and no host<->device
+ *     copies happen inside; `stream` is a cudaStream_t passed as void*.
+ *   - "stacked matrix": the R = nseg*bseg L2-normalised feature rows laid out as nseg segments of bseg rows,
+ *     segment s holding modality (s & 1) (0 = video, 1 = text) of rank (s >> 1); i.e. the layout an
+ *     all-gather of per-rank [2][bseg][dim] blocks produces.  One GPU: nseg = 2 (V rows then T rows).
+ *     Stacked row g belongs to sample (g / bseg >> 1) * bseg + g % bseg.
+ *   - the calling rank owns stacked rows [row_begin, row_begin + row_count).
+ */
+#ifndef CROSSCLR_B200_H_
+#define CROSSCLR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CROSSCLR_API __attribute__((visibility("default")))
+#else
+#define CROSSCLR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CROSSCLR_VERSION 100          /* 0.1.0 */
+
+/* error codes */
+#define CROSSCLR_OK            0
+#define CROSSCLR_EINVAL       -1      /* bad argument / unsupported shape for the requested path   */
+#define CROSSCLR_ECUDA        -2      /* a CUDA runtime/driver call failed (see crossclr_last_error) */
+#define CROSSCLR_EWORKSPACE   -3      /* workspace too small                                          */
+#define CROSSCLR_EUNSUPPORTED -4      /* device is not sm_100                                         */
+
+/* element types */
+#define CROSSCLR_F32  0
+#define CROSSCLR_F16  1
+#define CROSSCLR_BF16 2
+
+/* kernel families ("path") */
+#define CROSSCLR_PATH_AUTO 0          /* tensor-core path when the shape allows it, else SIMT        */
+#define CROSSCLR_PATH_SIMT 1          /* fp32 CUDA-core kernels, any B / D, fp32 stacked features     */
+#define CROSSCLR_PATH_TC   2          /* tcgen05 + TMA + TMEM kernels, fp16 stacked features,
+                                         requires bseg % 128 == 0 and dim % 64 == 0                   */
+
+typedef struct crossclr_problem {
+  int32_t nseg;             /* segments in the stacked matrix = 2 * world_size                        */
+  int32_t bseg;             /* rows per segment = local batch                                         */
+  int32_t dim;              /* embedding dim D                                                        */
+  int32_t row_begin;        /* first stacked row owned by the caller = 2 * rank * bseg                */
+  int32_t row_count;        /* owned rows = 2 * bseg                                                  */
+  float   temperature;      /* tau      (trainer/loss.py:54, read per call at :90-93)                 */
+  float   negative_weight;  /* w        (trainer/loss.py:56, read per call at :99-100)                */
+} crossclr_problem_t;
+
+CROSSCLR_API int         crossclr_version(void);
+CROSSCLR_API const char* crossclr_last_error(void);
+
+/* 1 if `device` can run this library (compute capability 10.x), 0 otherwise, <0 on error. */
+CROSSCLR_API int crossclr_device_supported(int device);
+
+/* Resolve CROSSCLR_PATH_AUTO for a problem: CROSSCLR_PATH_TC when the shape allows it (the fp16
+ * normalised operand keeps gradients within ~2e-4 of the fp32 reference), else CROSSCLR_PATH_SIMT.
+ * `in_dtype` / `exact` are hints: exact != 0 forces the fp32 SIMT path. */
+CROSSCLR_API int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact);
+
+/* Stacked-feature element type a path consumes: SIMT -> CROSSCLR_F32, TC -> CROSSCLR_F16. */
+CROSSCLR_API int crossclr_feature_dtype(int path);
+
+/* Bytes of scratch crossclr_bwd needs for this problem and path (crossclr_fwd needs none). */
+CROSSCLR_API size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path);
+
+/*
+ * L2-normalise one modality block `x` ([rows][dim], element stride 1, row stride `x_row_stride`
+ * elements, dtype `in_dtype`) into its segment of the stacked matrix: `feat_out` points at the first
+ * row of that segment (dtype `feat_dtype`, row stride dim) and receives x / max(||x||_2, 1e-12);
+ * `rnorm_out[rows]` receives 1 / max(||x||_2, 1e-12) (kept by the caller for the backward).
+ * Replaces: trainer/loss.py:79-80 (F.normalize x2).
+ */
+CROSSCLR_API int crossclr_pack(const void* x, int in_dtype, int64_t x_row_stride, int32_t rows, int32_t dim,
+                  void* feat_out, int feat_dtype, float* rnorm_out, void* stream);
+
+/*
+ * Forward statistics of the owned rows.  For every owned stacked row g writes
+ *   stats[2g+0] = X_g    = sum over the 2B-1 non-positive logits of 2^(logit*log2e - shift)
+ *                          (includes the intra-modal diagonal, which is logit 0: loss.py:65,96-97)
+ *   stats[2g+1] = xpos_g = positive logit * log2e - shift
+ * with shift = crossclr_shift(p).  `feat` is the full stacked matrix [nseg*bseg][dim] of normalised
+ * rows; `stats` has room for [nseg*bseg][2] floats (only the owned rows are written).
+ * Replaces: trainer/loss.py:83-100 (4 GEMMs, /tau, mask, weight, concat) and the row reductions of
+ * :59-60; no B x B intermediate is written to memory.
+ */
+CROSSCLR_API int crossclr_fwd(const crossclr_problem_t* p, int path, const void* feat, float* stats, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/*
+ * Loss and backward coefficients from the (all-gathered) statistics of ALL nseg*bseg rows:
+ *   loss_out[0] (double) = (1/2B) sum_g log1p(X_g * 2^-xpos_g)          trainer/loss.py:60,:111-114
+ *   coef[2g+0] = 1/Z_g, coef[2g+1] = X_g/Z_g   with Z_g = X_g + 2^xpos_g (shifted units)
+ *   scal[0] = sigma (power-of-two scale applied to the fp16 probability tiles), scal[1] = 1/sigma,
+ *   scal[2] = max_g X_g/Z_g, scal[3] reserved
+ */
+CROSSCLR_API int crossclr_finalize(const crossclr_problem_t* p, const float* stats, float* coef, double* loss_out,
+                      float* scal, void* stream);
+
+/*
+ * Gradients of loss * (*grad_out) * grad_scale w.r.t. the caller's own video/text rows.
+ * `rnorm_owned[row_count]`: reciprocal norms of the owned rows (video rows then text rows) from
+ * crossclr_pack.  `grad_out` is a DEVICE pointer to the upstream scalar gradient (double) or NULL for
+ * 1.0.  dv/dt: [bseg][dim] outputs, dtype `out_dtype`, row strides in elements.
+ * Replaces: the autograd backward of trainer/loss.py:79-114 (98 aten ops, 8 mm).
+ */
+CROSSCLR_API int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned,
+                 const float* coef, const float* scal, const double* grad_out, float grad_scale, void* dv,
+                 int64_t dv_row_stride, void* dt, int64_t dt_row_stride, int out_dtype, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+/* The constant log2-domain shift used by fwd/bwd for this problem: max(0, log2e*max(1,|w|)/tau - 96). */
+CROSSCLR_API float crossclr_shift(const crossclr_problem_t* p);
+
+/* Number of kernel launches issued so far by this library in this process (bench.py's gpu_launches). */
+CROSSCLR_API int64_t crossclr_launch_count(void);
+
+/*
+ * Per-kernel device timing (bench.py's roofline leg).  While enabled, every kernel launch of this library is
+ * bracketed by cudaEventRecord on its own stream.  crossclr_timing_read synchronises the recorded events,
+ * returns the summed duration / launch count of kernel family `kernel` (CROSSCLR_K_*) since the last read of
+ * that family and forgets them.  Disabled by default (no events, no overhead).
+ */
+#define CROSSCLR_K_PACK     0
+#define CROSSCLR_K_FWD      1
+#define CROSSCLR_K_FINALIZE 2
+#define CROSSCLR_K_BWD      3
+#define CROSSCLR_K_GRADFIN  4
+#define CROSSCLR_K_COUNT    5
+CROSSCLR_API int crossclr_timing_enable(int on);
+CROSSCLR_API int crossclr_timing_read(int kernel, double* total_ms, int64_t* launches);
+
+/*
+ * Hardware self-test of the tcgen05/TMA building blocks (descriptor encodings, TMEM layouts).
+ * `variant` selects the block under test (0: K-major x K-major, 1: swizzled thread-written A x MN-major
+ * B with b given as [k][n], n == 64, 2: A from TMEM); host buffers hold fp16 bit patterns: a [128][k],
+ * b [n][k] (variant 1: [k][n]), out [128][n] float.  Synchronous (allocates, copies, syncs); tests only.
+ */
+CROSSCLR_API int crossclr_selftest(int variant, const uint16_t* a_host, const uint16_t* b_host, float* out_host,
+                      int32_t n, int32_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROSSCLR_B200_H_ */

@@ -1,0 +1,256 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the module mirror) against
+  * the reference-generated golden vectors in tests/golden/ (outputs of the unmodified reference),
+  * the CPU oracle (oracle/crossclr_oracle.py) on the same seeded inputs,
+  * closed-form known-answer cases and size-independent properties at BASELINE.json sizes.
+
+Tolerances (BASELINE.json north_star: 1e-3 relative fp32):
+    |L - L_ref| <= 1e-3 |L_ref| + 1e-7,   ||g - g_ref||_F <= 1e-3 ||g_ref||_F,   max|g - g_ref| <= 1e-3 max|g_ref|
+The exact-fp32 SIMT path is held to a 20x tighter bar.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+TOL_SIMT = 5e-5
+
+
+def _mod():
+    import crossmodal_contrastive_learning_b200 as M
+    return M
+
+
+def run_gpu(v, t, tau, w, path="auto", dtype=torch.float32, grad_out=None):
+    M = _mod()
+    vd = torch.as_tensor(v).to("cuda", dtype).requires_grad_()
+    td = torch.as_tensor(t).to("cuda", dtype).requires_grad_()
+    crit = M.CrossCLR_onlyIntraModality(tau, w, path=path)
+    loss = crit(vd, td)
+    assert loss.dtype == torch.float64 and loss.dim() == 0 and loss.is_cuda
+    if grad_out is None:
+        loss.backward()
+    else:
+        (loss * grad_out).backward()
+    assert vd.grad.dtype == dtype and td.grad.dtype == dtype
+    return loss.item(), vd.grad.double().cpu().numpy(), td.grad.double().cpu().numpy()
+
+
+def check(loss, dv, dt, rloss, rdv, rdt, tol):
+    assert abs(loss - rloss) <= tol * abs(rloss) + 1e-7, (loss, rloss)
+    for g, r, name in ((dv, rdv, "dv"), (dt, rdt, "dt")):
+        rel = np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-300)
+        mx = np.abs(g - r).max() / max(np.abs(r).max(), 1e-300)
+        assert rel <= tol, (name, "rel-norm", rel)
+        assert mx <= tol, (name, "max", mx)
+
+
+FULL = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+              if not os.path.basename(p).startswith(("kat_", "c1_")))
+TC_OK = [p for p in FULL if (lambda g: g["v"].shape[0] % 128 == 0 and g["v"].shape[1] % 64 == 0)(np.load(p))]
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 / TMA building blocks
+@pytest.mark.parametrize("variant,n,k", [(0, 128, 64), (0, 128, 256), (0, 64, 128), (1, 64, 128), (1, 64, 64),
+                                         (2, 128, 128)])
+def test_tc_selftest(variant, n, k):
+    import ctypes
+    lib = _mod().load_native()
+    rng = np.random.default_rng(variant * 100 + n + k)
+    a = rng.standard_normal((128, k)).astype(np.float16)
+    b = (rng.standard_normal((k, n)) if variant == 1 else rng.standard_normal((n, k))).astype(np.float16)
+    out = np.zeros((128, n), dtype=np.float32)
+    rc = lib.crossclr_selftest(variant, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                               out.ctypes.data_as(ctypes.c_void_p), n, k)
+    assert rc == 0, lib.crossclr_last_error()
+    ref = a.astype(np.float32) @ (b.astype(np.float32) if variant == 1 else b.astype(np.float32).T)
+    err = np.abs(out - ref).max()
+    assert err < 1e-2, (variant, n, k, err)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors produced by the unmodified reference
+@pytest.mark.parametrize("path", FULL, ids=[os.path.basename(p)[:-4] for p in FULL])
+def test_simt_matches_reference_goldens(path):
+    g = np.load(path)
+    loss, dv, dt = run_gpu(g["v"], g["t"], float(g["tau"]), float(g["w"]), path="simt")
+    if "zero_row" in path:
+        # the zero row's gradient (~1e13, through the eps clamp) dominates every norm: compare rows separately
+        z = 3
+        keep = np.arange(len(dv)) != z
+        check(loss, dv[keep], dt, float(g["loss"]), g["dv"][keep], g["dt"], TOL_SIMT)
+        assert np.linalg.norm(dv[z] - g["dv"][z]) <= 1e-3 * np.linalg.norm(g["dv"][z])
+    else:
+        check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL_SIMT)
+
+
+@pytest.mark.parametrize("path", TC_OK, ids=[os.path.basename(p)[:-4] for p in TC_OK])
+def test_tc_matches_reference_goldens(path):
+    g = np.load(path)
+    loss, dv, dt = run_gpu(g["v"], g["t"], float(g["tau"]), float(g["w"]), path="tc")
+    check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL)
+
+
+@pytest.mark.parametrize("path", ["simt", "tc"])
+def test_c1_config_golden(path):
+    """BASELINE.json configs[0]: B=256 D=512 fp32 seed 0."""
+    g = np.load(os.path.join(GOLDEN, "c1_b256_d512_seed0.npz"))
+    loss, dv, dt = run_gpu(g["v"], g["t"], 0.03, 0.8, path=path)
+    tol = TOL_SIMT if path == "simt" else TOL
+    assert abs(loss - 7.00737577904705) <= tol * 7.0074
+    assert abs(np.linalg.norm(dv) - float(g["dv_norm"])) <= tol * float(g["dv_norm"])
+    assert abs(np.linalg.norm(dt) - float(g["dt_norm"])) <= tol * float(g["dt_norm"])
+    rows = g["rows"]
+    check(loss, dv[rows], dt[rows], float(g["loss"]), g["dv_rows"].astype(np.float64),
+          g["dt_rows"].astype(np.float64), tol)
+
+
+def test_known_answers():
+    from oracle import crossclr_oracle as O
+    ref = np.load(os.path.join(GOLDEN, "kat_reference_values.npz"))
+    cases = [(O.kat_identity(2, 1.0, 0.8), "identity_n2_tau1_w0.8"), (O.kat_identity(4, 0.5, 0.3), "identity_n4_tau0.5_w0.3"),
+             (O.kat_collinear(3, 1.0, 0.8), "collinear_n3_tau1_w0.8"), (O.kat_collinear(5, 0.5, 0.25), "collinear_n5_tau0.5_w0.25"),
+             (O.kat_antipodal(4, 0.5, 0.8), "antipodal_n4_tau0.5_w0.8")]
+    for (v, t, tau, w, expect), key in cases:
+        loss, dv, dt = run_gpu(v.astype(np.float32), t.astype(np.float32), tau, w, path="simt")
+        assert abs(loss - expect) <= 1e-5 * abs(expect) + 1e-7, (key, loss, expect)
+        assert abs(loss - float(ref[key])) <= 1e-5 * abs(expect) + 1e-7
+    # KAT-4 gradient: v = t = I_2, tau = 1, w = .8 -> off-diagonal 0.9 / (e + 3), diagonal 0
+    _, dv, dt = run_gpu(np.eye(2, dtype=np.float32), np.eye(2, dtype=np.float32), 1.0, 0.8, path="simt")
+    g = 0.9 / (np.e + 3)
+    assert np.allclose(dv, [[0, g], [g, 0]], atol=1e-6) and np.allclose(dt, [[0, g], [g, 0]], atol=1e-6)
+    # converged regime: loss ~ 5e-14 must not collapse to 0 / nan (log1p form)
+    v, t, tau, w, expect = O.kat_identity(8, 0.03, 0.8)
+    loss, _, _ = run_gpu(v.astype(np.float32), t.astype(np.float32), tau, w, path="simt")
+    assert abs(loss - expect) <= 1e-3 * expect
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle on seeded inputs at sizes it finishes in seconds
+def _seeded(B, D, seed, aligned=0.0, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randn(B, D, generator=g)
+    t = torch.randn(B, D, generator=g)
+    if aligned:
+        t = v + aligned * t
+    return v.to(dtype).float().numpy(), t.to(dtype).float().numpy()     # bf16-representable fp32
+
+
+@pytest.mark.parametrize("B,D,aligned,path,dtype", [
+    (1024, 512, 0.0, "tc", torch.bfloat16), (1024, 512, 3.0, "tc", torch.bfloat16), (1024, 512, 0.5, "tc", torch.bfloat16),
+    (512, 1024, 0.0, "tc", torch.bfloat16), (384, 320, 1.0, "tc", torch.float16), (640, 768, 0.0, "tc", torch.float32),
+    (1000, 200, 0.0, "simt", torch.float32), (333, 77, 2.0, "auto", torch.bfloat16), (2048, 256, 0.0, "auto", torch.bfloat16),
+])
+def test_against_oracle(B, D, aligned, path, dtype):
+    from oracle import crossclr_oracle as O
+    v, t = _seeded(B, D, 100 + B + D, aligned, dtype if dtype != torch.float32 else torch.bfloat16)
+    rloss, rdv, rdt = O.loss_and_grads(v, t, 0.03, 0.8)
+    loss, dv, dt = run_gpu(v, t, 0.03, 0.8, path=path, dtype=dtype)
+    # low-precision outputs: the gradient is rounded to the input dtype on the way out, as in the reference
+    tol = TOL if dtype == torch.float32 else 5e-3 if dtype == torch.bfloat16 else 1.5e-3
+    check(loss, dv, dt, rloss, rdv, rdt, tol)
+
+
+def test_c2_config_against_oracle():
+    """BASELINE.json configs[1]: B=4096 D=512 bf16 features, full-matrix check (fp32 grads out for a tight bar)."""
+    from oracle import crossclr_oracle as O
+    v, t = _seeded(4096, 512, 0)
+    rloss, rdv, rdt = O.loss_and_grads(v, t, 0.03, 0.8)
+    loss, dv, dt = run_gpu(v, t, 0.03, 0.8, path="tc", dtype=torch.float32)
+    check(loss, dv, dt, rloss, rdv, rdt, TOL)
+    lb, dvb, dtb = run_gpu(v, t, 0.03, 0.8, path="tc", dtype=torch.bfloat16)
+    assert abs(lb - rloss) <= TOL * abs(rloss)
+    assert np.linalg.norm(dvb - rdv) <= 5e-3 * np.linalg.norm(rdv)     # bf16 output rounding (2^-9 per element)
+
+
+def test_c3_config_sampled_rows_and_properties():
+    """BASELINE.json configs[2]: B=16384 D=1024 bf16.  Loss vs the row-blocked oracle, gradients on sampled
+    rows, plus size-independent properties (symmetry, scale invariance, dv orthogonal to v)."""
+    from oracle import crossclr_oracle as O
+    B, D = 16384, 1024
+    v, t = _seeded(B, D, 7)
+    rows = np.arange(0, B, 1024) + 3
+    rloss, rdv, rdt = O.loss_and_grads(v, t, 0.03, 0.8, rows=rows, row_block=2048)
+    loss, dv, dt = run_gpu(v, t, 0.03, 0.8, path="tc", dtype=torch.float32)
+    check(loss, dv[rows], dt[rows], rloss, rdv, rdt, TOL)
+    # L(v, t) == L(t, v) and the gradients swap
+    loss2, dv2, dt2 = run_gpu(t, v, 0.03, 0.8, path="tc", dtype=torch.float32)
+    assert abs(loss - loss2) <= 1e-6 * abs(loss)
+    assert np.linalg.norm(dv2 - dt) <= 1e-4 * np.linalg.norm(dt)
+    # scale invariance: L(4v, t) == L(v, t), dv scales by 1/4; dv is orthogonal to v
+    loss3, dv3, _ = run_gpu(4.0 * v, t, 0.03, 0.8, path="tc", dtype=torch.float32)
+    assert abs(loss - loss3) <= 1e-6 * abs(loss)
+    assert np.linalg.norm(4.0 * dv3 - dv) <= 1e-4 * np.linalg.norm(dv)
+    cosang = np.abs((dv * v).sum(1)) / (np.linalg.norm(dv, axis=1) * np.linalg.norm(v, axis=1))
+    assert cosang.max() < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# module surface / error behaviour
+def test_module_surface_and_errors():
+    M = _mod()
+    from trainer.loss import CrossCLR_onlyIntraModality as FromTrainer
+    assert FromTrainer is M.CrossCLR_onlyIntraModality
+    crit = M.CrossCLR_onlyIntraModality(temperature=0.03, negative_weight=0.8).cuda()
+    assert list(crit.state_dict().keys()) == ["logit_scale"]
+    assert crit.temperature == 0.03 and crit.negative_w == 0.8 and crit.logger is None
+    v = torch.randn(64, 32, device="cuda", requires_grad=True)
+    t = torch.randn(64, 32, device="cuda", requires_grad=True)
+    loss = crit(v, t)
+    loss.backward()
+    assert crit.logit_scale.grad is None
+    with torch.no_grad():
+        assert not crit(v, t).requires_grad
+    for bad in [(torch.randn(64, 32, device="cuda"), torch.randn(32, 32, device="cuda")),
+                (torch.randn(64, 32, device="cuda"), torch.randn(64, 16, device="cuda")),
+                (torch.randn(2, 64, 32, device="cuda"), torch.randn(2, 64, 32, device="cuda")),
+                (torch.randn(64, 32), torch.randn(64, 32))]:
+        with pytest.raises(RuntimeError):
+            crit(*bad)
+    # attributes are read per call
+    l1 = crit(v, t).item()
+    crit.temperature = 0.1
+    assert abs(crit(v, t).item() - l1) > 1e-3
+    # non-contiguous inputs, upstream gradient scaling, float64 inputs
+    crit.temperature = 0.03
+    big = torch.randn(64, 64, device="cuda")
+    vn = big[:, ::2].detach().requires_grad_()
+    l2 = crit(vn, t)
+    (l2 * 3.0).backward()
+    vc = big[:, ::2].contiguous().requires_grad_()
+    crit(vc, t).backward()
+    assert torch.allclose(vn.grad, 3.0 * vc.grad, rtol=1e-5, atol=1e-9)
+    v64 = v.detach().double().requires_grad_()
+    l3 = crit(v64, t.detach().double())
+    l3.backward()
+    assert v64.grad.dtype == torch.float64 and abs(l3.item() - l1) <= 1e-5 * abs(l1)
+
+
+def test_b1_and_w0_and_small_tau():
+    for name in ("b1_d16", "w0_b64_d32", "tau01_b64_d64"):
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        loss, dv, dt = run_gpu(g["v"], g["t"], float(g["tau"]), float(g["w"]))
+        check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL_SIMT)
+    # tau = 0.005 (beyond the fp32 exp range without the constant shift): compare with the float64 oracle
+    from oracle import crossclr_oracle as O
+    v, t = _seeded(256, 128, 5, aligned=2.0)
+    for tau in (0.005,):
+        rloss, rdv, rdt = O.loss_and_grads(v, t, tau, 0.8)
+        for path in ("simt", "tc"):
+            loss, dv, dt = run_gpu(v, t, tau, 0.8, path=path)
+            check(loss, dv, dt, rloss, rdv, rdt, TOL)
+
+
+def test_launch_counter_moves():
+    M = _mod()
+    n0 = M.launch_count()
+    v, t = _seeded(128, 64, 1)
+    run_gpu(v, t, 0.03, 0.8)
+    assert M.launch_count() - n0 >= 5
