@@ -28,6 +28,7 @@ extern std::atomic<int64_t> g_launches;
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \
     if (_e != cudaSuccess) {                                                                       \
+      (void)cudaGetLastError(); /* clear the non-sticky error so the next launch check is not blamed */ \
       ::crossclr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
       return CROSSCLR_ECUDA;                                                                       \
     }                                                                                              \

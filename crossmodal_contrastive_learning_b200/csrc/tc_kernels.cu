@@ -26,18 +26,21 @@ using namespace ptx;
 namespace {
 
 constexpr int TM = 128;                 // tile rows (TMEM lanes)
-constexpr int TN = 128;                 // similarity tile columns
 constexpr int KC = 64;                  // K chunk: 64 fp16 = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = TM * KC * 2;   // 16 KiB: a [128 rows][64 elems] box
 constexpr int MAX_RES_CHUNKS = 8;       // A row block stays resident for D <= 512
+constexpr int FWD_TN = 256;             // forward similarity tile columns (one N=256 MMA)
+constexpr int BWD_TN = 128;             // backward similarity / probability tile columns
 constexpr int SLAB = 256;               // dFhat columns per backward work item (TMEM columns)
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_SLOTS = 12;
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
 
-constexpr uint32_t kIdescS = make_idesc_f16(128, TN, 0, 0, 0, 0);     // S = A(K-major) * B(K-major)^T
-constexpr uint32_t kIdescG = make_idesc_f16(128, 64, 0, 0, 0, 1);     // dF += P(K-major) * F_J(MN-major)
+constexpr uint32_t kIdescS256 = make_idesc_f16(128, 256, 0, 0, 0, 0);   // S = A(K-major) * B(K-major)^T, N = 256
+constexpr uint32_t kIdescS128 = make_idesc_f16(128, 128, 0, 0, 0, 0);   // ... N = 128
+constexpr uint32_t kIdescG128 = make_idesc_f16(128, 128, 0, 0, 0, 1);   // dF += P(K-major) * F_J(MN-major), N = 128
+constexpr uint32_t kIdescG64 = make_idesc_f16(128, 64, 0, 0, 0, 1);     // ... N = 64 (odd chunk counts)
 
 __device__ __forceinline__ uint64_t kmajor_desc(uint32_t addr) { return make_smem_desc_sw128(addr, 1024, 0); }
 
@@ -51,17 +54,42 @@ struct Ring {
   }
 };
 
-// Issue the 4 K=16 MMAs of one 64-wide K chunk into a 128x128 accumulator.
-__device__ __forceinline__ void issue_s_chunk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, bool first_chunk) {
+// The 4 K=16 MMAs of one 64-wide K chunk into a 128 x N accumulator (A, B K-major 128-byte-swizzled boxes).
+__device__ __forceinline__ void issue_s_chunk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+                                              bool first_chunk) {
   const uint64_t ad = kmajor_desc(a_addr), bd = kmajor_desc(b_addr);
 #pragma unroll
   for (int k = 0; k < KC / 16; ++k)
-    umma_ss(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdescS, (first_chunk && k == 0) ? 0u : 1u);
+    umma_ss(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (first_chunk && k == 0) ? 0u : 1u);
+}
+
+// segment bookkeeping of a 128-aligned block of stacked rows starting at `r0`
+struct BlockSeg {
+  int mod;      // modality of the block (0 video / 1 text)
+  int samp0;    // sample index of its first row
+};
+__device__ __forceinline__ BlockSeg block_seg(int r0, int bseg) {
+  const int seg = r0 / bseg;
+  return BlockSeg{seg & 1, (seg >> 1) * bseg + (r0 - seg * bseg)};
 }
 
 // ================================================================================================
-// Forward
+// Forward.  Tile = 128 rows x 256 columns of the stacked Gram matrix; persistent, one CTA per SM.
+//   warp 0  TMA producer (all lanes run the loop, one elected lane issues)
+//   warp 1  MMA issuer   (same)
+//   warp 2  TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld (software pipelined) -> x = acc*k - shift -> ex2 -> thread-local row sums
 // ================================================================================================
+__device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float k, float nshift, float (&rs)[4]) {
+#pragma unroll
+  for (int q = 0; q < 32; q += 4) {
+    rs[0] += fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift));
+    rs[1] += fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift));
+    rs[2] += fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift));
+    rs[3] += fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift));
+  }
+}
+
 template <bool kResident>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __restrict__ stats, int tiles_total,
@@ -70,11 +98,11 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
   const uint32_t ring_base = a_region + (kResident ? nk * CHUNK_BYTES : 0);
-  const uint32_t stage_bytes = kResident ? CHUNK_BYTES : 2 * CHUNK_BYTES;
+  const uint32_t stage_bytes = (kResident ? 0 : CHUNK_BYTES) + 2 * CHUNK_BYTES;   // [A chunk] + B chunk of 256 rows
   const uint32_t bar_base = ring_base + num_stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  const uint32_t a_full = bar_base + 8u * (2 * MAX_STAGES);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
+  const uint32_t a_full = bar_base + 8u * (2 * MAX_SLOTS);
   const uint32_t a_empty = a_full + 8;
   auto tfull_bar = [&](int b) { return a_full + 16u + 8u * b; };
   auto tempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
@@ -82,8 +110,8 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long t_begin = (long long)blockIdx.x * tiles_total / gridDim.x;
-  const long long t_end = (long long)(blockIdx.x + 1) * tiles_total / gridDim.x;
+  const int t_begin = (int)((long long)blockIdx.x * tiles_total / gridDim.x);
+  const int t_end = (int)((long long)(blockIdx.x + 1) * tiles_total / gridDim.x);
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
   if (warp == 1 && lane == 0) {
@@ -92,173 +120,188 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      Ring ring(num_stages);
-      int cur_ib = -1;
-      uint32_t a_cnt = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int ib = (int)(t / ncb), jb = (int)(t % ncb);
-        const int row0 = g.row_begin + ib * TM, col0 = jb * TN;
-        if (kResident && ib != cur_ib) {
-          mbar_wait(a_empty, (a_cnt & 1) ^ 1);
+    Ring ring(num_stages);
+    int cur_ib = -1;
+    uint32_t a_cnt = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int ib = t / ncb, jb = t - ib * ncb;
+      const int row0 = g.row_begin + ib * TM, col0 = jb * FWD_TN;
+      if (kResident && ib != cur_ib) {
+        mbar_wait(a_empty, (a_cnt & 1) ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(a_full, nk * CHUNK_BYTES);
           for (int kc = 0; kc < nk; ++kc) tma_load_2d(a_region + kc * CHUNK_BYTES, &tmap, a_full, kc * KC, row0);
-          cur_ib = ib; ++a_cnt;
         }
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-          const uint32_t st = ring_base + ring.stage * stage_bytes;
-          if (kResident) {
-            mbar_arrive_expect_tx(full_bar(ring.stage), CHUNK_BYTES);
-            tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, col0);
-          } else {
-            mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
-            tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0);
-            tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, col0);
-          }
-          ring.advance();
+        __syncwarp();
+        cur_ib = ib; ++a_cnt;
+      }
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+        if (elect_one()) {
+          uint32_t st = ring_base + ring.stage * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(ring.stage), stage_bytes);
+          if (!kResident) { tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0); st += CHUNK_BYTES; }
+          tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, col0);
+          tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, col0 + TM);
         }
+        __syncwarp();
+        ring.advance();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      Ring ring(num_stages);
-      int cur_ib = -1;
-      uint32_t a_cnt = 0;
-      uint32_t iter = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++iter) {
-        const int ib = (int)(t / ncb);
-        const uint32_t buf = iter & 1;
-        mbar_wait(tempty_bar(buf), ((iter >> 1) & 1) ^ 1);
+    Ring ring(num_stages);
+    int cur_ib = -1;
+    uint32_t a_cnt = 0, iter = 0;
+    for (int t = t_begin; t < t_end; ++t, ++iter) {
+      const int ib = t / ncb;
+      const uint32_t buf = iter & 1;
+      mbar_wait(tempty_bar(buf), ((iter >> 1) & 1) ^ 1);
+      if (kResident && ib != cur_ib) {
+        mbar_wait(a_full, a_cnt & 1);
+        cur_ib = ib; ++a_cnt;
+      }
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * FWD_TN;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(full_bar(ring.stage), ring.phase);
         tc_fence_after();
-        if (kResident && ib != cur_ib) {
-          mbar_wait(a_full, a_cnt & 1);
-          tc_fence_after();
-          cur_ib = ib; ++a_cnt;
-        }
-        const uint32_t tmem_d = tmem_base + buf * TN;
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(full_bar(ring.stage), ring.phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t st = ring_base + ring.stage * stage_bytes;
           const uint32_t a_addr = kResident ? a_region + kc * CHUNK_BYTES : st;
           const uint32_t b_addr = kResident ? st : st + CHUNK_BYTES;
-          issue_s_chunk(tmem_d, a_addr, b_addr, kc == 0);
+          issue_s_chunk(tmem_d, a_addr, b_addr, kIdescS256, kc == 0);
           umma_commit(empty_bar(ring.stage));
-          ring.advance();
         }
-        umma_commit(tfull_bar(buf));
-        if (kResident) {
-          const bool last_of_block = (t + 1 == t_end) || ((int)((t + 1) / ncb) != ib);
-          if (last_of_block) umma_commit(a_empty);
-        }
+        __syncwarp();
+        ring.advance();
       }
+      const bool last_of_block = (t + 1 == t_end) || ((t + 1) / ncb != ib);
+      if (elect_one()) {
+        umma_commit(tfull_bar(buf));
+        if (kResident && last_of_block) umma_commit(a_empty);
+      }
+      __syncwarp();
     }
   } else if (warp >= EPI_WARP0) {
     const int ew = warp - EPI_WARP0;
     const int r = ew * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-    int cur_ib = -1, gi = 0, mod_i = 0, sb_i = 0;
-    float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+    int cur_ib = -1, gi = 0;
+    BlockSeg bi{0, 0};
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t iter = 0;
     const float diag_term = fast_exp2(-g.shift);
-    for (long long t = t_begin; t < t_end; ++t, ++iter) {
-      const int ib = (int)(t / ncb), jb = (int)(t % ncb);
+    const float nshift = -g.shift;
+    for (int t = t_begin; t < t_end; ++t, ++iter) {
+      const int ib = t / ncb, jb = t - ib * ncb;
       if (ib != cur_ib) {
-        if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs0 + rs1) + (rs2 + rs3));
-        rs0 = rs1 = rs2 = rs3 = 0.f;
+        if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
+        rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
         cur_ib = ib;
         const int row0 = g.row_begin + ib * TM;
         gi = row0 + r;
-        const int seg = row0 / g.bseg;
-        mod_i = seg & 1;
-        sb_i = (seg >> 1) * g.bseg + (row0 - seg * g.bseg);
+        bi = block_seg(row0, g.bseg);
       }
-      const int col0 = jb * TN;
-      const int segj = col0 / g.bseg;
-      const bool same_mod = ((segj & 1) == mod_i);
-      const int sb_j = (segj >> 1) * g.bseg + (col0 - segj * g.bseg);
-      const bool diag_tile = (sb_j == sb_i);
-      const float k = same_mod ? g.k_intra : g.k_inter;
-      const float nshift = -g.shift;
       const uint32_t buf = iter & 1;
+      const uint32_t tbase = lane_base + buf * FWD_TN;
       mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < TN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + buf * TN + c * 32, v);
-        tmem_ld_wait();
-        if (!diag_tile || (r >> 5) != c) {
+      uint32_t va[32], vb[32];
+      tmem_ld32(tbase, va);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            rs0 += fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift));
-            rs1 += fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift));
-            rs2 += fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift));
-            rs3 += fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift));
-          }
-        } else {
-          // this 32-column chunk holds the same-sample column (local column index == r)
+      for (int h = 0; h < 2; ++h) {                 // two 128-column halves, each inside one segment
+        const BlockSeg bj = block_seg(jb * FWD_TN + h * TM, g.bseg);
+        const bool same_mod = (bj.mod == bi.mod);
+        const bool diag_tile = (bj.samp0 == bi.samp0);
+        const float k = same_mod ? g.k_intra : g.k_inter;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float x = fmaf(__uint_as_float(v[q]), k, nshift);
-            float e = fast_exp2(x);
-            if (q == (r & 31)) {
-              if (same_mod) e = diag_term;                       // masked intra-modal diagonal: logit 0
-              else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }  // positive logit, kept out of X
+        for (int c2 = 0; c2 < 2; ++c2) {            // chunk pairs (software pipelined tcgen05.ld)
+          const int c = h * 4 + c2 * 2;             // 32-column chunk index in the tile (0..7), even
+          tmem_ld_wait();
+          tmem_ld32(tbase + (c + 1) * 32, vb);
+          if (!diag_tile || (r >> 5) != (c & 3)) {
+            fwd_sum_chunk(va, k, nshift, rs);
+          } else {
+            // this chunk holds the same-sample column (local column index == r)
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float x = fmaf(__uint_as_float(va[q]), k, nshift);
+              float e = fast_exp2(x);
+              if (q == (r & 31)) {
+                if (same_mod) e = diag_term;                       // masked intra-modal diagonal: logit 0
+                else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }  // positive logit, kept out of X
+              }
+              rs[q & 3] += e;
             }
-            rs0 += e;
+          }
+          tmem_ld_wait();
+          if (c + 2 < 8) tmem_ld32(tbase + (c + 2) * 32, va);
+          if (!diag_tile || (r >> 5) != ((c + 1) & 3)) {
+            fwd_sum_chunk(vb, k, nshift, rs);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float x = fmaf(__uint_as_float(vb[q]), k, nshift);
+              float e = fast_exp2(x);
+              if (q == (r & 31)) {
+                if (same_mod) e = diag_term;
+                else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }
+              }
+              rs[q & 3] += e;
+            }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
-    if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs0 + rs1) + (rs2 + rs3));
+    if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ================================================================================================
-// Backward.  Work item = (row block ib, 256-wide slab of D).  Per column block j:
-//   S(j)  = A_ib * Fhat_j^T            -> TMEM S buffer (double buffered)
+// Backward.  Work item = (128-row block ib, 256-wide slab of D).  Per 128-column block j:
+//   S(j)  = A_ib * Fhat_j^T            -> TMEM S buffer (double buffered, 2 x 128 columns)
 //   P(j)  = sigma * 2^(k S - shift) * (1/Z_g + 1/Z_j) * kappa   (same-sample column zeroed) -> fp16 smem tile
-//   dF   += P(j) * Fhat_j[:, slab]     -> TMEM slab accumulator (B operand read MN-major from the TMA tile)
+//           (double buffered: P(j+1) is written while dF(j) still reads P(j))
+//   dF   += P(j) * Fhat_j[:, slab]     -> TMEM slab accumulator (B operand read MN-major from the TMA tiles)
 // MMA issue order: S(0), [S(j+1), dF(j)] ...  so the tensor pipe computes S(j+1) while the epilogue warps
-// turn S(j) into P(j).
+// turn S(j) into P(j).  Ring slots are 16 KiB boxes; an operand that needs two boxes (streamed A+B chunk, or a
+// 128-wide dF operand) takes two consecutive slots under the first slot's barriers.
 // ================================================================================================
 template <bool kResident>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float* __restrict__ coef,
               const float* __restrict__ scal, float* __restrict__ dfhat, int n_items, int n_slabs, int ncb, int nk,
-              int num_stages) {
+              int num_slots, int npbuf) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
-  const uint32_t p_tile = a_region + (kResident ? nk * CHUNK_BYTES : 0);          // [2 atoms][128 rows][128 B]
-  const uint32_t ring_base = p_tile + 2 * CHUNK_BYTES;
-  const uint32_t stage_bytes = kResident ? CHUNK_BYTES : 2 * CHUNK_BYTES;
-  const uint32_t cvec_base = ring_base + num_stages * stage_bytes;                // float [2][128]
-  const uint32_t bar_base = cvec_base + 2 * TN * 4;
+  const uint32_t p_tiles = a_region + (kResident ? nk * CHUNK_BYTES : 0);         // npbuf x [2 atoms][128 rows][128 B]
+  const uint32_t ring_base = p_tiles + npbuf * 2 * CHUNK_BYTES;
+  const uint32_t cvec_base = ring_base + num_slots * CHUNK_BYTES;                 // float [2][128]
+  const uint32_t bar_base = cvec_base + 2 * BWD_TN * 4;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  const uint32_t a_full = bar_base + 8u * (2 * MAX_STAGES);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
+  const uint32_t a_full = bar_base + 8u * (2 * MAX_SLOTS);
   const uint32_t a_empty = a_full + 8;
   auto sfull_bar = [&](int b) { return a_full + 16u + 8u * b; };
   auto sempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
-  const uint32_t p_full = a_full + 48u, p_empty = a_full + 56u;
-  const uint32_t acc_full = a_full + 64u, acc_empty = a_full + 72u;
-  const uint32_t tmem_slot = a_full + 80u;
+  auto pfull_bar = [&](int b) { return a_full + 48u + 8u * b; };
+  auto pempty_bar = [&](int b) { return a_full + 64u + 8u * b; };
+  const uint32_t acc_full = a_full + 80u, acc_empty = a_full + 88u;
+  const uint32_t tmem_slot = a_full + 96u;
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw_u32));
   float* cvec = reinterpret_cast<float*>(smem_raw + (cvec_base - raw_u32));
@@ -267,10 +310,12 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < num_slots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), EPI_THREADS); }
-    mbar_init(p_full, EPI_THREADS); mbar_init(p_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), EPI_THREADS);
+      mbar_init(pfull_bar(b), EPI_THREADS); mbar_init(pempty_bar(b), 1);
+    }
     mbar_init(acc_full, 1); mbar_init(acc_empty, EPI_THREADS);
     fence_barrier_init();
   }
@@ -279,28 +324,36 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tmem_acc = tmem_base + 2 * TN;     // slab accumulator: columns [256, 512)
+  const uint32_t tmem_acc = tmem_base + 2 * BWD_TN;     // slab accumulator: columns [256, 512)
 
   if (warp == 0) {
-    if (lane == 0) {
-      Ring ring(num_stages);
-      uint32_t item_iter = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
-        const int ib = it / n_slabs, sb = it % n_slabs;
-        const int row0 = g.row_begin + ib * TM;
-        const int d0 = sb * SLAB;
-        const int nsc = min(SLAB, g.dim - d0) / KC;
-        if (kResident) {
-          mbar_wait(a_empty, (item_iter & 1) ^ 1);
+    Ring ring(num_slots);
+    uint32_t item_iter = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
+      const int ib = it / n_slabs, sb = it - ib * n_slabs;
+      const int row0 = g.row_begin + ib * TM;
+      const int d0 = sb * SLAB;
+      const int nsc = min(SLAB, g.dim - d0) / KC;
+      // a 128-wide dF operand spans two consecutive slots; slots stay pair-aligned only if every ring user moves in
+      // pairs (streamed A+B chunks do; resident single-slot S chunks do when nk is even)
+      const bool dpair = (nsc & 1) == 0 && (!kResident || (nk & 1) == 0);
+      const bool dadv2 = dpair || !kResident;
+      if (kResident) {
+        mbar_wait(a_empty, (item_iter & 1) ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(a_full, nk * CHUNK_BYTES);
           for (int kc = 0; kc < nk; ++kc) tma_load_2d(a_region + kc * CHUNK_BYTES, &tmap, a_full, kc * KC, row0);
         }
-        for (int step = 0; step <= ncb; ++step) {
-          if (step < ncb) {            // operands of S(step)
-            const int col0 = step * TN;
-            for (int kc = 0; kc < nk; ++kc) {
-              mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-              const uint32_t st = ring_base + ring.stage * stage_bytes;
+        __syncwarp();
+      }
+      for (int step = 0; step <= ncb; ++step) {
+        if (step < ncb) {            // operands of S(step)
+          const int col0 = step * BWD_TN;
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+            if (!kResident) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
+            if (elect_one()) {
+              const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
               if (kResident) {
                 mbar_arrive_expect_tx(full_bar(ring.stage), CHUNK_BYTES);
                 tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, col0);
@@ -308,125 +361,162 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
                 mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
                 tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0);
                 tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, col0);
+                mbar_arrive(full_bar(ring.stage + 1));
               }
-              ring.advance();
             }
+            __syncwarp();
+            ring.advance();
+            if (!kResident) ring.advance();
           }
-          if (step >= 1) {             // B operand of dF(step-1): Fhat_j[:, slab] as [128 j][64 d] boxes
-            const int col0 = (step - 1) * TN;
-            for (int c = 0; c < nsc; ++c) {
-              mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-              const uint32_t st = ring_base + ring.stage * stage_bytes;
-              mbar_arrive_expect_tx(full_bar(ring.stage), CHUNK_BYTES);
+        }
+        if (step >= 1) {             // B operand of dF(step-1): Fhat_j[:, slab] as [128 j][64 d] boxes
+          const int col0 = (step - 1) * BWD_TN;
+          for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+            if (dadv2) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
+            if (elect_one()) {
+              const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
+              mbar_arrive_expect_tx(full_bar(ring.stage), dpair ? 2 * CHUNK_BYTES : CHUNK_BYTES);
               tma_load_2d(st, &tmap, full_bar(ring.stage), d0 + c * KC, col0);
-              ring.advance();
+              if (dpair) tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), d0 + (c + 1) * KC, col0);
+              if (dadv2) mbar_arrive(full_bar(ring.stage + 1));   // keep the skipped slot's barriers in phase
             }
+            __syncwarp();
+            ring.advance();
+            if (dadv2) ring.advance();
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      Ring ring(num_stages);
-      uint32_t item_iter = 0, s_cnt = 0, p_cnt = 0;
-      auto issue_S = [&]() {
-        const uint32_t buf = s_cnt & 1;
-        mbar_wait(sempty_bar(buf), ((s_cnt >> 1) & 1) ^ 1);
+    Ring ring(num_slots);
+    uint32_t item_iter = 0, s_cnt = 0, p_cnt = 0;
+    auto issue_S = [&]() {
+      const uint32_t buf = s_cnt & 1;
+      mbar_wait(sempty_bar(buf), ((s_cnt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(full_bar(ring.stage), ring.phase);
         tc_fence_after();
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(full_bar(ring.stage), ring.phase);
-          tc_fence_after();
-          const uint32_t st = ring_base + ring.stage * stage_bytes;
+        if (elect_one()) {
+          const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
           const uint32_t a_addr = kResident ? a_region + kc * CHUNK_BYTES : st;
           const uint32_t b_addr = kResident ? st : st + CHUNK_BYTES;
-          issue_s_chunk(tmem_base + buf * TN, a_addr, b_addr, kc == 0);
+          issue_s_chunk(tmem_base + buf * BWD_TN, a_addr, b_addr, kIdescS128, kc == 0);
           umma_commit(empty_bar(ring.stage));
-          ring.advance();
+          if (!kResident) umma_commit(empty_bar(ring.stage + 1));
         }
-        umma_commit(sfull_bar(buf));
-        ++s_cnt;
-      };
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
-        const int sb = it % n_slabs;
-        const int d0 = sb * SLAB;
-        const int nsc = min(SLAB, g.dim - d0) / KC;
-        if (kResident) { mbar_wait(a_full, item_iter & 1); tc_fence_after(); }
-        mbar_wait(acc_empty, (item_iter & 1) ^ 1);
+        __syncwarp();
+        ring.advance();
+        if (!kResident) ring.advance();
+      }
+      if (elect_one()) umma_commit(sfull_bar(buf));
+      __syncwarp();
+      ++s_cnt;
+    };
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
+      const int ib = it / n_slabs, sb = it - ib * n_slabs;
+      const int d0 = sb * SLAB;
+      const int nsc = min(SLAB, g.dim - d0) / KC;
+      const bool dpair = (nsc & 1) == 0 && (!kResident || (nk & 1) == 0);
+      const bool dadv2 = dpair || !kResident;
+      if (kResident) mbar_wait(a_full, item_iter & 1);
+      mbar_wait(acc_empty, (item_iter & 1) ^ 1);
+      tc_fence_after();
+      issue_S();
+      for (int j = 0; j < ncb; ++j, ++p_cnt) {
+        if (j + 1 < ncb) issue_S();
+        const uint32_t pb = (npbuf == 2) ? (p_cnt & 1) : 0u;
+        const uint32_t p_tile = p_tiles + pb * 2 * CHUNK_BYTES;
+        mbar_wait(pfull_bar(pb), ((npbuf == 2) ? (p_cnt >> 1) : p_cnt) & 1);
         tc_fence_after();
-        issue_S();
-        for (int j = 0; j < ncb; ++j) {
-          if (j + 1 < ncb) issue_S();
-          mbar_wait(p_full, p_cnt & 1);
+        for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
+          mbar_wait(full_bar(ring.stage), ring.phase);
           tc_fence_after();
-          for (int c = 0; c < nsc; ++c) {
-            mbar_wait(full_bar(ring.stage), ring.phase);
-            tc_fence_after();
-            const uint32_t st = ring_base + ring.stage * stage_bytes;
+          if (elect_one()) {
+            const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
 #pragma unroll
-            for (int k16 = 0; k16 < TN / 16; ++k16) {
+            for (int k16 = 0; k16 < BWD_TN / 16; ++k16) {
               // A = P[:, 16 k16 .. +16): K-major, atom (k16 >> 2), 32-byte step inside the atom
               const uint64_t ad = kmajor_desc(p_tile + (k16 >> 2) * CHUNK_BYTES + (k16 & 3) * 32);
-              // B = Fhat_j[16 k16 .. +16, 64 d]: MN-major view of the TMA box; 16 K rows = 2048 bytes
+              // B = Fhat_j[16 k16 .. +16, 64 or 128 d]: MN-major view of the TMA boxes; 16 K rows = 2048 bytes,
+              // the second 64-wide MN atom is the next slot (LBO = 16 KiB)
               const uint64_t bd = make_smem_desc_sw128(st + k16 * 2048, 1024, CHUNK_BYTES);
-              umma_ss(tmem_acc + c * KC, ad, bd, kIdescG, (j > 0 || k16 > 0) ? 1u : 0u);
+              umma_ss(tmem_acc + c * KC, ad, bd, dpair ? kIdescG128 : kIdescG64, (j > 0 || k16 > 0) ? 1u : 0u);
             }
             umma_commit(empty_bar(ring.stage));
-            ring.advance();
+            if (dadv2) umma_commit(empty_bar(ring.stage + 1));
           }
-          umma_commit(p_empty);
-          ++p_cnt;
+          __syncwarp();
+          ring.advance();
+          if (dadv2) ring.advance();
         }
+        if (elect_one()) umma_commit(pempty_bar(pb));
+        __syncwarp();
+      }
+      if (elect_one()) {
         umma_commit(acc_full);
         if (kResident) umma_commit(a_empty);
       }
+      __syncwarp();
     }
   } else if (warp >= EPI_WARP0) {
     const int ew = warp - EPI_WARP0;
     const int r = ew * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
     const float sigma = scal[0];
+    const float nshift = -g.shift;
     uint32_t item_iter = 0, s_cnt = 0, p_cnt = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
-      const int ib = it / n_slabs, sb = it % n_slabs;
+      const int ib = it / n_slabs, sb = it - ib * n_slabs;
       const int row0 = g.row_begin + ib * TM;
       const int d0 = sb * SLAB;
       const int slab_w = min(SLAB, g.dim - d0);
       const int gi = row0 + r;
-      const int seg = row0 / g.bseg;
-      const int mod_i = seg & 1;
-      const int sb_i = (seg >> 1) * g.bseg + (row0 - seg * g.bseg);
+      const BlockSeg bi = block_seg(row0, g.bseg);
       const float iz_i = coef[2 * (int64_t)gi];
       for (int j = 0; j < ncb; ++j, ++s_cnt, ++p_cnt) {
-        const int col0 = j * TN;
-        const int segj = col0 / g.bseg;
-        const bool same_mod = ((segj & 1) == mod_i);
-        const int sb_j = (segj >> 1) * g.bseg + (col0 - segj * g.bseg);
-        const bool diag_tile = (sb_j == sb_i);
+        const int col0 = j * BWD_TN;
+        const BlockSeg bj = block_seg(col0, g.bseg);
+        const bool same_mod = (bj.mod == bi.mod);
+        const bool diag_tile = (bj.samp0 == bi.samp0);
         const float k = same_mod ? g.k_intra : g.k_inter;
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
-        const float nshift = -g.shift;
         const uint32_t buf = s_cnt & 1;
-        float* cv = cvec + buf * TN;
+        const uint32_t pb = (npbuf == 2) ? (p_cnt & 1) : 0u;
+        const uint32_t p_tile = p_tiles + pb * 2 * CHUNK_BYTES;
+        float* cv = cvec + buf * BWD_TN;
         cv[r] = coef[2 * (int64_t)(col0 + r)] * ks;     // column r of this tile: kappa*sigma / Z_j
         const float a_i = iz_i * ks;
         named_bar_sync(1, EPI_THREADS);
         mbar_wait(sfull_bar(buf), (s_cnt >> 1) & 1);
         tc_fence_after();
-        mbar_wait(p_empty, (p_cnt & 1) ^ 1);             // dF(j-1) has consumed the previous P tile
-#pragma unroll 1
-        for (int c = 0; c < TN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + buf * TN + c * 32, v);
-          tmem_ld_wait();
-          uint32_t packed[16];
+        mbar_wait(pempty_bar(pb), (((npbuf == 2) ? (p_cnt >> 1) : p_cnt) & 1) ^ 1);   // the dF that read this P buffer is done
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base + buf * BWD_TN, va);
 #pragma unroll
-          for (int q = 0; q < 32; q += 2) {
-            float e0 = fast_exp2(fmaf(__uint_as_float(v[q]), k, nshift)) * (a_i + cv[c * 32 + q]);
-            float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cv[c * 32 + q + 1]);
-            if (diag_tile && (c * 32 + q) == r) e0 = 0.f;        // same-sample pair handled in grad_finish
-            if (diag_tile && (c * 32 + q + 1) == r) e1 = 0.f;
-            __half2 h = __floats2half2_rn(e0, e1);
-            packed[q >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        for (int c = 0; c < BWD_TN / 32; ++c) {
+          uint32_t (&v)[32] = (c & 1) ? vb : va;
+          tmem_ld_wait();
+          if (c + 1 < BWD_TN / 32) tmem_ld32(lane_base + buf * BWD_TN + (c + 1) * 32, (c & 1) ? va : vb);
+          uint32_t packed[16];
+          const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const float4 cc = cv4[q >> 2];
+            float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
+            float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
+            float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
+            float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
+            if (diag_tile) {                                     // same-sample pair handled in grad_finish
+              if (c * 32 + q + 0 == r) e0 = 0.f;
+              if (c * 32 + q + 1 == r) e1 = 0.f;
+              if (c * 32 + q + 2 == r) e2 = 0.f;
+              if (c * 32 + q + 3 == r) e3 = 0.f;
+            }
+            __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+            packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
+            packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
           // P tile is a K-major SWIZZLE_128B operand: atom = 64 columns, 16-byte chunk index XOR (row & 7)
           const uint32_t row_addr = p_tile + (c >> 1) * CHUNK_BYTES + r * 128;
@@ -442,7 +532,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
         tc_fence_before();
         mbar_arrive(sempty_bar(buf));
         fence_proxy_async_smem();
-        mbar_arrive(p_full);
+        mbar_arrive(pfull_bar(pb));
       }
       // slab accumulator -> dfhat (fp32, still scaled by sigma; grad_finish divides it out)
       mbar_wait(acc_full, item_iter & 1);
@@ -451,7 +541,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
 #pragma unroll 1
       for (int c = 0; c < slab_w / 32; ++c) {
         uint32_t v[32];
-        tmem_ld32(lane_base + 2 * TN + c * 32, v);
+        tmem_ld32(lane_base + 2 * BWD_TN + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 32; q += 4)
@@ -472,8 +562,8 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
 // ================================================================================================
 // Self-test kernel: one CTA, D[128][n] = A[128][k] * B^T with the operand forms the real kernels use.
 //   variant 0: A, B K-major from TMA tiles (the S product)
-//   variant 1: A K-major written by threads with the swizzle formula (the P tile), B MN-major TMA tile
-//              (b_host is [k][n], n == 64)  (the dF product)
+//   variant 1: A K-major written by threads with the swizzle formula (the P tile), B MN-major TMA tiles
+//              (b_host is [k][n], n in {64, 128, 256}: n/64 boxes of [k rows][64], LBO = box size)  (the dF product)
 //   variant 2: A from TMEM (tcgen05.st packed fp16 pairs), B K-major  (candidate for a later revision)
 // ================================================================================================
 __global__ void __launch_bounds__(128, 1)
@@ -483,14 +573,15 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int nk = k / KC;
   const uint32_t a_s = base;                              // nk chunks of [128][64]
-  const uint32_t b_s = a_s + nk * CHUNK_BYTES;            // variant 0/2: nk chunks of [n<=128 rows][64]; variant 1: [k rows][64]
-  const uint32_t bar = b_s + max(nk, 2) * CHUNK_BYTES;
+  const uint32_t b_s = a_s + nk * CHUNK_BYTES;            // variant 0/2: nk chunks of [n rows][64]; variant 1: n/64 boxes of [k rows][64]
+  const uint32_t bchunk = (uint32_t)n * 128u;             // bytes of one [n rows][64] K-major chunk
+  const uint32_t bar = b_s + (uint32_t)n * (uint32_t)k * 2u;
   const uint32_t done_bar = bar + 8;
   const uint32_t tmem_slot = bar + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)lane;
   if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(done_bar, 1); fence_barrier_init(); }
-  if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -508,11 +599,11 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     fence_proxy_async_smem();
   }
   if (variant == 2) {
-    // A -> TMEM columns [128, 128 + k/2): lane = row, column c holds elements (2c, 2c+1)
+    // A -> TMEM columns [256, 256 + k/2): lane = row, column c holds elements (2c, 2c+1)
     for (int c0 = 0; c0 < k / 2; c0 += 16) {
       uint32_t v[16];
       for (int i = 0; i < 16; ++i) v[i] = *reinterpret_cast<const uint32_t*>(a_gmem + (size_t)r * k + 2 * (c0 + i));
-      tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 128 + c0, v);
+      tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -526,10 +617,12 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int kc = 0; kc < nk; ++kc) { tma_load_2d(a_s + kc * CHUNK_BYTES, &tmap_a, bar, kc * KC, 0); bytes += CHUNK_BYTES; }
     }
     if (variant == 1) {
-      tma_load_2d(b_s, &tmap_b, bar, 0, 0);               // box {64 n, k rows}
-      bytes += k * 128;
+      for (int a = 0; a < n / 64; ++a) {                  // boxes {64 n, k rows}
+        tma_load_2d(b_s + a * k * 128, &tmap_b, bar, a * 64, 0);
+        bytes += k * 128;
+      }
     } else {
-      for (int kc = 0; kc < nk; ++kc) { tma_load_2d(b_s + kc * CHUNK_BYTES, &tmap_b, bar, kc * KC, 0); bytes += n * 128; }
+      for (int kc = 0; kc < nk; ++kc) { tma_load_2d(b_s + kc * bchunk, &tmap_b, bar, kc * KC, 0); bytes += bchunk; }
     }
     mbar_arrive_expect_tx(bar, bytes);
     mbar_wait(bar, 0);
@@ -538,18 +631,18 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
       for (int kc = 0; kc < nk; ++kc)
         for (int kk = 0; kk < 4; ++kk)
-          umma_ss(tmem_base, kmajor_desc(a_s + kc * CHUNK_BYTES) + kk * 2, kmajor_desc(b_s + kc * CHUNK_BYTES) + kk * 2,
+          umma_ss(tmem_base, kmajor_desc(a_s + kc * CHUNK_BYTES) + kk * 2, kmajor_desc(b_s + kc * bchunk) + kk * 2,
                   idesc, (kc | kk) ? 1u : 0u);
     } else if (variant == 1) {
-      const uint32_t idesc = make_idesc_f16(128, 64, 0, 0, 0, 1);
+      const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 1);
       for (int k16 = 0; k16 < k / 16; ++k16)
         umma_ss(tmem_base, kmajor_desc(a_s + (k16 >> 2) * CHUNK_BYTES + (k16 & 3) * 32),
-                make_smem_desc_sw128(b_s + k16 * 2048, 1024, CHUNK_BYTES), idesc, k16 ? 1u : 0u);
+                make_smem_desc_sw128(b_s + k16 * 2048, 1024, (uint32_t)k * 128u), idesc, k16 ? 1u : 0u);
     } else {
       const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
       for (int kc = 0; kc < nk; ++kc)
         for (int kk = 0; kk < 4; ++kk)
-          umma_ts(tmem_base, tmem_base + 128 + (kc * 4 + kk) * 8, kmajor_desc(b_s + kc * CHUNK_BYTES) + kk * 2, idesc,
+          umma_ts(tmem_base, tmem_base + 256 + (kc * 4 + kk) * 8, kmajor_desc(b_s + kc * bchunk) + kk * 2, idesc,
                   (kc | kk) ? 1u : 0u);
     }
     umma_commit(done_bar);
@@ -564,7 +657,7 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -587,6 +680,15 @@ EncodeTiledFn get_encode_fn() {
 
 // fp16 matrix [rows][cols] (row-major) tiled into {64 cols, box_rows} boxes with 128-byte swizzle
 int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  // The driver-API encode needs a current context on THIS thread.  torch's autograd worker threads only get
+  // one lazily (first runtime call), so bind the primary context here; cudaFree(nullptr) is the documented no-op
+  // that does it.
+  static thread_local int bound_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_dev) {
+    cudaFree(nullptr);
+    bound_dev = dev;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return CROSSCLR_ECUDA; }
   cuuint64_t dims[2] = {cols, rows};
@@ -611,7 +713,8 @@ int sm_count() {
   return n;
 }
 
-constexpr int kBarBytes = 8 * (2 * MAX_STAGES) + 128;
+constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;
+constexpr size_t kMaxSmem = 232448;      // 227 KiB opt-in dynamic shared memory per CTA
 
 }  // namespace
 
@@ -619,13 +722,14 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
-  const int nk = g.dim / KC, ncb = g.rows / TN, nrb = g.row_count / TM;
+  const int nk = g.dim / KC, ncb = g.rows / FWD_TN, nrb = g.row_count / TM;
   const int tiles = nrb * ncb;
   TimedLaunch timed(CROSSCLR_K_FWD, st);
   const bool resident = nk <= MAX_RES_CHUNKS;
-  const int stages = resident ? 6 : 7;
-  const size_t smem = 1024 + (resident ? (size_t)nk * CHUNK_BYTES + (size_t)stages * CHUNK_BYTES
-                                       : (size_t)stages * 2 * CHUNK_BYTES) + kBarBytes;
+  const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
+  const size_t stage_bytes = (size_t)(resident ? 2 : 3) * CHUNK_BYTES;
+  const int stages = (int)std::min<size_t>(6, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);
+  const size_t smem = 1024 + a_bytes + (size_t)stages * stage_bytes + kBarBytes;
   const int grid = std::min(tiles, sm_count());
   if (resident) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -642,28 +746,34 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
-  const int nk = g.dim / KC, ncb = g.rows / TN, nrb = g.row_count / TM;
+  const int nk = g.dim / KC, ncb = g.rows / BWD_TN, nrb = g.row_count / TM;
   const int n_slabs = (g.dim + SLAB - 1) / SLAB;
   const int n_items = nrb * n_slabs;
   TimedLaunch timed(CROSSCLR_K_BWD, st);
   const bool resident = nk <= MAX_RES_CHUNKS;
-  const int stages = resident ? 4 : 6;
-  const size_t smem = 1024 + (resident ? (size_t)nk * CHUNK_BYTES : 0) + 2 * CHUNK_BYTES +
-                      (size_t)stages * (resident ? 1 : 2) * CHUNK_BYTES + 2 * TN * 4 + kBarBytes;
+  const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
+  const size_t avail = kMaxSmem - 1024 - 2 * BWD_TN * 4 - kBarBytes - a_bytes;
+  // double-buffer the P tile when that still leaves a ring of >= 4 slots (D <= 256 resident, or streamed A)
+  int npbuf = 2;
+  int slots = (int)((avail - 4 * CHUNK_BYTES) / CHUNK_BYTES);
+  if (avail < 4 * CHUNK_BYTES || slots < 4) { npbuf = 1; slots = (int)((avail - 2 * CHUNK_BYTES) / CHUNK_BYTES); }
+  slots = std::min(slots & ~1, MAX_SLOTS);
+  const size_t smem = 1024 + a_bytes + (size_t)npbuf * 2 * CHUNK_BYTES + (size_t)slots * CHUNK_BYTES + 2 * BWD_TN * 4 +
+                      kBarBytes;
   const int grid = std::min(n_items, sm_count());
   if (resident) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_items, n_slabs, ncb, nk, stages);
+    bwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_items, n_slabs, ncb, nk, slots, npbuf);
   } else {
     CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_items, n_slabs, ncb, nk, stages);
+    bwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_items, n_slabs, ncb, nk, slots, npbuf);
   }
   return check_launch("bwd_tc_kernel");
 }
 
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k) {
-  if (variant < 0 || variant > 2 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 128 ||
-      (variant == 1 && n != 64)) {
+  if (variant < 0 || variant > 2 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
+      (variant == 1 && n % 64 != 0)) {
     set_error("crossclr_selftest: unsupported variant/shape (variant %d n %d k %d)", variant, n, k);
     return CROSSCLR_EINVAL;
   }
@@ -676,10 +786,10 @@ int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, 
   CC_CHECK_CUDA(cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice));
   CUtensorMap ta, tb;
   int rc = make_tmap_f16(&ta, da, 128, (uint64_t)k, 128);
-  if (!rc) rc = (variant == 1) ? make_tmap_f16(&tb, db, (uint64_t)k, (uint64_t)n, (uint32_t)k)   // b is [k][n]
+  if (!rc) rc = (variant == 1) ? make_tmap_f16(&tb, db, (uint64_t)k, (uint64_t)n, (uint32_t)k)   // b is [k][n], box {64, k}
                                : make_tmap_f16(&tb, db, (uint64_t)n, (uint64_t)k, (uint32_t)n);  // b is [n][k]
   if (!rc) {
-    const size_t smem = 1024 + (size_t)(k / KC + std::max(k / KC, 2)) * CHUNK_BYTES + 64;
+    const size_t smem = 1024 + (size_t)(k / KC) * CHUNK_BYTES + (size_t)n * k * 2 + 64;
     cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     selftest_kernel<<<1, 128, smem>>>(ta, tb, variant, n, k, da, dout);
     rc = check_launch("selftest_kernel");

@@ -40,16 +40,31 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Spin on a phase; a (very generous) cycle budget turns a protocol bug into a trap instead of a hung GPU.
+// Spin on a phase; a (very generous) poll budget turns a protocol bug into a trap instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {   // ~4 s at 2 GHz
+    if (++polls > 200000000u) {            // each failed try_wait suspends for up to ~1 us: seconds in total
+#ifdef CROSSCLR_DEBUG_SYNC
       printf("crossclr: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }
+}
+
+// One lane of a converged warp (the same lane every time for a full mask).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)

@@ -63,75 +63,126 @@ def _rowmajor(x):
     return x if (x.stride(1) == 1 and x.stride(0) >= x.shape[1]) else x.contiguous()
 
 
-class _CrossCLRFunction(torch.autograd.Function):
-    """forward = pack -> [all-gather] -> fwd stats -> [all-gather] -> finalize; backward = bwd."""
+class _NativeOps:
+    """The C ABI of include/crossclr_b200.h on torch tensors (device pointers + the current stream).
 
+    This is the only implementation the criterion ever uses.  `_forward_impl` / `_backward_impl` take the ops object
+    as an argument so the rank / shard / all-gather orchestration can be exercised on CPU (gloo) by tests/ with a
+    checker-backed stand-in; nothing in the package selects anything but `_NativeOps`.
+    """
+
+    def __init__(self):
+        self.lib = N.load()
+
+    def plan(self, prob, in_dtype, exact):
+        code = self.lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[in_dtype], 1 if exact else 0)
+        if code < 0:
+            N.check(code, "crossclr_choose_path")
+        return code, _FEAT_TORCH[self.lib.crossclr_feature_dtype(code)]
+
+    def pack(self, x, feat_out, rnorm_out):
+        B, D = x.shape
+        N.check(self.lib.crossclr_pack(_ptr(x), _DTYPE_CODE[x.dtype], x.stride(0), B, D, _ptr(feat_out),
+                                       _DTYPE_CODE[feat_out.dtype], _ptr(rnorm_out), _stream()), "crossclr_pack")
+
+    def fwd(self, prob, code, feat_all, stats):
+        N.check(self.lib.crossclr_fwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(stats), None, 0, _stream()),
+                "crossclr_fwd")
+
+    def finalize(self, prob, stats, coef, loss, scal):
+        N.check(self.lib.crossclr_finalize(ctypes.byref(prob), _ptr(stats), _ptr(coef), _ptr(loss), _ptr(scal),
+                                           _stream()), "crossclr_finalize")
+
+    def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt):
+        ws_bytes = int(self.lib.crossclr_workspace_bytes(ctypes.byref(prob), code))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat_all.device)
+        N.check(self.lib.crossclr_bwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(rnorm), _ptr(coef), _ptr(scal),
+                                      _ptr(grad_out), grad_scale, _ptr(dv), dv.stride(0), _ptr(dt), dt.stride(0),
+                                      _DTYPE_CODE[dv.dtype], _ptr(ws), ws_bytes, _stream()), "crossclr_bwd")
+
+
+def _group_info(group):
+    if group is None:
+        return 1, 0
+    import torch.distributed as dist
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
+    """pack -> [all-gather features] -> row statistics of the owned rows -> [all-gather stats] -> finalize.
+
+    Rank r owns stacked rows [2 r B, 2 (r+1) B): its video rows then its text rows (include/crossclr_b200.h).
+    Returns (loss, prob, code, saved tensors)."""
+    B, D = v.shape
+    dev = v.device
+    world, rank = _group_info(group)
+    prob = N.Problem(2 * world, B, D, 2 * rank * B, 2 * B, float(temperature), float(negative_weight))
+    code, feat_dtype = ops.plan(prob, v.dtype, path == "simt")
+    if path == "tc" and code != N.PATH_TC:
+        raise RuntimeError(f"tensor-core path needs B % 128 == 0 and D % 64 == 0 (got B={B}, D={D})")
+    rows = 2 * world * B
+    feat_all = torch.empty((2 * world, B, D), dtype=feat_dtype, device=dev)
+    feat_loc = feat_all[2 * rank:2 * rank + 2]
+    rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
+    ops.pack(v, feat_loc[0], rnorm[:B])
+    ops.pack(t, feat_loc[1], rnorm[B:])
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1).clone(), group=group)
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+    ops.fwd(prob, code, feat_all, stats)
+    if world > 1:
+        import torch.distributed as dist
+        own = stats[2 * rank * B:2 * (rank + 1) * B].reshape(-1).clone()
+        dist.all_gather_into_tensor(stats.view(-1), own, group=group)
+    coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+    scal = torch.empty(4, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float64, device=dev)
+    ops.finalize(prob, stats, coef, loss, scal)
+    return loss, prob, code, (feat_all, rnorm, coef, scal)
+
+
+def _backward_impl(ops, prob, code, saved, grad_out, grad_scale, out_dtype):
+    feat_all, rnorm, coef, scal = saved
+    dev = feat_all.device
+    go = grad_out.detach().to(device=dev, dtype=torch.float64).contiguous()
+    dv = torch.empty((prob.bseg, prob.dim), dtype=out_dtype, device=dev)
+    dt = torch.empty((prob.bseg, prob.dim), dtype=out_dtype, device=dev)
+    ops.bwd(prob, code, feat_all, rnorm, coef, scal, go, float(grad_scale), dv, dt)
+    return dv, dt
+
+
+_native_ops = None
+
+
+def _ops():
+    global _native_ops
+    if _native_ops is None:
+        _native_ops = _NativeOps()
+    return _native_ops
+
+
+class _CrossCLRFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, video, text, temperature, negative_weight, path, group, grad_scale):
-        lib = N.load()
+        ops = _ops()
         _check_inputs(video, text)
         in_dtype = video.dtype
         if in_dtype == torch.float64:          # kernels compute in fp32; the reference's f64 inputs are down-cast
             video, text = video.float(), text.float()
         v, t = _rowmajor(video.detach()), _rowmajor(text.detach())
-        B, D = v.shape
-        dev = v.device
-        world, rank = 1, 0
-        if group is not None:
-            import torch.distributed as dist
-            world, rank = dist.get_world_size(group), dist.get_rank(group)
-        prob = N.Problem(2 * world, B, D, 2 * rank * B, 2 * B, float(temperature), float(negative_weight))
-        with torch.cuda.device(dev):
-            code = lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[v.dtype], 1 if path == "simt" else 0)
-            if code < 0:
-                N.check(code, "crossclr_choose_path")
-            if path == "tc" and code != N.PATH_TC:
-                raise RuntimeError(f"tensor-core path needs B % 128 == 0 and D % 64 == 0 (got B={B}, D={D})")
-            fdt = lib.crossclr_feature_dtype(code)
-            st = _stream()
-            rows = 2 * world * B
-            feat_all = torch.empty((2 * world, B, D), dtype=_FEAT_TORCH[fdt], device=dev)
-            feat_loc = feat_all[2 * rank:2 * rank + 2]
-            rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
-            N.check(lib.crossclr_pack(_ptr(v), _DTYPE_CODE[v.dtype], v.stride(0), B, D, _ptr(feat_loc[0]), fdt,
-                                      _ptr(rnorm), st), "crossclr_pack(video)")
-            N.check(lib.crossclr_pack(_ptr(t), _DTYPE_CODE[t.dtype], t.stride(0), B, D, _ptr(feat_loc[1]), fdt,
-                                      _ptr(rnorm[B:]), st), "crossclr_pack(text)")
-            if world > 1:
-                import torch.distributed as dist
-                dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1).clone(), group=group)
-            stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
-            N.check(lib.crossclr_fwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(stats), None, 0, st), "crossclr_fwd")
-            if world > 1:
-                import torch.distributed as dist
-                own = stats[2 * rank * B:2 * (rank + 1) * B].reshape(-1).clone()
-                dist.all_gather_into_tensor(stats.view(-1), own, group=group)
-            coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)
-            scal = torch.empty(4, dtype=torch.float32, device=dev)
-            loss = torch.empty((), dtype=torch.float64, device=dev)
-            N.check(lib.crossclr_finalize(ctypes.byref(prob), _ptr(stats), _ptr(coef), _ptr(loss), _ptr(scal), st),
-                    "crossclr_finalize")
-        ctx.save_for_backward(feat_all, rnorm, coef, scal)
+        with torch.cuda.device(v.device):
+            loss, prob, code, saved = _forward_impl(ops, v, t, temperature, negative_weight, path, group)
+        ctx.save_for_backward(*saved)
         ctx.prob, ctx.code, ctx.in_dtype, ctx.grad_scale = prob, code, in_dtype, float(grad_scale)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        lib = N.load()
-        feat_all, rnorm, coef, scal = ctx.saved_tensors
-        prob = ctx.prob
-        B, D = prob.bseg, prob.dim
-        dev = feat_all.device
+        saved = ctx.saved_tensors
         out_dtype = torch.float32 if ctx.in_dtype == torch.float64 else ctx.in_dtype
-        with torch.cuda.device(dev):
-            go = grad_out.detach().to(device=dev, dtype=torch.float64).contiguous()
-            dv = torch.empty((B, D), dtype=out_dtype, device=dev)
-            dt = torch.empty((B, D), dtype=out_dtype, device=dev)
-            ws_bytes = int(lib.crossclr_workspace_bytes(ctypes.byref(prob), ctx.code))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            N.check(lib.crossclr_bwd(ctypes.byref(prob), ctx.code, _ptr(feat_all), _ptr(rnorm), _ptr(coef), _ptr(scal),
-                                     _ptr(go), ctx.grad_scale, _ptr(dv), D, _ptr(dt), D, _DTYPE_CODE[out_dtype],
-                                     _ptr(ws), ws_bytes, _stream()), "crossclr_bwd")
+        with torch.cuda.device(saved[0].device):
+            dv, dt = _backward_impl(_ops(), ctx.prob, ctx.code, saved, grad_out, ctx.grad_scale, out_dtype)
         if ctx.in_dtype == torch.float64:
             dv, dt = dv.double(), dt.double()
         return dv, dt, None, None, None, None, None
