@@ -21,7 +21,7 @@ EXPORTS = (
     "crossclr_version", "crossclr_last_error", "crossclr_device_supported", "crossclr_choose_path",
     "crossclr_feature_dtype", "crossclr_workspace_bytes", "crossclr_pack", "crossclr_fwd",
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
-    "crossclr_timing_enable", "crossclr_timing_read",
+    "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
 
@@ -61,6 +61,10 @@ def _declare(lib):
     lib.crossclr_workspace_bytes.argtypes = [P, c.c_int]
     lib.crossclr_pack.restype = c.c_int
     lib.crossclr_pack.argtypes = [vp, c.c_int, c.c_int64, c.c_int32, c.c_int32, vp, c.c_int, vp, vp]
+    lib.crossclr_pack2.restype = c.c_int
+    lib.crossclr_pack2.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, vp, c.c_int, vp, vp]
+    lib.crossclr_forward.restype = c.c_int
+    lib.crossclr_forward.argtypes = [P, c.c_int, vp, vp, c.c_int, c.c_int64, c.c_int64, vp, vp, vp, vp, vp, vp, vp]
     lib.crossclr_fwd.restype = c.c_int
     lib.crossclr_fwd.argtypes = [P, c.c_int, vp, vp, vp, c.c_size_t, vp]
     lib.crossclr_finalize.restype = c.c_int

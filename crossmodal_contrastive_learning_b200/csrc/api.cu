@@ -113,6 +113,31 @@ int crossclr_pack(const void* x, int in_dtype, int64_t x_row_stride, int32_t row
   return launch_pack(x, in_dtype, x_row_stride, rows, dim, feat_out, feat_dtype, rnorm_out, (cudaStream_t)stream);
 }
 
+int crossclr_pack2(const void* video, const void* text, int in_dtype, int64_t video_row_stride, int64_t text_row_stride,
+                   int32_t rows, int32_t dim, void* feat_out, int feat_dtype, float* rnorm_out, void* stream) {
+  CC_REQUIRE(video && text && feat_out && rnorm_out, "crossclr_pack2: NULL pointer");
+  CC_REQUIRE(rows >= 0 && dim >= 1 && video_row_stride >= dim && text_row_stride >= dim,
+             "crossclr_pack2: bad shape/stride");
+  return launch_pack2(video, text, in_dtype, video_row_stride, text_row_stride, rows, dim, feat_out, feat_dtype,
+                      rnorm_out, (cudaStream_t)stream);
+}
+
+int crossclr_forward(const crossclr_problem_t* p, int path, const void* video, const void* text, int in_dtype,
+                     int64_t video_row_stride, int64_t text_row_stride, void* feat, float* rnorm, float* stats,
+                     float* coef, float* scal, double* loss_out, void* stream) {
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  CC_REQUIRE(p->nseg == 2, "crossclr_forward is the single-rank entry point (nseg must be 2, got %d)", p->nseg);
+  const int fdt = crossclr_feature_dtype(path);
+  if (fdt < 0) return fdt;
+  rc = crossclr_pack2(video, text, in_dtype, video_row_stride, text_row_stride, p->bseg, p->dim, feat, fdt, rnorm,
+                      stream);
+  if (rc) return rc;
+  rc = crossclr_fwd(p, path, feat, stats, nullptr, 0, stream);
+  if (rc) return rc;
+  return crossclr_finalize(p, stats, coef, loss_out, scal, stream);
+}
+
 int crossclr_fwd(const crossclr_problem_t* p, int path, const void* feat, float* stats, void* workspace,
                  size_t workspace_bytes, void* stream) {
   (void)workspace; (void)workspace_bytes;

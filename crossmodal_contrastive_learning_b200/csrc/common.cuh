@@ -133,6 +133,8 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(f
 // simt_kernels.cu
 int launch_pack(const void* x, int in_dtype, int64_t stride, int rows, int dim, void* out, int out_dtype,
                 float* rnorm, cudaStream_t st);
+int launch_pack2(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int dim, void* out,
+                 int out_dtype, float* rnorm, cudaStream_t st);
 int launch_fwd_simt(const Geometry& g, const float* feat, float* stats, cudaStream_t st);
 int launch_bwd_simt(const Geometry& g, const float* feat, const float* coef, float* dfhat, cudaStream_t st);
 int launch_finalize(const Geometry& g, const float* stats, float* coef, double* loss, float* scal, cudaStream_t st);

@@ -66,6 +66,69 @@ __global__ void __launch_bounds__(256) pack_bf16_f16_vec_kernel(const uint4* __r
   if (lane == 0) rnorm[row] = rn;
 }
 
+// Both modalities of one rank in one launch (rows [0, rows) from xv, [rows, 2 rows) from xt), bf16 -> fp16, rows
+// cached in registers between the norm and the scale pass (dim <= 1024).  out: [2 rows][dim], rnorm: [2 rows].
+__global__ void __launch_bounds__(256) pack2_bf16_f16_kernel(const uint4* __restrict__ xv, const uint4* __restrict__ xt,
+                                                            int64_t sv_vec, int64_t st_vec, int rows, int dim_vec,
+                                                            uint4* __restrict__ out, float* __restrict__ rnorm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= 2 * rows) return;
+  const uint4* src = row < rows ? xv + (int64_t)row * sv_vec : xt + (int64_t)(row - rows) * st_vec;
+  uint4* dst = out + (int64_t)row * dim_vec;
+  uint4 u[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim_vec) {
+      u[i] = __ldg(src + d);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  const float rn = 1.0f / fmaxf(sqrtf(ss), kEps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim_vec) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(h[q]);
+        oh[q] = __floats2half2_rn(f.x * rn, f.y * rn);
+      }
+      dst[d] = o;
+    }
+  }
+  if (lane == 0) rnorm[row] = rn;
+}
+
+int launch_pack2(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int dim, void* out,
+                 int out_dtype, float* rnorm, cudaStream_t st) {
+  if (rows == 0) return CROSSCLR_OK;
+  const size_t esz = out_dtype == CROSSCLR_F32 ? 4 : 2;
+  if (in_dtype == CROSSCLR_BF16 && out_dtype == CROSSCLR_F16 && dim % 8 == 0 && dim <= 1024 && sv % 8 == 0 &&
+      st_ % 8 == 0 && ((uintptr_t)xv % 16 == 0) && ((uintptr_t)xt % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
+    TimedLaunch timed(CROSSCLR_K_PACK, st);
+    dim3 block(256), grid((2 * rows + 7) / 8);
+    pack2_bf16_f16_kernel<<<grid, block, 0, st>>>((const uint4*)xv, (const uint4*)xt, sv / 8, st_ / 8, rows, dim / 8,
+                                                  (uint4*)out, rnorm);
+    return check_launch("pack2_bf16_f16_kernel");
+  }
+  int rc = launch_pack(xv, in_dtype, sv, rows, dim, out, out_dtype, rnorm, st);
+  if (rc) return rc;
+  return launch_pack(xt, in_dtype, st_, rows, dim, (char*)out + (size_t)rows * dim * esz, out_dtype, rnorm + rows, st);
+}
+
 template <typename Tin>
 static int pack_dispatch_out(const void* x, int64_t stride, int rows, int dim, void* out, int out_dtype,
                              float* rnorm, cudaStream_t st) {
@@ -318,14 +381,21 @@ __global__ void __launch_bounds__(1024) finalize_kernel(Geometry g, const float*
   double lsum = 0.0;
   float rho_max = 0.f;
   for (int i = threadIdx.x; i < g.rows; i += blockDim.x) {
-    const float X = stats[2 * (int64_t)i], xp = stats[2 * (int64_t)i + 1];
+    const float2 sx = reinterpret_cast<const float2*>(stats)[i];
+    const float X = sx.x, xp = sx.y;
     const float e = exp2f(xp);
     const float Z = X + e;
     const float iz = 1.0f / Z;
     const float rho = X / Z;
-    coef[2 * (int64_t)i] = iz;
-    coef[2 * (int64_t)i + 1] = rho;
-    lsum += log1p((double)X * exp2(-(double)xp));
+    reinterpret_cast<float2*>(coef)[i] = make_float2(iz, rho);
+    // loss_g = log1p(X 2^-xp) = ln2 * log2(1 + 2^t), t = log2 X - xp; fp32 pieces (1e-7 relative), double sum.
+    // The direct form keeps converged rows exact (log1p(y) ~ y); the log-domain form covers y beyond fp32 range.
+    const float t = log2f(X) - xp;
+    float lg;
+    if (t < 100.f) lg = log1pf(xp > -120.f ? X * exp2f(-xp) : exp2f(t));
+    else lg = 0.6931471805599453f * t;                 // log2(1 + 2^t) - t < 2^-100
+    if (!(X > 0.f)) lg = 0.f;
+    lsum += (double)lg;
     rho_max = fmaxf(rho_max, rho);
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

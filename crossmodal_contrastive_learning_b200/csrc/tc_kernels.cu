@@ -271,25 +271,52 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
 }
 
 // ================================================================================================
-// Backward.  Work item = (128-row block ib, 256-wide slab of D).  Per 128-column block j:
-//   S(j)  = A_ib * Fhat_j^T            -> TMEM S buffer (double buffered, 2 x 128 columns)
-//   P(j)  = sigma * 2^(k S - shift) * (1/Z_g + 1/Z_j) * kappa   (same-sample column zeroed) -> fp16 smem tile
-//           (double buffered: P(j+1) is written while dF(j) still reads P(j))
-//   dF   += P(j) * Fhat_j[:, slab]     -> TMEM slab accumulator (B operand read MN-major from the TMA tiles)
-// MMA issue order: S(0), [S(j+1), dF(j)] ...  so the tensor pipe computes S(j+1) while the epilogue warps
-// turn S(j) into P(j).  Ring slots are 16 KiB boxes; an operand that needs two boxes (streamed A+B chunk, or a
-// 128-wide dF operand) takes two consecutive slots under the first slot's barriers.
+// Backward.  Work unit = (128-row block ib, 256-wide slab sb of D, 128-column block j); a CTA owns a contiguous,
+// balanced range of units and walks it segment by segment (segment = the units of one (ib, sb) item).  Per j:
+//   S(j)  = A_ib * Fhat_j^T            -> TMEM buffer b = tile & 1 (128 fp32 columns)
+//   P(j)  = sigma * 2^(k S - shift) * (1/Z_g + 1/Z_j) * kappa   (same-sample column zeroed), fp16, written by the
+//           epilogue warps IN PLACE over the first 64 columns of buffer b (tcgen05.st) -- no shared-memory copy
+//   dF   += P(j) * Fhat_j[:, slab]     -> TMEM slab accumulator; A operand from TMEM, B read MN-major from the
+//           same TMA boxes the S product uses
+// MMA issue order: S(j0), S(j0+1), [dF(j), S(j+2)] ...; tcgen05.mma executes in issue order, so S(j+2) may reuse
+// buffer b right behind dF(j), and the epilogue of tile j+1 overlaps dF(j) + S(j+2).
+// Ring slots are 16 KiB boxes; an operand that needs two boxes (streamed A+B chunk, or a 128-wide dF operand)
+// takes two consecutive slots under the first slot's barriers (the second slot's barriers are cycled in step).
+// A segment that covers its whole item stores the slab; partial segments add into the zeroed dfhat (red.add).
 // ================================================================================================
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct BwdSeg {
+  int ib, sb, j0, j1;
+  bool last_of_ib;      // no later segment of this CTA uses the same row block
+};
+struct BwdWalk {
+  int u, u_end, ncb, n_slabs;
+  __device__ BwdWalk(int u0, int u1, int ncb_, int ns_) : u(u0), u_end(u1), ncb(ncb_), n_slabs(ns_) {}
+  __device__ __forceinline__ bool next(BwdSeg& s) {
+    if (u >= u_end) return false;
+    const int item = u / ncb;
+    s.j0 = u - item * ncb;
+    s.j1 = min(ncb, s.j0 + (u_end - u));
+    s.ib = item / n_slabs;
+    s.sb = item - s.ib * n_slabs;
+    u += s.j1 - s.j0;
+    s.last_of_ib = (u >= u_end) || ((u / ncb) / n_slabs != s.ib);
+    return true;
+  }
+};
+
 template <bool kResident>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float* __restrict__ coef,
-              const float* __restrict__ scal, float* __restrict__ dfhat, int n_items, int n_slabs, int ncb, int nk,
-              int num_slots, int npbuf) {
+              const float* __restrict__ scal, float* __restrict__ dfhat, int n_units, int n_slabs, int ncb, int nk,
+              int num_slots) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
-  const uint32_t p_tiles = a_region + (kResident ? nk * CHUNK_BYTES : 0);         // npbuf x [2 atoms][128 rows][128 B]
-  const uint32_t ring_base = p_tiles + npbuf * 2 * CHUNK_BYTES;
+  const uint32_t ring_base = a_region + (kResident ? nk * CHUNK_BYTES : 0);
   const uint32_t cvec_base = ring_base + num_slots * CHUNK_BYTES;                 // float [2][128]
   const uint32_t bar_base = cvec_base + 2 * BWD_TN * 4;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -297,25 +324,22 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
   const uint32_t a_full = bar_base + 8u * (2 * MAX_SLOTS);
   const uint32_t a_empty = a_full + 8;
   auto sfull_bar = [&](int b) { return a_full + 16u + 8u * b; };
-  auto sempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
-  auto pfull_bar = [&](int b) { return a_full + 48u + 8u * b; };
-  auto pempty_bar = [&](int b) { return a_full + 64u + 8u * b; };
-  const uint32_t acc_full = a_full + 80u, acc_empty = a_full + 88u;
-  const uint32_t tmem_slot = a_full + 96u;
+  auto pfull_bar = [&](int b) { return a_full + 32u + 8u * b; };
+  const uint32_t acc_full = a_full + 48u, acc_empty = a_full + 56u;
+  const uint32_t tmem_slot = a_full + 64u;
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw_u32));
   float* cvec = reinterpret_cast<float*>(smem_raw + (cvec_base - raw_u32));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u_begin = (int)((long long)blockIdx.x * n_units / gridDim.x);
+  const int u_end = (int)((long long)(blockIdx.x + 1) * n_units / gridDim.x);
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < num_slots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), EPI_THREADS);
-      mbar_init(pfull_bar(b), EPI_THREADS); mbar_init(pempty_bar(b), 1);
-    }
+    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(pfull_bar(b), EPI_THREADS); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, EPI_THREADS);
     fence_barrier_init();
   }
@@ -327,74 +351,82 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
   const uint32_t tmem_acc = tmem_base + 2 * BWD_TN;     // slab accumulator: columns [256, 512)
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     Ring ring(num_slots);
-    uint32_t item_iter = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
-      const int ib = it / n_slabs, sb = it - ib * n_slabs;
-      const int row0 = g.row_begin + ib * TM;
-      const int d0 = sb * SLAB;
+    int cur_ib = -1;
+    uint32_t a_cnt = 0;
+    BwdWalk walk(u_begin, u_end, ncb, n_slabs);
+    BwdSeg sg;
+    while (walk.next(sg)) {
+      const int row0 = g.row_begin + sg.ib * TM;
+      const int d0 = sg.sb * SLAB;
       const int nsc = min(SLAB, g.dim - d0) / KC;
       // a 128-wide dF operand spans two consecutive slots; slots stay pair-aligned only if every ring user moves in
       // pairs (streamed A+B chunks do; resident single-slot S chunks do when nk is even)
       const bool dpair = (nsc & 1) == 0 && (!kResident || (nk & 1) == 0);
       const bool dadv2 = dpair || !kResident;
-      if (kResident) {
-        mbar_wait(a_empty, (item_iter & 1) ^ 1);
+      if (kResident && sg.ib != cur_ib) {
+        mbar_wait(a_empty, (a_cnt & 1) ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(a_full, nk * CHUNK_BYTES);
           for (int kc = 0; kc < nk; ++kc) tma_load_2d(a_region + kc * CHUNK_BYTES, &tmap, a_full, kc * KC, row0);
         }
         __syncwarp();
+        cur_ib = sg.ib; ++a_cnt;
       }
-      for (int step = 0; step <= ncb; ++step) {
-        if (step < ncb) {            // operands of S(step)
-          const int col0 = step * BWD_TN;
-          for (int kc = 0; kc < nk; ++kc) {
-            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-            if (!kResident) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
-            if (elect_one()) {
-              const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
-              if (kResident) {
-                mbar_arrive_expect_tx(full_bar(ring.stage), CHUNK_BYTES);
-                tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, col0);
-              } else {
-                mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
-                tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0);
-                tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, col0);
-                mbar_arrive(full_bar(ring.stage + 1));
-              }
+      auto load_S = [&](int j) {           // operands of S(j)
+        const int col0 = j * BWD_TN;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+          if (!kResident) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
+          if (elect_one()) {
+            const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
+            if (kResident) {
+              mbar_arrive_expect_tx(full_bar(ring.stage), CHUNK_BYTES);
+              tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, col0);
+            } else {
+              mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
+              tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0);
+              tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, col0);
+              mbar_arrive(full_bar(ring.stage + 1));
             }
-            __syncwarp();
-            ring.advance();
-            if (!kResident) ring.advance();
           }
+          __syncwarp();
+          ring.advance();
+          if (!kResident) ring.advance();
         }
-        if (step >= 1) {             // B operand of dF(step-1): Fhat_j[:, slab] as [128 j][64 d] boxes
-          const int col0 = (step - 1) * BWD_TN;
-          for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
-            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-            if (dadv2) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
-            if (elect_one()) {
-              const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
-              mbar_arrive_expect_tx(full_bar(ring.stage), dpair ? 2 * CHUNK_BYTES : CHUNK_BYTES);
-              tma_load_2d(st, &tmap, full_bar(ring.stage), d0 + c * KC, col0);
-              if (dpair) tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), d0 + (c + 1) * KC, col0);
-              if (dadv2) mbar_arrive(full_bar(ring.stage + 1));   // keep the skipped slot's barriers in phase
-            }
-            __syncwarp();
-            ring.advance();
-            if (dadv2) ring.advance();
+      };
+      auto load_dF = [&](int j) {          // B operand of dF(j): Fhat_j[:, slab] as [128 j][64 d] boxes
+        const int col0 = j * BWD_TN;
+        for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
+          mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+          if (dadv2) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
+          if (elect_one()) {
+            const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
+            mbar_arrive_expect_tx(full_bar(ring.stage), dpair ? 2 * CHUNK_BYTES : CHUNK_BYTES);
+            tma_load_2d(st, &tmap, full_bar(ring.stage), d0 + c * KC, col0);
+            if (dpair) tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), d0 + (c + 1) * KC, col0);
+            if (dadv2) mbar_arrive(full_bar(ring.stage + 1));   // keep the skipped slot's barriers in phase
           }
+          __syncwarp();
+          ring.advance();
+          if (dadv2) ring.advance();
         }
+      };
+      load_S(sg.j0);
+      if (sg.j0 + 1 < sg.j1) load_S(sg.j0 + 1);
+      for (int j = sg.j0; j < sg.j1; ++j) {
+        load_dF(j);
+        if (j + 2 < sg.j1) load_S(j + 2);
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     Ring ring(num_slots);
-    uint32_t item_iter = 0, s_cnt = 0, p_cnt = 0;
+    int cur_ib = -1;
+    uint32_t a_cnt = 0, seg_iter = 0, s_issued = 0, p_cnt = 0;
     auto issue_S = [&]() {
-      const uint32_t buf = s_cnt & 1;
-      mbar_wait(sempty_bar(buf), ((s_cnt >> 1) & 1) ^ 1);
-      tc_fence_after();
+      const uint32_t buf = s_issued & 1;
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(full_bar(ring.stage), ring.phase);
         tc_fence_after();
@@ -412,24 +444,29 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
       }
       if (elect_one()) umma_commit(sfull_bar(buf));
       __syncwarp();
-      ++s_cnt;
+      ++s_issued;
     };
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
-      const int ib = it / n_slabs, sb = it - ib * n_slabs;
-      const int d0 = sb * SLAB;
+    BwdWalk walk(u_begin, u_end, ncb, n_slabs);
+    BwdSeg sg;
+    while (walk.next(sg)) {
+      const int d0 = sg.sb * SLAB;
       const int nsc = min(SLAB, g.dim - d0) / KC;
       const bool dpair = (nsc & 1) == 0 && (!kResident || (nk & 1) == 0);
       const bool dadv2 = dpair || !kResident;
-      if (kResident) mbar_wait(a_full, item_iter & 1);
-      mbar_wait(acc_empty, (item_iter & 1) ^ 1);
-      tc_fence_after();
-      issue_S();
-      for (int j = 0; j < ncb; ++j, ++p_cnt) {
-        if (j + 1 < ncb) issue_S();
-        const uint32_t pb = (npbuf == 2) ? (p_cnt & 1) : 0u;
-        const uint32_t p_tile = p_tiles + pb * 2 * CHUNK_BYTES;
-        mbar_wait(pfull_bar(pb), ((npbuf == 2) ? (p_cnt >> 1) : p_cnt) & 1);
+      if (kResident && sg.ib != cur_ib) {
+        mbar_wait(a_full, a_cnt & 1);
         tc_fence_after();
+        cur_ib = sg.ib; ++a_cnt;
+      }
+      issue_S();
+      if (sg.j0 + 1 < sg.j1) issue_S();
+      mbar_wait(acc_empty, (seg_iter & 1) ^ 1);       // the epilogue has drained the previous segment's slab
+      tc_fence_after();
+      for (int j = sg.j0; j < sg.j1; ++j, ++p_cnt) {
+        const uint32_t buf = p_cnt & 1;
+        mbar_wait(pfull_bar(buf), (p_cnt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_tmem = tmem_base + buf * BWD_TN;
         for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
           mbar_wait(full_bar(ring.stage), ring.phase);
           tc_fence_after();
@@ -437,12 +474,12 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
             const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
 #pragma unroll
             for (int k16 = 0; k16 < BWD_TN / 16; ++k16) {
-              // A = P[:, 16 k16 .. +16): K-major, atom (k16 >> 2), 32-byte step inside the atom
-              const uint64_t ad = kmajor_desc(p_tile + (k16 >> 2) * CHUNK_BYTES + (k16 & 3) * 32);
+              // A = P[:, 16 k16 .. +16) from TMEM: 8 columns of packed fp16 pairs per K = 16 step
               // B = Fhat_j[16 k16 .. +16, 64 or 128 d]: MN-major view of the TMA boxes; 16 K rows = 2048 bytes,
               // the second 64-wide MN atom is the next slot (LBO = 16 KiB)
               const uint64_t bd = make_smem_desc_sw128(st + k16 * 2048, 1024, CHUNK_BYTES);
-              umma_ss(tmem_acc + c * KC, ad, bd, dpair ? kIdescG128 : kIdescG64, (j > 0 || k16 > 0) ? 1u : 0u);
+              umma_ts(tmem_acc + c * KC, p_tmem + k16 * 8, bd, dpair ? kIdescG128 : kIdescG64,
+                      (j > sg.j0 || k16 > 0) ? 1u : 0u);
             }
             umma_commit(empty_bar(ring.stage));
             if (dadv2) umma_commit(empty_bar(ring.stage + 1));
@@ -451,54 +488,54 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
           ring.advance();
           if (dadv2) ring.advance();
         }
-        if (elect_one()) umma_commit(pempty_bar(pb));
-        __syncwarp();
+        if (j + 2 < sg.j1) issue_S();                  // reuses buffer `buf` right behind dF(j)
       }
       if (elect_one()) {
         umma_commit(acc_full);
-        if (kResident) umma_commit(a_empty);
+        if (kResident && sg.last_of_ib) umma_commit(a_empty);
       }
       __syncwarp();
+      ++seg_iter;
     }
   } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue
     const int ew = warp - EPI_WARP0;
     const int r = ew * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
     const float sigma = scal[0];
     const float nshift = -g.shift;
-    uint32_t item_iter = 0, s_cnt = 0, p_cnt = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_iter) {
-      const int ib = it / n_slabs, sb = it - ib * n_slabs;
-      const int row0 = g.row_begin + ib * TM;
-      const int d0 = sb * SLAB;
+    uint32_t seg_iter = 0, p_cnt = 0;
+    BwdWalk walk(u_begin, u_end, ncb, n_slabs);
+    BwdSeg sg;
+    while (walk.next(sg)) {
+      const int row0 = g.row_begin + sg.ib * TM;
+      const int d0 = sg.sb * SLAB;
       const int slab_w = min(SLAB, g.dim - d0);
       const int gi = row0 + r;
       const BlockSeg bi = block_seg(row0, g.bseg);
       const float iz_i = coef[2 * (int64_t)gi];
-      for (int j = 0; j < ncb; ++j, ++s_cnt, ++p_cnt) {
+      for (int j = sg.j0; j < sg.j1; ++j, ++p_cnt) {
         const int col0 = j * BWD_TN;
         const BlockSeg bj = block_seg(col0, g.bseg);
         const bool same_mod = (bj.mod == bi.mod);
         const bool diag_tile = (bj.samp0 == bi.samp0);
         const float k = same_mod ? g.k_intra : g.k_inter;
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
-        const uint32_t buf = s_cnt & 1;
-        const uint32_t pb = (npbuf == 2) ? (p_cnt & 1) : 0u;
-        const uint32_t p_tile = p_tiles + pb * 2 * CHUNK_BYTES;
+        const uint32_t buf = p_cnt & 1;
+        const uint32_t tbuf = lane_base + buf * BWD_TN;
         float* cv = cvec + buf * BWD_TN;
         cv[r] = coef[2 * (int64_t)(col0 + r)] * ks;     // column r of this tile: kappa*sigma / Z_j
         const float a_i = iz_i * ks;
         named_bar_sync(1, EPI_THREADS);
-        mbar_wait(sfull_bar(buf), (s_cnt >> 1) & 1);
+        mbar_wait(sfull_bar(buf), (p_cnt >> 1) & 1);
         tc_fence_after();
-        mbar_wait(pempty_bar(pb), (((npbuf == 2) ? (p_cnt >> 1) : p_cnt) & 1) ^ 1);   // the dF that read this P buffer is done
         uint32_t va[32], vb[32];
-        tmem_ld32(lane_base + buf * BWD_TN, va);
+        tmem_ld32(tbuf, va);
 #pragma unroll
         for (int c = 0; c < BWD_TN / 32; ++c) {
           uint32_t (&v)[32] = (c & 1) ? vb : va;
           tmem_ld_wait();
-          if (c + 1 < BWD_TN / 32) tmem_ld32(lane_base + buf * BWD_TN + (c + 1) * 32, (c & 1) ? va : vb);
+          if (c + 1 < BWD_TN / 32) tmem_ld32(tbuf + (c + 1) * 32, (c & 1) ? va : vb);
           uint32_t packed[16];
           const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
@@ -518,39 +555,40 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
             packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
             packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          // P tile is a K-major SWIZZLE_128B operand: atom = 64 columns, 16-byte chunk index XOR (row & 7)
-          const uint32_t row_addr = p_tile + (c >> 1) * CHUNK_BYTES + r * 128;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t chunk = (uint32_t)((c & 1) * 4 + ch) ^ (uint32_t)(r & 7);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + chunk * 16),
-                         "r"(packed[ch * 4 + 0]), "r"(packed[ch * 4 + 1]), "r"(packed[ch * 4 + 2]),
-                         "r"(packed[ch * 4 + 3])
-                         : "memory");
-          }
+          // P(j) columns [32c, 32c+32) -> packed fp16 pairs in TMEM columns [16c, 16c+16) of the same buffer
+          // (S columns < 32(c+1) are already in registers, so nothing unread is overwritten)
+          tmem_st16(tbuf + c * 16, packed);
         }
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(sempty_bar(buf));
-        fence_proxy_async_smem();
-        mbar_arrive(pfull_bar(pb));
+        mbar_arrive(pfull_bar(buf));
       }
       // slab accumulator -> dfhat (fp32, still scaled by sigma; grad_finish divides it out)
-      mbar_wait(acc_full, item_iter & 1);
+      mbar_wait(acc_full, seg_iter & 1);
       tc_fence_after();
       float* out = dfhat + (int64_t)(gi - g.row_begin) * g.dim + d0;
+      const bool whole = (sg.j0 == 0 && sg.j1 == ncb);
 #pragma unroll 1
       for (int c = 0; c < slab_w / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(lane_base + 2 * BWD_TN + c * 32, v);
         tmem_ld_wait();
+        if (whole) {
 #pragma unroll
-        for (int q = 0; q < 32; q += 4)
-          *reinterpret_cast<float4*>(out + c * 32 + q) =
-              make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
-                          __uint_as_float(v[q + 3]));
+          for (int q = 0; q < 32; q += 4)
+            *reinterpret_cast<float4*>(out + c * 32 + q) =
+                make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
+                            __uint_as_float(v[q + 3]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4)
+            red_add_f32x4(out + c * 32 + q, __uint_as_float(v[q]), __uint_as_float(v[q + 1]),
+                          __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+        }
       }
       tc_fence_before();
       mbar_arrive(acc_empty);
+      ++seg_iter;
     }
   }
 
@@ -748,25 +786,24 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   if (rc) return rc;
   const int nk = g.dim / KC, ncb = g.rows / BWD_TN, nrb = g.row_count / TM;
   const int n_slabs = (g.dim + SLAB - 1) / SLAB;
-  const int n_items = nrb * n_slabs;
+  const long long n_units_ll = (long long)nrb * n_slabs * ncb;
+  if (n_units_ll > 0x7fffffffLL) { set_error("crossclr_bwd: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
+  const int n_units = (int)n_units_ll;
   TimedLaunch timed(CROSSCLR_K_BWD, st);
   const bool resident = nk <= MAX_RES_CHUNKS;
   const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
   const size_t avail = kMaxSmem - 1024 - 2 * BWD_TN * 4 - kBarBytes - a_bytes;
-  // double-buffer the P tile when that still leaves a ring of >= 4 slots (D <= 256 resident, or streamed A)
-  int npbuf = 2;
-  int slots = (int)((avail - 4 * CHUNK_BYTES) / CHUNK_BYTES);
-  if (avail < 4 * CHUNK_BYTES || slots < 4) { npbuf = 1; slots = (int)((avail - 2 * CHUNK_BYTES) / CHUNK_BYTES); }
-  slots = std::min(slots & ~1, MAX_SLOTS);
-  const size_t smem = 1024 + a_bytes + (size_t)npbuf * 2 * CHUNK_BYTES + (size_t)slots * CHUNK_BYTES + 2 * BWD_TN * 4 +
-                      kBarBytes;
-  const int grid = std::min(n_items, sm_count());
+  const int slots = std::min((int)(avail / CHUNK_BYTES) & ~1, MAX_SLOTS);
+  const size_t smem = 1024 + a_bytes + (size_t)slots * CHUNK_BYTES + 2 * BWD_TN * 4 + kBarBytes;
+  const int grid = std::min(n_units, sm_count());
+  // CTAs own balanced unit ranges; a range that cuts an item adds its partial slab into dfhat
+  CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   if (resident) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_items, n_slabs, ncb, nk, slots, npbuf);
+    bwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_units, n_slabs, ncb, nk, slots);
   } else {
     CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_items, n_slabs, ncb, nk, slots, npbuf);
+    bwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_units, n_slabs, ncb, nk, slots);
   }
   return check_launch("bwd_tc_kernel");
 }

@@ -85,6 +85,18 @@ class _NativeOps:
         N.check(self.lib.crossclr_pack(_ptr(x), _DTYPE_CODE[x.dtype], x.stride(0), B, D, _ptr(feat_out),
                                        _DTYPE_CODE[feat_out.dtype], _ptr(rnorm_out), _stream()), "crossclr_pack")
 
+    def pack2(self, v, t, feat_out, rnorm_out):
+        B, D = v.shape
+        N.check(self.lib.crossclr_pack2(_ptr(v), _ptr(t), _DTYPE_CODE[v.dtype], v.stride(0), t.stride(0), B, D,
+                                        _ptr(feat_out), _DTYPE_CODE[feat_out.dtype], _ptr(rnorm_out), _stream()),
+                "crossclr_pack2")
+
+    def forward_single(self, prob, code, v, t, feat_all, rnorm, stats, coef, scal, loss):
+        """pack2 + fwd + finalize in one C call (single rank)."""
+        N.check(self.lib.crossclr_forward(ctypes.byref(prob), code, _ptr(v), _ptr(t), _DTYPE_CODE[v.dtype], v.stride(0),
+                                          t.stride(0), _ptr(feat_all), _ptr(rnorm), _ptr(stats), _ptr(coef), _ptr(scal),
+                                          _ptr(loss), _stream()), "crossclr_forward")
+
     def fwd(self, prob, code, feat_all, stats):
         N.check(self.lib.crossclr_fwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(stats), None, 0, _stream()),
                 "crossclr_fwd")
@@ -122,22 +134,20 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
         raise RuntimeError(f"tensor-core path needs B % 128 == 0 and D % 64 == 0 (got B={B}, D={D})")
     rows = 2 * world * B
     feat_all = torch.empty((2 * world, B, D), dtype=feat_dtype, device=dev)
-    feat_loc = feat_all[2 * rank:2 * rank + 2]
     rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
-    ops.pack(v, feat_loc[0], rnorm[:B])
-    ops.pack(t, feat_loc[1], rnorm[B:])
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1).clone(), group=group)
-    stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
-    ops.fwd(prob, code, feat_all, stats)
-    if world > 1:
-        import torch.distributed as dist
-        own = stats[2 * rank * B:2 * (rank + 1) * B].reshape(-1).clone()
-        dist.all_gather_into_tensor(stats.view(-1), own, group=group)
-    coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)
-    scal = torch.empty(4, dtype=torch.float32, device=dev)
+    small = torch.empty(4 * rows + 4, dtype=torch.float32, device=dev)      # stats | coef | scal
+    stats, coef, scal = small[:2 * rows].view(rows, 2), small[2 * rows:4 * rows].view(rows, 2), small[4 * rows:]
     loss = torch.empty((), dtype=torch.float64, device=dev)
+    if world == 1:
+        ops.forward_single(prob, code, v, t, feat_all, rnorm, stats, coef, scal, loss)
+        return loss, prob, code, (feat_all, rnorm, coef, scal)
+    import torch.distributed as dist
+    feat_loc = feat_all[2 * rank:2 * rank + 2]
+    ops.pack2(v, t, feat_loc, rnorm)
+    # in-place all-gather: rank r's block already sits at its slot of the output
+    dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1), group=group)
+    ops.fwd(prob, code, feat_all, stats)
+    dist.all_gather_into_tensor(stats.view(-1), stats[2 * rank * B:2 * (rank + 1) * B].reshape(-1), group=group)
     ops.finalize(prob, stats, coef, loss, scal)
     return loss, prob, code, (feat_all, rnorm, coef, scal)
 

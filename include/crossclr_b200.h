@@ -92,6 +92,24 @@ CROSSCLR_API int crossclr_pack(const void* x, int in_dtype, int64_t x_row_stride
                   void* feat_out, int feat_dtype, float* rnorm_out, void* stream);
 
 /*
+ * Both modality blocks of one rank in one launch: rows of `video` then rows of `text` are normalised into the
+ * rank's two consecutive segments starting at `feat_out` ([2*rows][dim]); `rnorm_out[2*rows]`.
+ * Replaces: trainer/loss.py:79-80.
+ */
+CROSSCLR_API int crossclr_pack2(const void* video, const void* text, int in_dtype, int64_t video_row_stride,
+                   int64_t text_row_stride, int32_t rows, int32_t dim, void* feat_out, int feat_dtype,
+                   float* rnorm_out, void* stream);
+
+/*
+ * Single-rank forward in one call (nseg == 2): crossclr_pack2 -> crossclr_fwd -> crossclr_finalize on `stream`.
+ * Buffers as in the individual calls: feat [2*bseg][dim] (dtype crossclr_feature_dtype(path)), rnorm [2*bseg],
+ * stats / coef [2*bseg][2], scal [4], loss_out double[1].  Replaces: trainer/loss.py:79-114 (forward).
+ */
+CROSSCLR_API int crossclr_forward(const crossclr_problem_t* p, int path, const void* video, const void* text, int in_dtype,
+                     int64_t video_row_stride, int64_t text_row_stride, void* feat, float* rnorm, float* stats,
+                     float* coef, float* scal, double* loss_out, void* stream);
+
+/*
  * Forward statistics of the owned rows.  For every owned stacked row g writes
  *   stats[2g+0] = X_g    = sum over the 2B-1 non-positive logits of 2^(logit*log2e - shift)
  *                          (includes the intra-modal diagonal, which is logit 0: loss.py:65,96-97)

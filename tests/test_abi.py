@@ -1,0 +1,76 @@
+"""CPU-side checks of the C-ABI boundary: the in-tree shared library loads, exports every symbol that
+include/crossclr_b200.h declares, and its argument validation / planning entry points (which never touch a
+device) behave.  No compute is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "crossclr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"CROSSCLR_API\s+[\w\s\*]+?\b(crossclr_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from crossmodal_contrastive_learning_b200 import _native as N
+    lib = N.load()
+    names = _declared_symbols()
+    assert len(names) >= 15, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(N.EXPORTS) == names           # the ctypes binding covers exactly the header
+    assert lib.crossclr_version() == 100
+
+
+def test_planning_and_validation_without_a_device():
+    from crossmodal_contrastive_learning_b200 import _native as N
+    lib = N.load()
+    P = N.Problem
+    ok = P(2, 4096, 512, 0, 8192, 0.03, 0.8)
+    assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 0) == N.PATH_TC
+    assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 1) == N.PATH_SIMT
+    ragged = P(2, 100, 72, 0, 200, 0.03, 0.8)
+    assert lib.crossclr_choose_path(ctypes.byref(ragged), N.F32, 0) == N.PATH_SIMT
+    assert lib.crossclr_feature_dtype(N.PATH_TC) == N.F16 and lib.crossclr_feature_dtype(N.PATH_SIMT) == N.F32
+    assert lib.crossclr_workspace_bytes(ctypes.byref(ok), N.PATH_TC) >= 8192 * 512 * 4
+    assert lib.crossclr_shift(ctypes.byref(ok)) == 0.0
+    small_tau = P(2, 128, 64, 0, 256, 0.0075, 0.8)
+    assert abs(lib.crossclr_shift(ctypes.byref(small_tau)) - (1.4426950408889634 / 0.0075 - 96.0)) < 1e-3
+    # rank 3 of 4 owns stacked rows [6 B, 8 B)
+    r3 = P(8, 256, 128, 6 * 256, 512, 0.03, 0.8)
+    assert lib.crossclr_choose_path(ctypes.byref(r3), N.BF16, 0) == N.PATH_TC
+    for bad in (P(3, 4, 4, 0, 8, 0.03, 0.8), P(2, 0, 4, 0, 0, 0.03, 0.8), P(2, 4, 4, 4, 8, 0.03, 0.8),
+                P(2, 4, 4, 0, 8, 0.0, 0.8), P(2, 4, 4, 0, 8, 0.03, float("nan"))):
+        assert lib.crossclr_choose_path(ctypes.byref(bad), N.F32, 0) == -1          # CROSSCLR_EINVAL
+        assert len(lib.crossclr_last_error()) > 0
+    assert lib.crossclr_fwd(ctypes.byref(ok), 7, None, None, None, 0, None) == -1
+    tot, n = ctypes.c_double(), ctypes.c_int64()
+    assert lib.crossclr_timing_read(99, ctypes.byref(tot), ctypes.byref(n)) == -1
+
+
+def test_module_surface_on_cpu():
+    import crossmodal_contrastive_learning_b200 as M
+    from trainer.loss import CrossCLR_onlyIntraModality
+    assert CrossCLR_onlyIntraModality is M.CrossCLR_onlyIntraModality
+    crit = CrossCLR_onlyIntraModality(temperature=0.07, negative_weight=0.5, logger="log")
+    assert (crit.temperature, crit.negative_w, crit.logger) == (0.07, 0.5, "log")
+    sd = crit.state_dict()
+    assert list(sd.keys()) == ["logit_scale"] and sd["logit_scale"].dtype == torch.float32 and sd["logit_scale"].item() == 1.0
+    assert [n for n, _ in crit.named_children()] == ["criterion"]
+    ref_like = {"logit_scale": torch.tensor(3.0)}
+    crit.load_state_dict(ref_like, strict=True)
+    # no CPU path: same exception class the reference raises for CPU inputs / bad shapes (RuntimeError)
+    with pytest.raises(RuntimeError):
+        crit(torch.randn(4, 8), torch.randn(4, 8))
+    with pytest.raises(RuntimeError):
+        crit(torch.randn(4, 8), torch.randn(5, 8))
+    with pytest.raises(RuntimeError):
+        crit(torch.randn(2, 4, 8), torch.randn(2, 4, 8))
+    with pytest.raises(ValueError):
+        CrossCLR_onlyIntraModality(path="cpu")

@@ -246,7 +246,9 @@ def test_b1_and_w0_and_small_tau():
         rloss, rdv, rdt = O.loss_and_grads(v, t, tau, 0.8)
         for path in ("simt", "tc"):
             loss, dv, dt = run_gpu(v, t, tau, 0.8, path=path)
-            check(loss, dv, dt, rloss, rdv, rdt, TOL)
+            # fp16 operand rounding of the unit rows perturbs each logit by ~1.7e-5/tau (DESIGN.md "Numerics"):
+            # the tensor-core path's gradient error grows as 1/tau and is ~1.3e-3 here
+            check(loss, dv, dt, rloss, rdv, rdt, TOL_SIMT if path == "simt" else 4e-3)
 
 
 def test_launch_counter_moves():
