@@ -26,7 +26,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -149,56 +148,65 @@ def run_reference_arm(args):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """SM clock / throttle reasons during the timed region, sampled by an `nvidia-smi -lms` child process (the
+    recipe of B200_PROFILING.md).  A child process, not a thread: NVML polling from this interpreter holds the GIL
+    and slows the Python launch path that is being timed.  Samples are filtered to the [begin(), end()] window."""
 
-    def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._thr = None
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index, period_ms=10):
+        import subprocess
+        self.t0 = self.t1 = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", str(period_ms)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.nv = None
+            self.proc = None
 
-    def _loop(self):
-        nv = self.nv
-        names = {
-            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
-        }
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            time.sleep(0.002)
+    def begin(self):
+        self.t0 = time.time()
 
-    def __enter__(self):
-        if self.nv is not None:
-            self._thr = threading.Thread(target=self._loop, daemon=True)
-            self._thr.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        if self._thr is not None:
-            self._thr.join()
+    def end(self):
+        self.t1 = time.time()
 
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            text, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return out
+        clocks, allclocks, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in text.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) != 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                mhz, mx = int(f[1]), int(f[2])
+            except ValueError:
+                continue
+            out["sm_max_mhz"] = mx
+            allclocks.append(mhz)
+            if self.t0 is not None and self.t0 - 0.005 <= ts <= self.t1 + 0.005:
+                clocks.append(mhz)
+                for n, v in zip(names, f[3:]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        use = clocks or allclocks
+        use.sort()
+        out.update(sm_mhz=(use[len(use) // 2] if use else None), reasons=sorted(reasons), samples=len(clocks),
+                   window_ms=round((self.t1 - self.t0) * 1e3, 1) if self.t0 else None)
+        return out
 
 
 def run_b200_arm(args):
@@ -280,6 +288,7 @@ def run_b200_arm(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    clk = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes a moment to produce its first sample
     for _ in range(max(args.warmup, 3)):
         step_resident()
     for _ in range(3):
@@ -287,11 +296,14 @@ def run_b200_arm(args):
     torch.cuda.synchronize()
 
     n0 = M.launch_count()
-    with ClockSampler(local_rank) as clk:
-        total_ms = timed(step_resident, args.steps)
+    if clk is not None:
+        clk.begin()
+    total_ms = timed(step_resident, args.steps)
+    if clk is not None:
+        clk.end()
     launches = M.launch_count() - n0
     e2e_ms = timed(step_e2e, args.steps)
-    loss_val = float(loss_host)
+    loss_val = float(loss_host.detach())
 
     # second pass with the library's per-kernel events on (its own stream-ordered cudaEvents)
     NAT.timing_enable(True)
@@ -353,14 +365,19 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shape", default=None, help="experiment override B,D (not a BASELINE config)")
     args = ap.parse_args()
     if args.workload is None:
         args.workload = "c2" if args.gpus == 1 else "c4"
+    if args.shape:
+        B, D = (int(x) for x in args.shape.split(","))
+        WORKLOADS["x"] = dict(B=B, D=D, desc=f"experiment B={B} D={D} bf16")
+        args.workload = "x"
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -1,0 +1,70 @@
+"""Multi-GPU parity (NCCL): the row-sharded criterion on world_size GPUs of one box against the oracle on the
+concatenated batch -- identical global loss on every rank, per-rank gradients of the GLOBAL loss.
+Skipped on boxes with one GPU (run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, B, D, path, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import crossmodal_contrastive_learning_b200 as M
+        g = torch.Generator().manual_seed(77)
+        v = torch.randn(B, D, generator=g).to(torch.bfloat16)
+        t = (v.float() + 2.0 * torch.randn(B, D, generator=g)).to(torch.bfloat16)
+        bl = B // world
+        vl = v[rank * bl:(rank + 1) * bl].float().cuda().requires_grad_()
+        tl = t[rank * bl:(rank + 1) * bl].float().cuda().requires_grad_()
+        crit = M.CrossCLR_onlyIntraModality(0.03, 0.8, process_group=dist.group.WORLD, path=path)
+        for _ in range(2):                       # twice: buffers are recycled by the caching allocator
+            vl.grad = tl.grad = None
+            loss = crit(vl, tl)
+            loss.backward()
+        torch.cuda.synchronize()
+        out[rank] = (loss.item(), vl.grad.double().cpu().numpy(), tl.grad.double().cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,D,path", [(1024, 256, "tc"), (512, 512, "tc"), (1024, 1024, "tc"), (384, 96, "simt")])
+def test_sharded_gpu_matches_global_oracle(B, D, path):
+    import torch.multiprocessing as mp
+    from oracle import crossclr_oracle as O
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    if path == "tc" and (B // world) % 128:
+        world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), B, D, path, out), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(77)
+    v = torch.randn(B, D, generator=g).to(torch.bfloat16)
+    t = (v.float() + 2.0 * torch.randn(B, D, generator=g)).to(torch.bfloat16)
+    rloss, rdv, rdt = O.loss_and_grads(v.float().numpy(), t.float().numpy(), 0.03, 0.8)
+    tol = 1e-3 if path == "tc" else 5e-5
+    bl = B // world
+    for r in range(world):
+        loss, dv, dt = out[r]
+        assert abs(loss - rloss) <= tol * abs(rloss) + 1e-7, (r, loss, rloss)
+        assert loss == out[0][0]                                         # bit-identical global loss on every rank
+        sl = slice(r * bl, (r + 1) * bl)
+        for a, b, n in ((dv, rdv[sl], "dv"), (dt, rdt[sl], "dt")):
+            rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+            assert rel <= tol, (r, n, rel)
