@@ -52,6 +52,15 @@ def measured_peaks():
         return 1590.0, 1400.0, "fallback"
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[workload]["bytes"]
+    except Exception:
+        return None
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -344,7 +353,7 @@ def run_b200_arm(args):
                     "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "bwd_tc_kernel", "achieved": achieved, "peak": burst,
-                         "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": None,
+                         "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": ncu_traffic(args.workload),
                          "peak_source": f"{src} bf16_tflops (burst; kernel timed alone with CUDA events)",
                          "algorithmic_flops_per_launch": alg_bwd, "avg_launch_ms": bwd_ms, "launches_timed": bwd_n,
                          "fwd_kernel": {"avg_launch_ms": fwd_ms, "algorithmic_flops_per_launch": alg_fwd,
