@@ -96,10 +96,13 @@ int crossclr_feature_dtype(int path) {
   return CROSSCLR_EINVAL;
 }
 
+static size_t workspace_bytes(const crossclr_problem_t* p, int path) {
+  return dfhat_bytes(p) + ((path == CROSSCLR_PATH_TC && p->dim <= 512) ? bwd_pair_scratch_bytes() : 0);
+}
+
 size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {
-  (void)path;
   if (validate_problem(p)) return 0;
-  return dfhat_bytes(p);
+  return workspace_bytes(p, path);
 }
 
 float crossclr_shift(const crossclr_problem_t* p) { return problem_shift(p); }
@@ -173,8 +176,8 @@ int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const 
   if (rc) return rc;
   CC_REQUIRE(feat && rnorm_owned && coef && scal && dv && dt, "crossclr_bwd: NULL pointer");
   CC_REQUIRE(dv_row_stride >= p->dim && dt_row_stride >= p->dim, "crossclr_bwd: output row stride < dim");
-  if (workspace == nullptr || workspace_bytes < dfhat_bytes(p)) {
-    set_error("crossclr_bwd: workspace too small (%zu < %zu)", workspace_bytes, dfhat_bytes(p));
+  if (workspace == nullptr || workspace_bytes < ::workspace_bytes(p, path)) {
+    set_error("crossclr_bwd: workspace too small (%zu < %zu)", workspace_bytes, ::workspace_bytes(p, path));
     return CROSSCLR_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -185,7 +188,7 @@ int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const 
   if (path == CROSSCLR_PATH_TC) {
     CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
                p->bseg, p->dim);
-    rc = launch_bwd_tc(g, feat, coef, scal, dfhat, st);
+    rc = launch_bwd_tc(g, feat, coef, scal, dfhat, (char*)workspace + dfhat_bytes(p), st);
     feat_dtype = CROSSCLR_F16;
     use_sigma = true;
   } else {

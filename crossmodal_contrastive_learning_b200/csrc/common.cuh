@@ -145,7 +145,8 @@ int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, cons
 // tc_kernels.cu
 int launch_fwd_tc(const Geometry& g, const void* feat_f16, float* stats, cudaStream_t st);
 int launch_bwd_tc(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
-                  cudaStream_t st);
+                  void* scratch, cudaStream_t st);
+size_t bwd_pair_scratch_bytes();   // global-memory P-tile rings of the paired backward (D <= 512)
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k);
 
 }  // namespace crossclr

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace crossclr {
@@ -598,11 +599,441 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
 }
 
 // ================================================================================================
+// Backward for D <= 512: a CLUSTER OF TWO CTAs per work range, specialised by role, so that S is formed once per
+// (row block, column block) instead of once per 256-wide slab of D.
+//   rank 0, "S-CTA": S = A_ib Fhat_J^T for a 256-column block J (N = 256 MMAs, two TMEM buffers) -> two epilogue
+//                    warpgroups ping-pong over the tiles and turn each into two 128-column fp16 probability tiles
+//                    P(j), written row-major into a small per-pair ring of scratch tiles in global memory (8 x 32 KiB,
+//                    L2-resident; distributed-shared-memory stores top out near 21 B/clk and stalled the exp warps);
+//                    a signaller warp publishes each tile (gpu-scope fence) with an arrival on the peer's mbarrier
+//   rank 1, "G-CTA": dF[128 x D] += P(j) Fhat_j   -- accumulator = up to all 512 TMEM columns; A = P(j) from its
+//                    shared memory, B = [64 j][64 d] TMA boxes of Fhat_j read MN-major, four boxes (N = 256) per
+//                    MMA group, four groups in flight; a loader warp TMA-loads each published P tile into one of 3
+//                    shared-memory buffers; tcgen05.commit hands the scratch slot back with a multicast arrival on
+//                    the S-CTA's mbarrier
+// Both CTAs walk the same balanced range of (row block, 256-column block) units; per unit each spends the same
+// 128*256*D MACs on its tensor core.  Shared-memory map (identical barrier block in both CTAs):
+//   [0, 1 KiB) mbarriers + TMEM slot | [1, 3 KiB) column coefficient vectors (S-CTA) |
+//   S-CTA: A row block (nk x 16 KiB) + ring of 32 KiB stages      G-CTA: 3 P tiles (32 KiB) + 4 groups of 4 x 8 KiB
+// ================================================================================================
+constexpr int PAIR_THREADS = 384;        // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int PAIR_EPI_THREADS = 256;
+constexpr int PAIR_TN = 256;             // S tile columns in the S-CTA
+constexpr int PAIR_PBUF = 3;             // 128-column P tiles in flight in the G-CTA's shared memory
+constexpr int PAIR_NSLOT = 8;            // scratch P tiles per pair in global memory (ring)
+constexpr int PTILE_BYTES = TM * BWD_TN * 2;   // 32 KiB
+constexpr int PAIR_GGROUPS = 4;          // G-CTA ring: groups of four [64 j][64 d] boxes
+constexpr int GBOX_BYTES = 64 * KC * 2;  // 8 KiB
+constexpr int PAIR_HDR = 3072;
+
+struct PairSeg { int ib, j0, j1; bool last_of_ib; };
+struct PairWalk {
+  int u, u_end, ncb;
+  __device__ PairWalk(int u0, int u1, int ncb_) : u(u0), u_end(u1), ncb(ncb_) {}
+  __device__ __forceinline__ bool next(PairSeg& s) {
+    if (u >= u_end) return false;
+    s.ib = u / ncb;
+    s.j0 = u - s.ib * ncb;
+    s.j1 = min(ncb, s.j0 + (u_end - u));
+    u += s.j1 - s.j0;
+    s.last_of_ib = (u >= u_end) || (u / ncb != s.ib);
+    return true;
+  }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64, Geometry g,
+                const float* __restrict__ coef,
+                const float* __restrict__ scal, float* __restrict__ dfhat, uint8_t* __restrict__ scratch, int n_units,
+                int ncb, int nk, int s_stages, int exp_flags, unsigned long long* __restrict__ trace) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  // debug timeline (CROSSCLR_PAIR_TRACE): pair 0 stamps clock64 per role / tile / event
+  auto TR = [&](int role, int tile, int ev) {
+    if (trace != nullptr && blockIdx.x < 2 && tile < 64) trace[(role * 64 + tile) * 4 + ev] = clock64();
+  };
+  auto full_bar = [&](int s) { return base + 8u * s; };
+  auto empty_bar = [&](int s) { return base + 96u + 8u * s; };
+  const uint32_t a_full = base + 192u, a_empty = base + 200u;
+  auto sfull_bar = [&](int b) { return base + 208u + 8u * b; };
+  auto sempty_bar = [&](int b) { return base + 224u + 8u * b; };
+  auto staged_bar = [&](int b) { return base + 240u + 8u * b; };     // S-CTA: a P tile's 128 rows are in global memory
+  auto pready_bar = [&](int b) { return base + 304u + 8u * b; };     // G-CTA: that tile is published (remote arrival)
+  auto pempty_bar = [&](int b) { return base + 368u + 8u * b; };     // S-CTA: scratch slot consumed (multicast commit)
+  auto pbfull_bar = [&](int b) { return base + 432u + 8u * b; };     // G-CTA: P tile landed in a smem buffer (TMA)
+  auto pbempty_bar = [&](int b) { return base + 456u + 8u * b; };    // G-CTA: smem buffer consumed
+  const uint32_t acc_full = base + 480u, acc_empty = base + 488u;
+  const uint32_t tmem_slot = base + 496u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 496);
+  float* cvec = reinterpret_cast<float*>(smem_raw + 1024);          // [2][256]
+  const uint32_t data = base + PAIR_HDR;
+
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int u_begin = (int)((long long)pair * n_units / npairs);
+  const int u_end = (int)((long long)(pair + 1) * n_units / npairs);
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap); prefetch_tmap(&tmap64); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), EPI_THREADS); }
+    for (int b = 0; b < PAIR_NSLOT; ++b) {
+      mbar_init(staged_bar(b), EPI_THREADS); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), 1);
+    }
+    for (int b = 0; b < PAIR_PBUF; ++b) { mbar_init(pbfull_bar(b), 1); mbar_init(pbempty_bar(b), 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, PAIR_EPI_THREADS);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // both CTAs' barriers are initialised before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (rank == 0 && (exp_flags & 8)) {
+    // perf experiment: S-CTA idle
+  } else if (rank == 1 && (exp_flags & 4)) {
+    // perf experiment: G-CTA idle
+  } else if (rank == 0) {
+    // =========================================================================== S-CTA
+    const uint32_t a_region = data;
+    const uint32_t ring_base = data + nk * CHUNK_BYTES;
+    const uint32_t stage_bytes = 2 * CHUNK_BYTES;
+    if (warp == 0) {
+      Ring ring(s_stages);
+      int cur_ib = -1;
+      uint32_t a_cnt = 0;
+      PairWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        const int row0 = g.row_begin + sg.ib * TM;
+        if (sg.ib != cur_ib) {
+          mbar_wait(a_empty, (a_cnt & 1) ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(a_full, nk * CHUNK_BYTES);
+            for (int kc = 0; kc < nk; ++kc) tma_load_2d(a_region + kc * CHUNK_BYTES, &tmap, a_full, kc * KC, row0);
+          }
+          __syncwarp();
+          cur_ib = sg.ib; ++a_cnt;
+        }
+        for (int j = sg.j0; j < sg.j1; ++j) {
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+            if (elect_one()) {
+              const uint32_t st = ring_base + ring.stage * stage_bytes;
+              mbar_arrive_expect_tx(full_bar(ring.stage), stage_bytes);
+              tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, j * PAIR_TN);
+              tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, j * PAIR_TN + TM);
+            }
+            __syncwarp();
+            ring.advance();
+          }
+        }
+      }
+    } else if (warp == 1) {
+      Ring ring(s_stages);
+      int cur_ib = -1;
+      uint32_t a_cnt = 0, t = 0;
+      PairWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        if (sg.ib != cur_ib) {
+          mbar_wait(a_full, a_cnt & 1);
+          cur_ib = sg.ib; ++a_cnt;
+        }
+        for (int j = sg.j0; j < sg.j1; ++j, ++t) {
+          const uint32_t buf = t & 1;
+          if (lane == 0) TR(0, t, 0);
+          mbar_wait(sempty_bar(buf), ((t >> 1) & 1) ^ 1);
+          if (lane == 0) TR(0, t, 1);
+          tc_fence_after();
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(full_bar(ring.stage), ring.phase);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_s_chunk(tmem_base + buf * PAIR_TN, a_region + kc * CHUNK_BYTES, ring_base + ring.stage * stage_bytes,
+                            kIdescS256, kc == 0);
+              umma_commit(empty_bar(ring.stage));
+            }
+            __syncwarp();
+            ring.advance();
+          }
+          if (elect_one()) {
+            umma_commit(sfull_bar(buf));
+            if (sg.last_of_ib && j + 1 == sg.j1) umma_commit(a_empty);
+          }
+          if (lane == 0) TR(0, t, 2);
+          __syncwarp();
+        }
+      }
+    } else if (warp == 3) {
+      // signaller: once the 128 rows of P tile th are in global memory (staged), make them visible GPU-wide and tell
+      // the G-CTA's loader warp
+      const uint32_t pready_remote = mapa_cluster(pready_bar(0), 1);
+      const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
+      for (uint32_t th = 0; th < n_ptiles; ++th) {
+        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
+        mbar_wait(staged_bar(slot), use & 1);
+        if (elect_one()) {
+          fence_acq_rel_gpu();
+          mbar_arrive_cluster_relaxed(pready_remote + 8u * slot);
+        }
+        __syncwarp();
+      }
+    } else if (warp >= EPI_WARP0) {
+      // Two epilogue warpgroups ping-pong over the S tiles (wg handles tiles t with (t & 1) == wg, i.e. TMEM buffer
+      // wg), so one group's load / barrier latencies overlap the other group's exp work.  Tile t is unit
+      // u_begin + t of this pair; it yields the 128-column P tiles 2t and 2t + 1.
+      const int quad = warp & 3, wg = (warp - EPI_WARP0) >> 2;
+      const int r = quad * 32 + lane;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + wg * PAIR_TN;
+      const float sigma = scal[0];
+      const float nshift = -g.shift;
+      // scratch P tile layout = the no-swizzle K-major operand layout: [16 column chunks of 8][128 rows][16 bytes], so
+      // one warp store instruction (32 rows x 16 B) writes 512 contiguous bytes
+      uint8_t* const p_scratch = scratch + (size_t)pair * PAIR_NSLOT * PTILE_BYTES + (size_t)r * 16;
+      const int n_tiles = u_end - u_begin;
+      int cur_ib = -1, gi = 0;
+      BlockSeg bi{0, 0};
+      float iz_i = 0.f;
+      float* cv = cvec + wg * PAIR_TN;
+      // column coefficients of this thread's two columns for the group's next tile, fetched one tile ahead
+      float izj0 = 0.f, izj1 = 0.f;
+      if (wg < n_tiles) {
+        const int jn = (u_begin + wg) % ncb;
+        izj0 = coef[2 * (int64_t)(jn * PAIR_TN + r)];
+        izj1 = coef[2 * (int64_t)(jn * PAIR_TN + TM + r)];
+      }
+      for (int t = wg; t < n_tiles; t += 2) {
+        const int u = u_begin + t;
+        const int ib = u / ncb, j = u - ib * ncb;
+        if (ib != cur_ib) {
+          cur_ib = ib;
+          const int row0 = g.row_begin + ib * TM;
+          gi = row0 + r;
+          bi = block_seg(row0, g.bseg);
+          iz_i = coef[2 * (int64_t)gi];
+        }
+        const BlockSeg bj0 = block_seg(j * PAIR_TN, g.bseg), bj1 = block_seg(j * PAIR_TN + TM, g.bseg);
+        const float ks0 = ((bj0.mod == bi.mod) ? g.w : 1.0f) * sigma, ks1 = ((bj1.mod == bi.mod) ? g.w : 1.0f) * sigma;
+        cv[r] = izj0 * ks0;                                        // kappa*sigma / Z_j of the tile's 256 columns
+        cv[TM + r] = izj1 * ks1;
+        if (t + 2 < n_tiles) {
+          const int jn = (u + 2) % ncb;
+          izj0 = coef[2 * (int64_t)(jn * PAIR_TN + r)];
+          izj1 = coef[2 * (int64_t)(jn * PAIR_TN + TM + r)];
+        }
+        named_bar_sync(1 + wg, EPI_THREADS);
+        if (r == 0) TR(1 + wg, t >> 1, 0);
+        mbar_wait(sfull_bar(wg), ((uint32_t)t >> 1) & 1);
+        if (r == 0) TR(1 + wg, t >> 1, 1);
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base, va);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                              // the two 128-column P tiles of this S tile
+          const BlockSeg bj = h ? bj1 : bj0;
+          const bool same_mod = (bj.mod == bi.mod);
+          const bool diag_tile = (bj.samp0 == bi.samp0);
+          const float k = same_mod ? g.k_intra : g.k_inter;
+          const float a_i = iz_i * (h ? ks1 : ks0);
+          const uint32_t th = 2u * (uint32_t)t + h;                // P tile index of this pair
+          const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
+          if (!(exp_flags & 2)) mbar_wait(pempty_bar(slot), (use & 1) ^ 1);   // the dF that read this scratch slot is done
+          uint8_t* const prow = p_scratch + (size_t)slot * PTILE_BYTES;       // this thread's 16 bytes of column chunk 0
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int c = h * 4 + c4;                               // 32-column chunk of the S tile (0..7)
+            uint32_t (&v)[32] = (c & 1) ? vb : va;
+            tmem_ld_wait();
+            if (c + 1 < 8) tmem_ld32(lane_base + (c + 1) * 32, (c & 1) ? va : vb);
+            uint32_t packed[16];
+            const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              const float4 cc = cv4[q >> 2];
+              float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
+              float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
+              float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
+              float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
+              if (diag_tile) {                                     // same-sample pair handled in grad_finish
+                const int cbase = c4 * 32 + q;
+                if (cbase + 0 == r) e0 = 0.f;
+                if (cbase + 1 == r) e1 = 0.f;
+                if (cbase + 2 == r) e2 = 0.f;
+                if (cbase + 3 == r) e3 = 0.f;
+              }
+              __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+              packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
+              packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              if (!(exp_flags & 1) || packed[ch * 4] == 0x7fff7fffu)    // exp bit0: perf experiment without the stores
+                st_global_v4(prow + (c4 * 4 + ch) * (TM * 16), packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2],
+                             packed[ch * 4 + 3]);
+          }
+          fence_proxy_async_global();                              // these generic-proxy writes will be read by TMA
+          mbar_arrive(staged_bar(slot));
+          if (r == 0) TR(1 + wg, t >> 1, 2 + h);
+        }
+        tc_fence_before();
+        mbar_arrive(sempty_bar(wg));
+      }
+    }
+  } else {
+    // =========================================================================== G-CTA
+    const uint32_t p_tiles = data;
+    const uint32_t ring_base = data + PAIR_PBUF * 2 * CHUNK_BYTES;
+    const uint32_t group_bytes = 4 * GBOX_BYTES;
+    const int ndg = (nk + 3) / 4;                     // d-groups of up to four 64-wide boxes (N = 64 * boxes <= 256)
+    if (warp == 0) {
+      Ring ring(PAIR_GGROUPS);
+      PairWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh) {           // 128-column P tiles
+          for (int dg = 0; dg < ndg; ++dg) {
+            const int nb = min(4, nk - dg * 4);
+            for (int kh = 0; kh < 2; ++kh) {                        // 64-row halves of the K = 128 j rows
+              mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+              if (elect_one()) {
+                const uint32_t st = ring_base + ring.stage * group_bytes;
+                mbar_arrive_expect_tx(full_bar(ring.stage), nb * GBOX_BYTES);
+                for (int q = 0; q < nb; ++q)
+                  tma_load_2d(st + q * GBOX_BYTES, &tmap64, full_bar(ring.stage), (dg * 4 + q) * KC, jh * TM + kh * 64);
+              }
+              __syncwarp();
+              ring.advance();
+            }
+          }
+        }
+      }
+    } else if (warp == 3) {
+      // P loader: published scratch tile -> one of the 3 shared-memory P buffers (two [128][64] swizzled boxes)
+      const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
+      for (uint32_t th = 0; th < n_ptiles; ++th) {
+        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
+        const uint32_t pb = th % PAIR_PBUF, puse = th / PAIR_PBUF;
+        if (lane == 0) TR(4, th, 0);
+        if (!(exp_flags & 2)) mbar_wait_cluster(pready_bar(slot), use & 1);
+        if (lane == 0) TR(4, th, 1);
+        fence_proxy_async_global();
+        mbar_wait(pbempty_bar(pb), (puse & 1) ^ 1);
+        if (lane == 0) TR(4, th, 2);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(pbfull_bar(pb), PTILE_BYTES);
+          bulk_load_1d(p_tiles + pb * PTILE_BYTES, scratch + ((size_t)pair * PAIR_NSLOT + slot) * PTILE_BYTES, PTILE_BYTES,
+                       pbfull_bar(pb));
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      Ring ring(PAIR_GGROUPS);
+      uint32_t th = 0, seg_iter = 0;
+      PairWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        mbar_wait(acc_empty, (seg_iter & 1) ^ 1);       // the drain warps have emptied the previous segment's slab
+        tc_fence_after();
+        for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh, ++th) {
+          const uint32_t pb = th % PAIR_PBUF, puse = th / PAIR_PBUF;
+          const uint32_t slot = th % PAIR_NSLOT;
+          if (lane == 0) TR(5, th, 0);
+          mbar_wait(pbfull_bar(pb), puse & 1);          // the P tile has landed in shared memory (TMA)
+          if (lane == 0) TR(5, th, 1);
+          tc_fence_after();
+          const uint32_t p_tile = p_tiles + pb * PTILE_BYTES;
+          for (int dg = 0; dg < ndg; ++dg) {
+            const int nb = min(4, nk - dg * 4);
+            const uint32_t idesc = make_idesc_f16(128, 64 * nb, 0, 0, 0, 1);
+            for (int kh = 0; kh < 2; ++kh) {
+              mbar_wait(full_bar(ring.stage), ring.phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t st = ring_base + ring.stage * group_bytes;
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  // A = P[:, 64 kh + 16 k16 .. +16): no-swizzle K-major, column chunks 8 kh + 2 k16 and the next one
+                  // (2048 bytes apart), 8-row groups 128 bytes apart; B = Fhat rows 64 kh + 16 k16 .. +16 of the
+                  // [64 j][64 d] boxes, MN-major: 16 K rows = 2048 bytes, next 64-wide MN atom = next box
+                  const uint64_t ad = make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * (TM * 16), TM * 16, 128);
+                  const uint64_t bd = make_smem_desc_sw128(st + k16 * 2048, 1024, GBOX_BYTES);
+                  umma_ss(tmem_base + dg * 256, ad, bd, idesc, (jh > 2 * sg.j0 || kh > 0 || k16 > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(ring.stage));
+              }
+              __syncwarp();
+              ring.advance();
+            }
+          }
+          if (elect_one()) {
+            umma_commit(pbempty_bar(pb));
+            umma_commit_multicast(pempty_bar(slot), (uint16_t)1);   // scratch slot free -> the S-CTA (cluster rank 0)
+          }
+          if (lane == 0) TR(5, th, 2);
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(acc_full);
+        __syncwarp();
+        ++seg_iter;
+      }
+    } else if (warp >= EPI_WARP0) {
+      const int quad = warp & 3, wg = (warp - EPI_WARP0) >> 2;      // wg: which 256-column half of the slab
+      const int r = quad * 32 + lane;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+      uint32_t seg_iter = 0;
+      PairWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        const int gi = g.row_begin + sg.ib * TM + r;
+        mbar_wait(acc_full, seg_iter & 1);
+        tc_fence_after();
+        float* out = dfhat + (int64_t)(gi - g.row_begin) * g.dim;
+        const bool whole = (sg.j0 == 0 && sg.j1 == ncb);
+        const int c_end = min(g.dim, wg * 256 + 256) / 32;
+#pragma unroll 1
+        for (int c = wg * 8; c < c_end; ++c) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c * 32, v);
+          tmem_ld_wait();
+          if (whole) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              *reinterpret_cast<float4*>(out + c * 32 + q) =
+                  make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
+                              __uint_as_float(v[q + 3]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              red_add_f32x4(out + c * 32 + q, __uint_as_float(v[q]), __uint_as_float(v[q + 1]),
+                            __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+        ++seg_iter;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // neither CTA leaves while its peer may still touch its shared memory
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ================================================================================================
 // Self-test kernel: one CTA, D[128][n] = A[128][k] * B^T with the operand forms the real kernels use.
 //   variant 0: A, B K-major from TMA tiles (the S product)
 //   variant 1: A K-major written by threads with the swizzle formula (the P tile), B MN-major TMA tiles
 //              (b_host is [k][n], n in {64, 128, 256}: n/64 boxes of [k rows][64], LBO = box size)  (the dF product)
-//   variant 2: A from TMEM (tcgen05.st packed fp16 pairs), B K-major  (candidate for a later revision)
+//   variant 2: A from TMEM (tcgen05.st packed fp16 pairs), B K-major  (the single-CTA backward's P operand)
+//   variant 3: A K-major WITHOUT swizzle, written by threads as [k/8][128 rows][16 B] (the paired backward's P), B K-major
 // ================================================================================================
 __global__ void __launch_bounds__(128, 1)
 selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int variant,
@@ -634,6 +1065,15 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const uint32_t addr = a_s + atom * CHUNK_BYTES + r * 128 + (((uint32_t)ch ^ (uint32_t)(r & 7)) * 16);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
       }
+    fence_proxy_async_smem();
+  }
+  if (variant == 3) {
+    // A in the no-swizzle K-major layout the paired backward uses for P: [k/8 column chunks][128 rows][16 bytes]
+    for (int ch = 0; ch < k / 8; ++ch) {
+      const uint4 val = *reinterpret_cast<const uint4*>(a_gmem + (size_t)r * k + ch * 8);
+      const uint32_t addr = a_s + ch * 2048 + r * 16;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+    }
     fence_proxy_async_smem();
   }
   if (variant == 2) {
@@ -676,6 +1116,11 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       for (int k16 = 0; k16 < k / 16; ++k16)
         umma_ss(tmem_base, kmajor_desc(a_s + (k16 >> 2) * CHUNK_BYTES + (k16 & 3) * 32),
                 make_smem_desc_sw128(b_s + k16 * 2048, 1024, (uint32_t)k * 128u), idesc, k16 ? 1u : 0u);
+    } else if (variant == 3) {
+      const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
+      for (int k16 = 0; k16 < k / 16; ++k16)
+        umma_ss(tmem_base, make_smem_desc_nosw(a_s + k16 * 2 * 2048, 2048, 128),
+                kmajor_desc(b_s + (k16 >> 2) * bchunk) + (k16 & 3) * 2, idesc, k16 ? 1u : 0u);
     } else {
       const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
       for (int kc = 0; kc < nk; ++kc)
@@ -752,6 +1197,16 @@ int sm_count() {
 }
 
 constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;
+
+// CROSSCLR_BWD_VARIANT=1 forces the single-CTA slab kernel for D <= 512 (A/B measurements, tests); default 0.
+int bwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CROSSCLR_BWD_VARIANT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
 constexpr size_t kMaxSmem = 232448;      // 227 KiB opt-in dynamic shared memory per CTA
 
 }  // namespace
@@ -779,11 +1234,78 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   return check_launch("fwd_tc_kernel");
 }
 
+// How many 2-CTA clusters of bwd_pair_kernel can be resident at once (<= SMs / 2; a GPC with an odd SM count
+// strands one SM).  Queried once per process.
+static int pair_clusters_resident() {
+  static int n = 0;
+  if (n == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (sm_count() / 2));
+    cfg.blockDim = dim3(PAIR_THREADS);
+    cfg.dynamicSmemBytes = kMaxSmem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int c = 0;
+    cudaFuncSetAttribute(bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (cudaOccupancyMaxActiveClusters(&c, bwd_pair_kernel, &cfg) != cudaSuccess || c <= 0) {
+      (void)cudaGetLastError();
+      c = sm_count() / 2;
+    }
+    n = std::min(c, sm_count() / 2);
+  }
+  return n;
+}
+
+size_t bwd_pair_scratch_bytes() { return (size_t)(sm_count() / 2) * PAIR_NSLOT * PTILE_BYTES; }
+
+static int launch_bwd_pair(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
+                           const float* scal, float* dfhat, void* scratch, cudaStream_t st) {
+  CUtensorMap tmap64;                     // [64 rows][64 cols] boxes for the G-CTA's MN-major operand groups
+  int rc = make_tmap_f16(&tmap64, feat, (uint64_t)g.rows, (uint64_t)g.dim, 64);
+  if (rc) return rc;
+  const int nk = g.dim / KC, ncb = g.rows / PAIR_TN, nrb = g.row_count / TM;
+  const long long n_units_ll = (long long)nrb * ncb;
+  if (n_units_ll > 0x7fffffffLL) { set_error("crossclr_bwd: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
+  const int n_units = (int)n_units_ll;
+  CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  const int s_stages = std::min((int)((kMaxSmem - PAIR_HDR - (size_t)nk * CHUNK_BYTES) / (2 * CHUNK_BYTES)), MAX_SLOTS);
+  const int npairs = std::min(n_units, pair_clusters_resident());
+  CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
+  static const int exp_flags = getenv("CROSSCLR_PAIR_EXP") ? atoi(getenv("CROSSCLR_PAIR_EXP")) : 0;
+  static unsigned long long* trace = nullptr;
+  static const bool want_trace = getenv("CROSSCLR_PAIR_TRACE") != nullptr;
+  if (want_trace && trace == nullptr) { cudaMalloc(&trace, 6 * 64 * 4 * 8); }
+  if (want_trace) cudaMemsetAsync(trace, 0, 6 * 64 * 4 * 8, st);
+  bwd_pair_kernel<<<2 * npairs, PAIR_THREADS, kMaxSmem, st>>>(tmap, tmap64, g, coef, scal, dfhat,
+                                                              (uint8_t*)scratch, n_units, ncb, nk, s_stages, exp_flags,
+                                                              trace);
+  if (want_trace) {
+    static unsigned long long host[6 * 64 * 4];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("CROSSCLR_PAIR_TRACE"), "w");
+    if (f) {
+      for (int role = 0; role < 6; ++role)
+        for (int t = 0; t < 64; ++t)
+          fprintf(f, "%d %d %llu %llu %llu %llu\n", role, t, host[(role * 64 + t) * 4], host[(role * 64 + t) * 4 + 1],
+                  host[(role * 64 + t) * 4 + 2], host[(role * 64 + t) * 4 + 3]);
+      fclose(f);
+    }
+  }
+  return check_launch("bwd_pair_kernel");
+}
+
 int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const float* scal, float* dfhat,
-                  cudaStream_t st) {
+                  void* scratch, cudaStream_t st) {
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
+  if (g.dim <= 512 && bwd_variant() != 1) {          // whole D fits one accumulator: role-specialised CTA pairs
+    TimedLaunch timed(CROSSCLR_K_BWD, st);
+    return launch_bwd_pair(tmap, feat, g, coef, scal, dfhat, scratch, st);
+  }
   const int nk = g.dim / KC, ncb = g.rows / BWD_TN, nrb = g.row_count / TM;
   const int n_slabs = (g.dim + SLAB - 1) / SLAB;
   const long long n_units_ll = (long long)nrb * n_slabs * ncb;
@@ -809,7 +1331,7 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
 }
 
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k) {
-  if (variant < 0 || variant > 2 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
+  if (variant < 0 || variant > 3 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
       (variant == 1 && n % 64 != 0)) {
     set_error("crossclr_selftest: unsupported variant/shape (variant %d n %d k %d)", variant, n, k);
     return CROSSCLR_EINVAL;

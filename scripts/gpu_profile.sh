@@ -6,7 +6,7 @@ WL=${1:-c2}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$WL.csv \
     python bench.py --steps 3 --warmup 3 --workload $WL --no-cpu-baseline > gpurun_out/ncu_bench_$WL.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'fwd_tc_kernel|bwd_tc_kernel' -s 6 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:'fwd_tc_kernel|bwd_tc_kernel|bwd_pair_kernel' -s 6 -c 2 \
     -f -o gpurun_out/prof_$WL python bench.py --steps 2 --warmup 3 --workload $WL --no-cpu-baseline > gpurun_out/ncu_full_$WL.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out

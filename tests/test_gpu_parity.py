@@ -59,7 +59,7 @@ TC_OK = [p for p in FULL if (lambda g: g["v"].shape[0] % 128 == 0 and g["v"].sha
 # ---------------------------------------------------------------------------------------------
 # tcgen05 / TMA building blocks
 @pytest.mark.parametrize("variant,n,k", [(0, 128, 64), (0, 128, 256), (0, 64, 128), (0, 256, 128), (1, 64, 128),
-                                         (1, 64, 64), (1, 128, 128), (1, 256, 128), (2, 128, 128)])
+                                         (1, 64, 64), (1, 128, 128), (1, 256, 128), (2, 128, 128), (3, 128, 128), (3, 64, 64)])
 def test_tc_selftest(variant, n, k):
     import ctypes
     lib = _mod().load_native()
