@@ -851,6 +851,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             uint32_t (&v)[32] = (c & 1) ? vb : va;
             tmem_ld_wait();
             if (c + 1 < 8) tmem_ld32(lane_base + (c + 1) * 32, (c & 1) ? va : vb);
+            else { tc_fence_before(); mbar_arrive(sempty_bar(wg)); }   // whole S tile is in registers: free the buffer
             uint32_t packed[16];
             const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
@@ -881,8 +882,6 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           mbar_arrive(staged_bar(slot));
           if (r == 0) TR(1 + wg, t >> 1, 2 + h);
         }
-        tc_fence_before();
-        mbar_arrive(sempty_bar(wg));
       }
     }
   } else {
@@ -1302,7 +1301,7 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
-  if (g.dim <= 512 && bwd_variant() != 1) {          // whole D fits one accumulator: role-specialised CTA pairs
+  if (g.dim > 256 && g.dim <= 512 && bwd_variant() != 1) {   // two slabs would recompute S: role-specialised CTA pairs
     TimedLaunch timed(CROSSCLR_K_BWD, st);
     return launch_bwd_pair(tmap, feat, g, coef, scal, dfhat, scratch, st);
   }
