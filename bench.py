@@ -352,7 +352,7 @@ def run_b200_arm(args):
             "e2e": {"value": Bg / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": ("bwd_pair_kernel" if 256 < D <= 512 else "bwd_tc_kernel"),
+            "roofline": {"bound": "tensor", "kernel": ("bwd_pair_kernel" if 256 < D <= 1536 else "bwd_tc_kernel"),
                          "achieved": achieved, "peak": burst,
                          "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": ncu_traffic(args.workload),
                          "peak_source": f"{src} bf16_tflops (burst; kernel timed alone with CUDA events)",

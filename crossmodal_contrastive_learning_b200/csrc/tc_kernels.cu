@@ -641,7 +641,8 @@ struct PairWalk {
   }
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+template <bool kResident>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
 bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64, Geometry g,
                 const float* __restrict__ coef,
                 const float* __restrict__ scal, float* __restrict__ dfhat, uint8_t* __restrict__ scratch, int n_units,
@@ -670,8 +671,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t data = base + PAIR_HDR;
 
   const uint32_t rank = cluster_ctarank();
+  const uint32_t csize = cluster_nctarank();          // 1 S-CTA + (csize - 1) G-CTAs, one per 512-wide slab of D
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair = blockIdx.x / csize, npairs = gridDim.x / csize;
   const int u_begin = (int)((long long)pair * n_units / npairs);
   const int u_end = (int)((long long)(pair + 1) * n_units / npairs);
 
@@ -681,7 +683,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), EPI_THREADS); }
     for (int b = 0; b < PAIR_NSLOT; ++b) {
-      mbar_init(staged_bar(b), EPI_THREADS); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), 1);
+      mbar_init(staged_bar(b), EPI_THREADS); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), csize - 1);
     }
     for (int b = 0; b < PAIR_PBUF; ++b) { mbar_init(pbfull_bar(b), 1); mbar_init(pbempty_bar(b), 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, PAIR_EPI_THREADS);
@@ -696,13 +698,13 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
   if (rank == 0 && (exp_flags & 8)) {
     // perf experiment: S-CTA idle
-  } else if (rank == 1 && (exp_flags & 4)) {
+  } else if (rank >= 1 && (exp_flags & 4)) {
     // perf experiment: G-CTA idle
   } else if (rank == 0) {
     // =========================================================================== S-CTA
     const uint32_t a_region = data;
-    const uint32_t ring_base = data + nk * CHUNK_BYTES;
-    const uint32_t stage_bytes = 2 * CHUNK_BYTES;
+    const uint32_t ring_base = data + (kResident ? nk * CHUNK_BYTES : 0);
+    const uint32_t stage_bytes = (kResident ? 2 : 3) * CHUNK_BYTES;     // [A chunk, streamed] + 256-row B chunk
     if (warp == 0) {
       Ring ring(s_stages);
       int cur_ib = -1;
@@ -711,7 +713,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       PairSeg sg;
       while (walk.next(sg)) {
         const int row0 = g.row_begin + sg.ib * TM;
-        if (sg.ib != cur_ib) {
+        if (kResident && sg.ib != cur_ib) {
           mbar_wait(a_empty, (a_cnt & 1) ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(a_full, nk * CHUNK_BYTES);
@@ -724,8 +726,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
             if (elect_one()) {
-              const uint32_t st = ring_base + ring.stage * stage_bytes;
+              uint32_t st = ring_base + ring.stage * stage_bytes;
               mbar_arrive_expect_tx(full_bar(ring.stage), stage_bytes);
+              if (!kResident) { tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0); st += CHUNK_BYTES; }
               tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, j * PAIR_TN);
               tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, j * PAIR_TN + TM);
             }
@@ -741,7 +744,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       PairWalk walk(u_begin, u_end, ncb);
       PairSeg sg;
       while (walk.next(sg)) {
-        if (sg.ib != cur_ib) {
+        if (kResident && sg.ib != cur_ib) {
           mbar_wait(a_full, a_cnt & 1);
           cur_ib = sg.ib; ++a_cnt;
         }
@@ -755,8 +758,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             mbar_wait(full_bar(ring.stage), ring.phase);
             tc_fence_after();
             if (elect_one()) {
-              issue_s_chunk(tmem_base + buf * PAIR_TN, a_region + kc * CHUNK_BYTES, ring_base + ring.stage * stage_bytes,
-                            kIdescS256, kc == 0);
+              const uint32_t st = ring_base + ring.stage * stage_bytes;
+              issue_s_chunk(tmem_base + buf * PAIR_TN, kResident ? a_region + kc * CHUNK_BYTES : st,
+                            kResident ? st : st + CHUNK_BYTES, kIdescS256, kc == 0);
               umma_commit(empty_bar(ring.stage));
             }
             __syncwarp();
@@ -764,7 +768,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           }
           if (elect_one()) {
             umma_commit(sfull_bar(buf));
-            if (sg.last_of_ib && j + 1 == sg.j1) umma_commit(a_empty);
+            if (kResident && sg.last_of_ib && j + 1 == sg.j1) umma_commit(a_empty);
           }
           if (lane == 0) TR(0, t, 2);
           __syncwarp();
@@ -773,14 +777,13 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     } else if (warp == 3) {
       // signaller: once the 128 rows of P tile th are in global memory (staged), make them visible GPU-wide and tell
       // the G-CTA's loader warp
-      const uint32_t pready_remote = mapa_cluster(pready_bar(0), 1);
       const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
       for (uint32_t th = 0; th < n_ptiles; ++th) {
         const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
         mbar_wait(staged_bar(slot), use & 1);
         if (elect_one()) {
           fence_acq_rel_gpu();
-          mbar_arrive_cluster_relaxed(pready_remote + 8u * slot);
+          for (uint32_t gr = 1; gr < csize; ++gr) mbar_arrive_cluster_relaxed(mapa_cluster(pready_bar(slot), gr));
         }
         __syncwarp();
       }
@@ -889,7 +892,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const uint32_t p_tiles = data;
     const uint32_t ring_base = data + PAIR_PBUF * 2 * CHUNK_BYTES;
     const uint32_t group_bytes = 4 * GBOX_BYTES;
-    const int ndg = (nk + 3) / 4;                     // d-groups of up to four 64-wide boxes (N = 64 * boxes <= 256)
+    const int kc0 = (int)(rank - 1) * 8;              // this G-CTA's 512-wide slab of D starts at chunk kc0
+    const int nkg = min(8, nk - kc0);                 // 64-wide chunks in the slab
+    const int ndg = (nkg + 3) / 4;                    // d-groups of up to four 64-wide boxes (N = 64 * boxes <= 256)
     if (warp == 0) {
       Ring ring(PAIR_GGROUPS);
       PairWalk walk(u_begin, u_end, ncb);
@@ -897,14 +902,15 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       while (walk.next(sg)) {
         for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh) {           // 128-column P tiles
           for (int dg = 0; dg < ndg; ++dg) {
-            const int nb = min(4, nk - dg * 4);
+            const int nb = min(4, nkg - dg * 4);
             for (int kh = 0; kh < 2; ++kh) {                        // 64-row halves of the K = 128 j rows
               mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
               if (elect_one()) {
                 const uint32_t st = ring_base + ring.stage * group_bytes;
                 mbar_arrive_expect_tx(full_bar(ring.stage), nb * GBOX_BYTES);
                 for (int q = 0; q < nb; ++q)
-                  tma_load_2d(st + q * GBOX_BYTES, &tmap64, full_bar(ring.stage), (dg * 4 + q) * KC, jh * TM + kh * 64);
+                  tma_load_2d(st + q * GBOX_BYTES, &tmap64, full_bar(ring.stage), (kc0 + dg * 4 + q) * KC,
+                              jh * TM + kh * 64);
               }
               __syncwarp();
               ring.advance();
@@ -948,7 +954,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           tc_fence_after();
           const uint32_t p_tile = p_tiles + pb * PTILE_BYTES;
           for (int dg = 0; dg < ndg; ++dg) {
-            const int nb = min(4, nk - dg * 4);
+            const int nb = min(4, nkg - dg * 4);
             const uint32_t idesc = make_idesc_f16(128, 64 * nb, 0, 0, 0, 1);
             for (int kh = 0; kh < 2; ++kh) {
               mbar_wait(full_bar(ring.stage), ring.phase);
@@ -992,9 +998,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const int gi = g.row_begin + sg.ib * TM + r;
         mbar_wait(acc_full, seg_iter & 1);
         tc_fence_after();
-        float* out = dfhat + (int64_t)(gi - g.row_begin) * g.dim;
+        float* out = dfhat + (int64_t)(gi - g.row_begin) * g.dim + kc0 * KC;
         const bool whole = (sg.j0 == 0 && sg.j1 == ncb);
-        const int c_end = min(g.dim, wg * 256 + 256) / 32;
+        const int c_end = min(nkg * KC, wg * 256 + 256) / 32;
 #pragma unroll 1
         for (int c = wg * 8; c < c_end; ++c) {
           uint32_t v[32];
@@ -1233,53 +1239,75 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   return check_launch("fwd_tc_kernel");
 }
 
-// How many 2-CTA clusters of bwd_pair_kernel can be resident at once (<= SMs / 2; a GPC with an odd SM count
-// strands one SM).  Queried once per process.
-static int pair_clusters_resident() {
-  static int n = 0;
-  if (n == 0) {
+// How many clusters of bwd_pair_kernel (1 S-CTA + csize-1 G-CTAs) can be resident at once.  Queried once per
+// process and cluster size; 0 if the device cannot schedule that cluster shape.
+template <bool kResident>
+static int pair_clusters_resident(int csize) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static bool done[9] = {false, false, false, false, false, false, false, false, false};
+  if (!done[csize]) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (sm_count() / 2));
+    cfg.gridDim = dim3(csize * (sm_count() / csize));
     cfg.blockDim = dim3(PAIR_THREADS);
     cfg.dynamicSmemBytes = kMaxSmem;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
     int c = 0;
-    cudaFuncSetAttribute(bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (cudaOccupancyMaxActiveClusters(&c, bwd_pair_kernel, &cfg) != cudaSuccess || c <= 0) {
+    cudaFuncSetAttribute(bwd_pair_kernel<kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (cudaOccupancyMaxActiveClusters(&c, bwd_pair_kernel<kResident>, &cfg) != cudaSuccess || c < 0) {
       (void)cudaGetLastError();
-      c = sm_count() / 2;
+      c = 0;
     }
-    n = std::min(c, sm_count() / 2);
+    cache[csize] = std::min(c, sm_count() / csize);
+    done[csize] = true;
   }
-  return n;
+  return cache[csize];
 }
 
 size_t bwd_pair_scratch_bytes() { return (size_t)(sm_count() / 2) * PAIR_NSLOT * PTILE_BYTES; }
 
-static int launch_bwd_pair(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
-                           const float* scal, float* dfhat, void* scratch, cudaStream_t st) {
-  CUtensorMap tmap64;                     // [64 rows][64 cols] boxes for the G-CTA's MN-major operand groups
+// cluster size for embedding dim `dim`: one G-CTA per 512 columns; 0 = use the single-CTA kernel
+static int pair_cluster_size(int dim) {
+  if (bwd_variant() == 1 || dim <= 256) return 0;
+  const int csize = 1 + (dim + 511) / 512;
+  if (csize > 4) return 0;
+  const int resident = dim <= 512 ? pair_clusters_resident<true>(csize) : pair_clusters_resident<false>(csize);
+  return resident * csize * 10 >= sm_count() * 8 ? csize : 0;     // needs >= 80 % of the SMs in clusters
+}
+
+template <bool kResident>
+static int launch_bwd_pair_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
+                             const float* scal, float* dfhat, void* scratch, int csize, cudaStream_t st) {
+  CUtensorMap tmap64;                     // [64 rows][64 cols] boxes for the G-CTAs' MN-major operand groups
   int rc = make_tmap_f16(&tmap64, feat, (uint64_t)g.rows, (uint64_t)g.dim, 64);
   if (rc) return rc;
   const int nk = g.dim / KC, ncb = g.rows / PAIR_TN, nrb = g.row_count / TM;
   const long long n_units_ll = (long long)nrb * ncb;
   if (n_units_ll > 0x7fffffffLL) { set_error("crossclr_bwd: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
   const int n_units = (int)n_units_ll;
-  CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  const int s_stages = std::min((int)((kMaxSmem - PAIR_HDR - (size_t)nk * CHUNK_BYTES) / (2 * CHUNK_BYTES)), MAX_SLOTS);
-  const int npairs = std::min(n_units, pair_clusters_resident());
+  CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_pair_kernel<kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  const size_t a_bytes = kResident ? (size_t)nk * CHUNK_BYTES : 0;
+  const int s_stages = std::min((int)((kMaxSmem - PAIR_HDR - a_bytes) / ((kResident ? 2 : 3) * CHUNK_BYTES)), MAX_SLOTS);
+  const int nclusters = std::min(n_units, pair_clusters_resident<kResident>(csize));
   CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   static const int exp_flags = getenv("CROSSCLR_PAIR_EXP") ? atoi(getenv("CROSSCLR_PAIR_EXP")) : 0;
   static unsigned long long* trace = nullptr;
   static const bool want_trace = getenv("CROSSCLR_PAIR_TRACE") != nullptr;
   if (want_trace && trace == nullptr) { cudaMalloc(&trace, 6 * 64 * 4 * 8); }
   if (want_trace) cudaMemsetAsync(trace, 0, 6 * 64 * 4 * 8, st);
-  bwd_pair_kernel<<<2 * npairs, PAIR_THREADS, kMaxSmem, st>>>(tmap, tmap64, g, coef, scal, dfhat,
-                                                              (uint8_t*)scratch, n_units, ncb, nk, s_stages, exp_flags,
-                                                              trace);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize * nclusters);
+  cfg.blockDim = dim3(PAIR_THREADS);
+  cfg.dynamicSmemBytes = kMaxSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_pair_kernel<kResident>, tmap, tmap64, g, coef, scal, dfhat,
+                                   (uint8_t*)scratch, n_units, ncb, nk, s_stages, exp_flags, trace));
   if (want_trace) {
     static unsigned long long host[6 * 64 * 4];
     cudaStreamSynchronize(st);
@@ -1301,9 +1329,10 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
-  if (g.dim > 256 && g.dim <= 512 && bwd_variant() != 1) {   // two slabs would recompute S: role-specialised CTA pairs
+  if (const int csize = pair_cluster_size(g.dim)) {    // > 1 slab would recompute S: role-specialised CTA clusters
     TimedLaunch timed(CROSSCLR_K_BWD, st);
-    return launch_bwd_pair(tmap, feat, g, coef, scal, dfhat, scratch, st);
+    return g.dim <= 512 ? launch_bwd_pair_t<true>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st)
+                        : launch_bwd_pair_t<false>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st);
   }
   const int nk = g.dim / KC, ncb = g.rows / BWD_TN, nrb = g.row_count / TM;
   const int n_slabs = (g.dim + SLAB - 1) / SLAB;
