@@ -97,7 +97,7 @@ int crossclr_feature_dtype(int path) {
 }
 
 static size_t workspace_bytes(const crossclr_problem_t* p, int path) {
-  return dfhat_bytes(p) + ((path == CROSSCLR_PATH_TC && p->dim > 256) ? bwd_pair_scratch_bytes() : 0);
+  return dfhat_bytes(p) + (path == CROSSCLR_PATH_TC ? bwd_pair_scratch_bytes() : 0);   // + P-tile scratch rings
 }
 
 size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {

@@ -91,6 +91,61 @@ __device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float k, 
   }
 }
 
+// Epilogue of one 128-row x 256-column accumulator tile (thread = row r of the block): x = acc*k - shift, 2^x summed
+// into the thread-local row sums; the same-sample column is the masked intra-modal diagonal (logit 0,
+// trainer/loss.py:65,96-97) or the positive (kept out of X, written to stats[.,1]).
+template <int H0 = 0, int H1 = 2>       // 128-column halves [H0, H1) of the tile
+__device__ __forceinline__ void fwd_tile_epilogue(uint32_t tbase, int jb, const BlockSeg& bi, int r, int gi,
+                                                  const Geometry& g, float diag_term, float nshift, float (&rs)[4],
+                                                  float* __restrict__ stats) {
+  uint32_t va[32], vb[32];
+  tmem_ld32(tbase + H0 * TM, va);
+#pragma unroll
+  for (int h = H0; h < H1; ++h) {               // 128-column halves, each inside one segment
+    const BlockSeg bj = block_seg(jb * FWD_TN + h * TM, g.bseg);
+    const bool same_mod = (bj.mod == bi.mod);
+    const bool diag_tile = (bj.samp0 == bi.samp0);
+    const float k = same_mod ? g.k_intra : g.k_inter;
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {            // chunk pairs (software pipelined tcgen05.ld)
+      const int c = h * 4 + c2 * 2;             // 32-column chunk index in the tile (0..7), even
+      tmem_ld_wait();
+      tmem_ld32(tbase + (c + 1) * 32, vb);
+      if (!diag_tile || (r >> 5) != (c & 3)) {
+        fwd_sum_chunk(va, k, nshift, rs);
+      } else {
+        // this chunk holds the same-sample column (local column index == r)
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float x = fmaf(__uint_as_float(va[q]), k, nshift);
+          float e = fast_exp2(x);
+          if (q == (r & 31)) {
+            if (same_mod) e = diag_term;                       // masked intra-modal diagonal: logit 0
+            else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }  // positive logit, kept out of X
+          }
+          rs[q & 3] += e;
+        }
+      }
+      tmem_ld_wait();
+      if (c + 2 < H1 * 4) tmem_ld32(tbase + (c + 2) * 32, va);
+      if (!diag_tile || (r >> 5) != ((c + 1) & 3)) {
+        fwd_sum_chunk(vb, k, nshift, rs);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const float x = fmaf(__uint_as_float(vb[q]), k, nshift);
+          float e = fast_exp2(x);
+          if (q == (r & 31)) {
+            if (same_mod) e = diag_term;
+            else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }
+          }
+          rs[q & 3] += e;
+        }
+      }
+    }
+  }
+}
+
 template <bool kResident>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __restrict__ stats, int tiles_total,
@@ -198,7 +253,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
     BlockSeg bi{0, 0};
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     uint32_t iter = 0;
-    const float diag_term = fast_exp2(-g.shift);
+    const float k_diag_term = fast_exp2(-g.shift);
     const float nshift = -g.shift;
     for (int t = t_begin; t < t_end; ++t, ++iter) {
       const int ib = t / ncb, jb = t - ib * ncb;
@@ -214,52 +269,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
       const uint32_t tbase = lane_base + buf * FWD_TN;
       mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
       tc_fence_after();
-      uint32_t va[32], vb[32];
-      tmem_ld32(tbase, va);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {                 // two 128-column halves, each inside one segment
-        const BlockSeg bj = block_seg(jb * FWD_TN + h * TM, g.bseg);
-        const bool same_mod = (bj.mod == bi.mod);
-        const bool diag_tile = (bj.samp0 == bi.samp0);
-        const float k = same_mod ? g.k_intra : g.k_inter;
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {            // chunk pairs (software pipelined tcgen05.ld)
-          const int c = h * 4 + c2 * 2;             // 32-column chunk index in the tile (0..7), even
-          tmem_ld_wait();
-          tmem_ld32(tbase + (c + 1) * 32, vb);
-          if (!diag_tile || (r >> 5) != (c & 3)) {
-            fwd_sum_chunk(va, k, nshift, rs);
-          } else {
-            // this chunk holds the same-sample column (local column index == r)
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float x = fmaf(__uint_as_float(va[q]), k, nshift);
-              float e = fast_exp2(x);
-              if (q == (r & 31)) {
-                if (same_mod) e = diag_term;                       // masked intra-modal diagonal: logit 0
-                else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }  // positive logit, kept out of X
-              }
-              rs[q & 3] += e;
-            }
-          }
-          tmem_ld_wait();
-          if (c + 2 < 8) tmem_ld32(tbase + (c + 2) * 32, va);
-          if (!diag_tile || (r >> 5) != ((c + 1) & 3)) {
-            fwd_sum_chunk(vb, k, nshift, rs);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float x = fmaf(__uint_as_float(vb[q]), k, nshift);
-              float e = fast_exp2(x);
-              if (q == (r & 31)) {
-                if (same_mod) e = diag_term;
-                else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }
-              }
-              rs[q & 3] += e;
-            }
-          }
-        }
-      }
+      fwd_tile_epilogue(tbase, jb, bi, r, gi, g, k_diag_term, nshift, rs, stats);
       tc_fence_before();
       mbar_arrive(tempty_bar(buf));
     }
@@ -269,6 +279,173 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ================================================================================================
+// Forward, cta_group::2.  A cluster of two CTAs (one TPC) owns a 256-row x 256-column tile of the stacked Gram matrix:
+// CTA r holds rows [128 r, +128) of the row-block pair (resident for D <= 512) and stages rows [128 r, +128) of the
+// 256-row column block, so every B chunk is written to shared memory once per PAIR and each SM's tensor core reads
+// 4 KiB (A) + 4 KiB (its half of B) per 128-cycle MMA instead of 4 + 8: the single-CTA kernel above is bound by
+// shared-memory bandwidth (TMA fill + operand reads ~160 B/clk against 128), this one is not.
+// The leader (rank 0) issues every MMA (M = 256, N = 256) and multicasts the commits; all TMA loads count their
+// bytes on the leader's barriers; each CTA's epilogue drains its own 128 accumulator rows from its own TMEM and
+// its warps arrive (one lane each) on the leader's tempty barrier.
+// ================================================================================================
+constexpr uint32_t kIdescS256x2 = make_idesc_f16(256, 256, 0, 0, 0, 0);
+
+constexpr int FWD2_THREADS = 384;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue warpgroups
+
+template <bool kResident>
+__global__ void __launch_bounds__(FWD2_THREADS, 1)
+fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __restrict__ stats, int tiles_total,
+               int ncb, int nk, int num_stages, int exp_flags) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_region = base;
+  const uint32_t ring_base = a_region + (kResident ? nk * CHUNK_BYTES : 0);
+  const uint32_t stage_bytes = (kResident ? 1 : 2) * CHUNK_BYTES;   // [own A chunk] + own half of the B chunk
+  const uint32_t bar_base = ring_base + num_stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
+  const uint32_t a_full = bar_base + 8u * (2 * MAX_SLOTS);
+  const uint32_t a_empty = a_full + 8;
+  auto tfull_bar = [&](int b) { return a_full + 16u + 8u * b; };
+  auto tempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
+  const uint32_t tmem_slot = a_full + 48u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int t_begin = (int)((long long)pair * tiles_total / npairs);
+  const int t_end = (int)((long long)(pair + 1) * tiles_total / npairs);
+
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 16); }   // 8 warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // both CTAs' barriers exist before any remote arrival / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // TMA producer (both CTAs): own A rows, own half of every B chunk; bytes counted on the leader's barriers
+    Ring ring(num_stages);
+    int cur_ib = -1;
+    uint32_t a_cnt = 0;
+    const uint32_t a_full_ldr = mapa_cluster(a_full, 0);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int ib = t / ncb, jb = t - ib * ncb;
+      const int row0 = g.row_begin + (2 * ib + (int)rank) * TM, col0 = jb * FWD_TN + (int)rank * TM;
+      if (kResident && ib != cur_ib) {
+        mbar_wait(a_empty, (a_cnt & 1) ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(a_full, 2 * nk * CHUNK_BYTES);
+          for (int kc = 0; kc < nk; ++kc) tma_load_2d_2sm(a_region + kc * CHUNK_BYTES, &tmap, a_full_ldr, kc * KC, row0);
+        }
+        __syncwarp();
+        cur_ib = ib; ++a_cnt;
+      }
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+        if (elect_one()) {
+          uint32_t st = ring_base + ring.stage * stage_bytes;
+          const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * stage_bytes);
+          if (!kResident) { tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, row0); st += CHUNK_BYTES; }
+          tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, col0);
+        }
+        __syncwarp();
+        ring.advance();
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // MMA issuer (leader only)
+    Ring ring(num_stages);
+    int cur_ib = -1;
+    uint32_t a_cnt = 0, iter = 0;
+    for (int t = t_begin; t < t_end; ++t, ++iter) {
+      const int ib = t / ncb;
+      const uint32_t buf = iter & 1;
+      mbar_wait_cluster(tempty_bar(buf), ((iter >> 1) & 1) ^ 1);
+      if (kResident && ib != cur_ib) {
+        mbar_wait(a_full, a_cnt & 1);
+        cur_ib = ib; ++a_cnt;
+      }
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * FWD_TN;
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(full_bar(ring.stage), ring.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = ring_base + ring.stage * stage_bytes;
+          const uint64_t ad = kmajor_desc(kResident ? a_region + kc * CHUNK_BYTES : st);
+          const uint64_t bd = kmajor_desc(kResident ? st : st + CHUNK_BYTES);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            if (!(exp_flags & 2))
+              umma_ss_2sm(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdescS256x2, (kc == 0 && k == 0) ? 0u : 1u);
+          umma_commit_2sm(empty_bar(ring.stage), (uint16_t)3);
+        }
+        __syncwarp();
+        ring.advance();
+      }
+      const bool last_of_block = (t + 1 == t_end) || ((t + 1) / ncb != ib);
+      if (elect_one()) {
+        umma_commit_2sm(tfull_bar(buf), (uint16_t)3);
+        if (kResident && last_of_block) umma_commit_2sm(a_empty, (uint16_t)3);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= EPI_WARP0) {
+    // both epilogue warpgroups work on EVERY tile, group wg on its 128-column half: a TMEM buffer is held for
+    // MMA time + drain time, and with two buffers that sum has to stay under two MMA times -- halving the drain
+    // latency (instead of ping-ponging whole tiles between the groups) is what keeps the tensor pipe fed
+    const int quad = warp & 3, wg = (warp - EPI_WARP0) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int cur_ib = -1, gi = 0;
+    BlockSeg bi{0, 0};
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    const float k_diag_term = fast_exp2(-g.shift);
+    const float nshift = -g.shift;
+    const uint32_t tempty_ldr0 = mapa_cluster(tempty_bar(0), 0), tempty_ldr1 = mapa_cluster(tempty_bar(1), 0);
+    uint32_t iter = 0;
+    for (int t = t_begin; t < t_end; ++t, ++iter) {
+      const int ib = t / ncb, jb = t - ib * ncb;
+      if (ib != cur_ib) {
+        if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
+        rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
+        cur_ib = ib;
+        const int row0 = g.row_begin + (2 * ib + (int)rank) * TM;
+        gi = row0 + r;
+        bi = block_seg(row0, g.bseg);
+      }
+      const uint32_t buf = iter & 1;
+      const uint32_t tbase = lane_base + buf * FWD_TN;
+      mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
+      tc_fence_after();
+      if (!(exp_flags & 1)) {
+        if (wg == 0) fwd_tile_epilogue<0, 1>(tbase, jb, bi, r, gi, g, k_diag_term, nshift, rs, stats);
+        else fwd_tile_epilogue<1, 2>(tbase, jb, bi, r, gi, g, k_diag_term, nshift, rs, stats);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(buf ? tempty_ldr1 : tempty_ldr0);
+    }
+    if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // neither CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
 }
 
 // ================================================================================================
@@ -881,7 +1058,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 st_global_v4(prow + (c4 * 4 + ch) * (TM * 16), packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2],
                              packed[ch * 4 + 3]);
           }
-          fence_proxy_async_global();                              // these generic-proxy writes will be read by TMA
+          // No proxy fence here: the arrive releases these generic-proxy stores (cta scope), the signaller's gpu-scope
+          // fence is cumulative over them, and the reading side fences generic -> async before its TMA load.  (A
+          // fence.proxy.async.global per epilogue thread is a MEMBAR.GPU each: it cost as much as the tile's math.)
           mbar_arrive(staged_bar(slot));
           if (r == 0) TR(1 + wg, t >> 1, 2 + h);
         }
@@ -1033,6 +1212,441 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 }
 
 // ================================================================================================
+// Backward for D <= 512, D % 128 == 0: a CLUSTER OF FOUR CTAs = an S-pair (ranks 0, 1) and a G-pair (ranks 2, 3), each
+// pair driving ONE cta_group::2 MMA stream (M = 256) issued by its even-ranked leader.  The unit of work is a
+// (256-row block pair, 256-column block) of the stacked Gram matrix; CTA r of a pair owns rows [128 r, +128).
+//   S-pair: S[256 x 256] = A F_J^T.  CTA r keeps its 128 rows of A resident and stages rows [128 r, +128) of the 256-row
+//           column block, so each B chunk is fetched from L2 once per PAIR and read from shared memory once per SM.  Its
+//           two epilogue warpgroups turn its own 128 accumulator rows into fp16 P tiles (scratch ring in global memory,
+//           one channel per S-CTA -> G-CTA (2 + r)), exactly as in bwd_pair_kernel.
+//   G-pair: dF[256 x D] += P F_J.  A = P(j) (each CTA its own 128 rows, same buffer index in both), B = F_J[16 j x 256 d]
+//           MN-major with the 256 d of every MMA split half / half over the two CTAs, accumulators in all D TMEM columns
+//           of each CTA for its own 128 rows.
+// Why: both single-CTA-per-role kernels above are bound by L2 -> SM operand traffic (2 R^2 D / 128 bytes for each of S
+// and dF, ~1.1 GB at B=4096 D=512 against ~10 TB/s) and by shared-memory bandwidth; pairing halves both.
+// Barriers live at the same offsets in all four CTAs; "leader" barriers collect TMA bytes / arrivals of the pair,
+// tcgen05.commit multicasts hand buffers back to both CTAs of a pair (mask 0b0011 = S-pair, 0b1100 = G-pair).
+// ================================================================================================
+constexpr int QUAD_THREADS = 640;        // warps 0-3: producer / MMA / TMEM alloc / signaller-loader; warps 4-19: epilogue
+constexpr uint16_t kMaskS = 0x3, kMaskG = 0xC;
+constexpr int QUAD_HDR = 1024 + 16 * 2 * 64 * 4 + 1024;   // barriers | per-warp column coefficients | pad: 10 KiB, 1 KiB aligned
+
+struct QuadSeg { int ib, j0, j1; bool last_of_ib; };     // ib = index of the 256-row block pair
+using QuadWalk = PairWalk;
+
+__global__ void __launch_bounds__(QUAD_THREADS, 1)
+bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
+                const __grid_constant__ CUtensorMap tmap_p, Geometry g, const float* __restrict__ coef,
+                const float* __restrict__ scal, float* __restrict__ dfhat, uint8_t* __restrict__ scratch, int n_units,
+                int ncb, int nk, int s_stages, int exp_flags, unsigned long long* __restrict__ trace) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  if (base & 1023u) __trap();
+  // debug timeline (CROSSCLR_PAIR_TRACE): quad 0 stamps clock64 per role / tile / event
+  auto TR = [&](int role, int tile, int ev) {
+    if (trace != nullptr && blockIdx.x < 4 && tile < 64) trace[(role * 64 + tile) * 4 + ev] = clock64();
+  };
+  auto full_bar = [&](int s) { return base + 8u * s; };
+  auto empty_bar = [&](int s) { return base + 96u + 8u * s; };
+  const uint32_t a_full = base + 192u, a_empty = base + 200u;
+  auto sfull_bar = [&](int b) { return base + 208u + 8u * b; };
+  auto sempty_bar = [&](int b) { return base + 224u + 8u * b; };
+  auto staged_bar = [&](int b) { return base + 240u + 8u * b; };     // S-CTA: a P tile's 128 rows are in global memory
+  auto pready_bar = [&](int b) { return base + 304u + 8u * b; };     // G-CTA: that tile is published (remote arrival)
+  auto pempty_bar = [&](int b) { return base + 368u + 8u * b; };     // S-CTA: scratch slot consumed (multicast commit)
+  auto pbfull_bar = [&](int b) { return base + 432u + 8u * b; };     // G leader: both CTAs' P tiles landed (TMA bytes)
+  auto pbempty_bar = [&](int b) { return base + 456u + 8u * b; };    // G-CTA: smem P buffer consumed (multicast commit)
+  const uint32_t acc_full = base + 480u, acc_empty = base + 488u;
+  const uint32_t tmem_slot = base + 496u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 496);
+  float* cvw = reinterpret_cast<float*>(smem_raw + 1024);           // S-CTA: [16 epilogue warps][2 tile parities][64]
+
+  const uint32_t rank = cluster_ctarank();
+  const bool is_s = rank < 2;
+  const uint32_t data = base + (is_s ? QUAD_HDR : 1024);            // G-CTAs need all of the rest for P tiles + boxes
+  const uint32_t sub = rank & 1;                       // position in the pair = which 128 rows of the block pair
+  const uint32_t leader = rank & ~1u;                  // cluster rank of this pair's MMA-issuing CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = blockIdx.x >> 2, nquads = gridDim.x >> 2;
+  const int u_begin = (int)((long long)quad * n_units / nquads);
+  const int u_end = (int)((long long)(quad + 1) * n_units / nquads);
+  const int channel = quad * 2 + (int)sub;             // scratch ring S-CTA `sub` -> G-CTA `2 + sub`
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap); prefetch_tmap(&tmap64); prefetch_tmap(&tmap_p); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 32); }    // 16 warps x 2 CTAs
+    for (int b = 0; b < PAIR_NSLOT; ++b) {
+      mbar_init(staged_bar(b), 8); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), 1);   // staged: 8 warps per P tile
+    }
+    for (int b = 0; b < PAIR_PBUF; ++b) { mbar_init(pbfull_bar(b), 1); mbar_init(pbempty_bar(b), 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 16);                                             // 8 warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // every CTA's barriers are initialised before any remote arrival
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if ((is_s && (exp_flags & 8)) || (!is_s && (exp_flags & 4))) {
+    // perf experiment: this pair idles
+  } else if (is_s) {
+    // =========================================================================== S-pair
+    const uint32_t a_region = data;
+    const uint32_t ring_base = data + nk * CHUNK_BYTES;
+    if (warp == 0) {
+      // TMA producer: own 128 rows of A (resident), own half of each 256-row B chunk; bytes counted on the leader
+      Ring ring(s_stages);
+      int cur_ib = -1;
+      uint32_t a_cnt = 0;
+      const uint32_t a_full_ldr = mapa_cluster(a_full, leader);
+      QuadWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        const int row0 = g.row_begin + (2 * sg.ib + (int)sub) * TM;
+        if (sg.ib != cur_ib) {
+          mbar_wait(a_empty, (a_cnt & 1) ^ 1);
+          if (elect_one()) {
+            if (sub == 0) mbar_arrive_expect_tx(a_full, 2 * nk * CHUNK_BYTES);
+            for (int kc = 0; kc < nk; ++kc) tma_load_2d_2sm(a_region + kc * CHUNK_BYTES, &tmap, a_full_ldr, kc * KC, row0);
+          }
+          __syncwarp();
+          cur_ib = sg.ib; ++a_cnt;
+        }
+        for (int j = sg.j0; j < sg.j1; ++j) {
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+            if (elect_one()) {
+              if (exp_flags & 512) {                                 // perf experiment: no B-chunk loads
+                if (sub == 0) mbar_arrive(full_bar(ring.stage));
+              } else {
+                if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
+                tma_load_2d_2sm(ring_base + ring.stage * CHUNK_BYTES, &tmap, mapa_cluster(full_bar(ring.stage), leader),
+                                kc * KC, j * PAIR_TN + (int)sub * TM);
+              }
+            }
+            __syncwarp();
+            ring.advance();
+          }
+        }
+      }
+    } else if (warp == 1 && sub == 0) {
+      // MMA issuer (leader): S tile t -> TMEM buffer t & 1 of both CTAs
+      Ring ring(s_stages);
+      int cur_ib = -1;
+      uint32_t a_cnt = 0, t = 0;
+      QuadWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        if (sg.ib != cur_ib) {
+          mbar_wait(a_full, a_cnt & 1);
+          cur_ib = sg.ib; ++a_cnt;
+        }
+        for (int j = sg.j0; j < sg.j1; ++j, ++t) {
+          const uint32_t buf = t & 1;
+          if (lane == 0) TR(0, t, 0);
+          mbar_wait_cluster(sempty_bar(buf), ((t >> 1) & 1) ^ 1);
+          if (lane == 0) TR(0, t, 1);
+          tc_fence_after();
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(full_bar(ring.stage), ring.phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad = kmajor_desc(a_region + kc * CHUNK_BYTES);
+              const uint64_t bd = kmajor_desc(ring_base + ring.stage * CHUNK_BYTES);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                if (!(exp_flags & 256))                              // perf experiment: no S MMAs
+                  umma_ss_2sm(tmem_base + buf * PAIR_TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdescS256x2,
+                              (kc == 0 && k == 0) ? 0u : 1u);
+              umma_commit_2sm(empty_bar(ring.stage), kMaskS);
+            }
+            __syncwarp();
+            ring.advance();
+          }
+          if (elect_one()) {
+            umma_commit_2sm(sfull_bar(buf), kMaskS);
+            if (sg.last_of_ib && j + 1 == sg.j1) umma_commit_2sm(a_empty, kMaskS);
+          }
+          if (lane == 0) TR(0, t, 2);
+          __syncwarp();
+        }
+      }
+    } else if (warp == 2 || warp == 3) {
+      // two signallers (P tiles of even / odd index): once the 128 rows of P tile th are in global memory (staged), make
+      // them visible GPU-wide and tell this channel's G-CTA
+      const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
+      for (uint32_t th = (uint32_t)(warp - 2); th < n_ptiles; th += 2) {
+        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
+        mbar_wait(staged_bar(slot), use & 1);
+        if (elect_one()) {
+          fence_acq_rel_gpu();
+          mbar_arrive_cluster_relaxed(mapa_cluster(pready_bar(slot), 2 + sub));
+        }
+        __syncwarp();
+      }
+    } else if (warp >= EPI_WARP0) {
+      // Sixteen epilogue warps, four per TMEM lane quadrant: warp (quadrant q, slice s) owns rows [32 q, +32) x columns
+      // [64 s, +64) of EVERY S tile.  Its 64 accumulators per row come out of TMEM with two back-to-back loads and the
+      // buffer is released as soon as they land (~tile read-out time, not the math time), so two TMEM buffers keep the
+      // tensor pipe busy; four warps per scheduler hide the ex2 / convert latencies that two could not.
+      // Slices 0,1 form P tile 2t of this channel, slices 2,3 P tile 2t + 1.
+      const int quadw = warp & 3, sl = (warp - EPI_WARP0) >> 2;
+      const int r = quadw * 32 + lane;
+      const int half = sl >> 1;                                     // which 128-column P tile of the S tile
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16) + sl * 64;
+      const float sigma = scal[0];
+      const float nshift = -g.shift;
+      const uint32_t sempty_ldr0 = mapa_cluster(sempty_bar(0), leader), sempty_ldr1 = mapa_cluster(sempty_bar(1), leader);
+      // scratch P tile layout = the no-swizzle K-major operand layout: [16 column chunks of 8][128 rows][16 bytes]
+      uint8_t* const p_scratch = scratch + (size_t)channel * PAIR_NSLOT * PTILE_BYTES + (size_t)r * 16 +
+                                 (size_t)(sl & 1) * 8 * (TM * 16);
+      const int n_tiles = u_end - u_begin;
+      const bool no_store = (exp_flags & 1) != 0;                   // perf experiment without the stores
+      int cur_ib = -1, gi = 0;
+      BlockSeg bi{0, 0};
+      float iz_i = 0.f;
+      // column coefficients kappa*sigma / Z_j of the slice's 64 columns: every warp keeps a private copy in shared memory
+      // (lane l publishes columns l and 32 + l, fetched one tile ahead), so the epilogue warps never wait for each other
+      float* const cv_warp = cvw + (warp - EPI_WARP0) * 128;        // [tile parity][64]
+      // running tile coordinates (no divisions in the loop): block pair ib, column block j, and the segment / offset of
+      // this warp's 128-column half of the column block
+      int ib = u_begin / ncb, j = u_begin - ib * ncb;
+      int jseg = (j * PAIR_TN + half * TM) / g.bseg, joff = (j * PAIR_TN + half * TM) - jseg * g.bseg;
+      const float* const coef_col = coef + 2 * (int64_t)(sl * 64 + lane);
+      float izj0 = 0.f, izj1 = 0.f;
+      if (n_tiles > 0) { izj0 = coef_col[2 * (int64_t)j * PAIR_TN]; izj1 = coef_col[2 * ((int64_t)j * PAIR_TN + 32)]; }
+      for (int t = 0; t < n_tiles; ++t) {
+        if (ib != cur_ib) {
+          cur_ib = ib;
+          const int row0 = g.row_begin + (2 * ib + (int)sub) * TM;
+          gi = row0 + r;
+          bi = block_seg(row0, g.bseg);
+          iz_i = coef[2 * (int64_t)gi];
+        }
+        const bool same_mod = ((jseg & 1) == bi.mod);
+        const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
+        const float k = same_mod ? g.k_intra : g.k_inter;
+        const float ks = (same_mod ? g.w : 1.0f) * sigma;
+        float* cv = cv_warp + (t & 1) * 64;
+        cv[lane] = izj0 * ks;
+        cv[32 + lane] = izj1 * ks;
+        // advance to the next unit; fetch its column coefficients now, a whole tile ahead of their use
+        if (++j == ncb) { j = 0; ++ib; jseg = (half * TM) / g.bseg; joff = half * TM - jseg * g.bseg; }
+        else { joff += PAIR_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
+        if (t + 1 < n_tiles) { izj0 = coef_col[2 * (int64_t)j * PAIR_TN]; izj1 = coef_col[2 * ((int64_t)j * PAIR_TN + 32)]; }
+        __syncwarp();
+        const float a_i = iz_i * ks;
+        const uint32_t buf = (uint32_t)t & 1;
+        const uint32_t tb = lane_base + buf * PAIR_TN;
+        const uint32_t th = 2u * (uint32_t)t + half;               // P tile index of this channel
+        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
+        if (r == 0 && sl == 0) TR(1 + sub, t, 0);
+        mbar_wait(sfull_bar(buf), ((uint32_t)t >> 1) & 1);
+        if (r == 0 && sl == 0) TR(1 + sub, t, 1);
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        tmem_ld32(tb, va);
+        tmem_ld32(tb + 32, vb);
+        if (!(exp_flags & 2)) mbar_wait(pempty_bar(slot), (use & 1) ^ 1);   // the dF MMAs that read this scratch slot are done
+        uint8_t* const prow = p_scratch + (size_t)slot * PTILE_BYTES;
+        tmem_ld_wait();
+        tc_fence_before();                                          // this warp's part of the S tile is in registers
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf ? sempty_ldr1 : sempty_ldr0);
+        if (r == 0 && sl == 0) TR(1 + sub, t, 2);
+        // 32 columns of this thread's row -> 16 packed fp16 pairs -> four 16-byte stores.  The same-sample column
+        // (handled in grad_finish) is cleared after packing, in the one chunk of a diagonal tile that holds it, so the
+        // hot loop carries no per-element predicate.
+        auto p_chunk = [&](const uint32_t (&v)[32], int c) {       // c: 32-column chunk of the slice (0 / 1)
+          uint32_t packed[16];
+          const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const float4 cc = cv4[q >> 2];
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
+            const float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
+            const float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
+            __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
+            packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
+            packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          if (diag_tile && ((sl & 1) * 2 + c) == quadw) {          // warp-uniform: this chunk holds column r of the P tile
+            const int pi = (r & 31) >> 1;
+            const uint32_t keep = (r & 1) ? 0x0000ffffu : 0xffff0000u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i == pi) packed[i] &= keep;
+          }
+          if (!no_store) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              st_global_v4(prow + (c * 4 + ch) * (TM * 16), packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2],
+                           packed[ch * 4 + 3]);
+          }
+        };
+        p_chunk(va, 0);
+        p_chunk(vb, 1);
+        // No proxy fence here: the arrive releases these generic-proxy stores (cta scope), the signaller's gpu-scope
+        // fence is cumulative over them, and the reading side fences generic -> async before its TMA load.
+        // (Measured alternatives, both slower: staging P in shared memory and writing it with bulk copies -- eight 512-byte
+        // copies per warp or one 32 KiB copy per tile -- queues the stores in front of the operand loads in the copy
+        // engine and starves the MMAs.)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(staged_bar(slot));
+        if (r == 0 && sl == 0) TR(1 + sub, t, 3);
+      }
+    }
+  } else {
+    // =========================================================================== G-pair
+    const uint32_t p_tiles = data;
+    const uint32_t ring_base = data + PAIR_PBUF * PTILE_BYTES;
+    const int nbox = g.dim / 128;                      // own [64 j][64 d] boxes per 64-row group: half of each MMA's N
+    const uint32_t group_bytes = (uint32_t)nbox * GBOX_BYTES;
+    const int nmma = (g.dim + 255) / 256;              // MMAs per K = 16 step: N = 256 each (last one 128 if D % 256)
+    if (warp == 0) {
+      Ring ring(PAIR_GGROUPS);
+      QuadWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh) {           // 128-column P tiles
+          for (int kh = 0; kh < 2; ++kh) {                          // 64-row halves of the K = 128 j rows
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+            if (elect_one()) {
+              const uint32_t st = ring_base + ring.stage * group_bytes;
+              const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), leader);
+              if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * group_bytes);
+              for (int q = 0; q < nbox; ++q) {
+                const int m = q >> 1;                               // MMA index; its N = nm, this CTA's half = nm / 2
+                const int nm = min(256, g.dim - m * 256);
+                const int d0 = m * 256 + (int)sub * (nm >> 1) + (q & 1) * 64;
+                tma_load_2d_2sm(st + q * GBOX_BYTES, &tmap64, full_ldr, d0, jh * TM + kh * 64);
+              }
+            }
+            __syncwarp();
+            ring.advance();
+          }
+        }
+      }
+    } else if (warp == 2 || warp == 3) {
+      // two P loaders (even / odd tiles): this channel's published scratch tile -> smem P buffer pb (same pb in both
+      // CTAs); bytes counted on the leader's pbfull barrier
+      const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
+      for (uint32_t th = (uint32_t)(warp - 2); th < n_ptiles; th += 2) {
+        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
+        const uint32_t pb = th % PAIR_PBUF, puse = th / PAIR_PBUF;
+        if (!(exp_flags & 2)) mbar_wait_cluster(pready_bar(slot), use & 1);
+        fence_proxy_async_global();
+        mbar_wait(pbempty_bar(pb), (puse & 1) ^ 1);
+        if (elect_one()) {
+          if (sub == 0) mbar_arrive_expect_tx(pbfull_bar(pb), 2 * PTILE_BYTES);
+          tma_load_2d_2sm(p_tiles + pb * PTILE_BYTES, &tmap_p, mapa_cluster(pbfull_bar(pb), leader), 0,
+                          (channel * PAIR_NSLOT + (int)slot) * 256);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1 && sub == 0) {
+      Ring ring(PAIR_GGROUPS);
+      uint32_t th = 0, seg_iter = 0;
+      QuadWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        mbar_wait_cluster(acc_empty, (seg_iter & 1) ^ 1);   // both CTAs' drain warps have emptied the previous segment
+        tc_fence_after();
+        for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh, ++th) {
+          const uint32_t pb = th % PAIR_PBUF, puse = th / PAIR_PBUF;
+          const uint32_t slot = th % PAIR_NSLOT;
+          if (lane == 0) TR(5, th, 0);
+          mbar_wait(pbfull_bar(pb), puse & 1);              // both P tiles have landed in shared memory (TMA)
+          if (lane == 0) TR(5, th, 1);
+          tc_fence_after();
+          const uint32_t p_tile = p_tiles + pb * PTILE_BYTES;
+          for (int kh = 0; kh < 2; ++kh) {
+            mbar_wait(full_bar(ring.stage), ring.phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t st = ring_base + ring.stage * group_bytes;
+              for (int m = 0; m < nmma; ++m) {
+                const int nm = min(256, g.dim - m * 256);
+                const uint32_t idesc = make_idesc_f16(256, nm, 0, 0, 0, 1);
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  // A = P[:, 64 kh + 16 k16 .. +16): no-swizzle K-major, column chunks 8 kh + 2 k16 and the next one
+                  // (2048 bytes apart), 8-row groups 128 bytes apart; B = Fhat rows 64 kh + 16 k16 .. +16 of this CTA's
+                  // [64 j][64 d] boxes 2m, 2m + 1, MN-major: 16 K rows = 2048 bytes, next 64-wide MN atom = next box
+                  const uint64_t ad = make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * (TM * 16), TM * 16, 128);
+                  const uint64_t bd = make_smem_desc_sw128(st + 2 * m * GBOX_BYTES + k16 * 2048, 1024, GBOX_BYTES);
+                  umma_ss_2sm(tmem_base + m * 256, ad, bd, idesc, (jh > 2 * sg.j0 || kh > 0 || k16 > 0) ? 1u : 0u);
+                }
+              }
+              umma_commit_2sm(empty_bar(ring.stage), kMaskG);
+            }
+            __syncwarp();
+            ring.advance();
+          }
+          if (elect_one()) {
+            umma_commit_2sm(pbempty_bar(pb), kMaskG);
+            umma_commit_2sm(pempty_bar(slot), kMaskS);      // scratch slot `slot` of both channels is free again
+          }
+          if (lane == 0) TR(5, th, 2);
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_2sm(acc_full, kMaskG);
+        __syncwarp();
+        ++seg_iter;
+      }
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 8) {
+      const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;     // wg: which 256-column half of D
+      const int r = quadw * 32 + lane;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16);
+      const uint32_t acc_empty_ldr = mapa_cluster(acc_empty, leader);
+      uint32_t seg_iter = 0;
+      QuadWalk walk(u_begin, u_end, ncb);
+      PairSeg sg;
+      while (walk.next(sg)) {
+        const int gi = g.row_begin + (2 * sg.ib + (int)sub) * TM + r;
+        mbar_wait(acc_full, seg_iter & 1);
+        tc_fence_after();
+        float* out = dfhat + (int64_t)(gi - g.row_begin) * g.dim;
+        const bool whole = (sg.j0 == 0 && sg.j1 == ncb);
+        const int c_end = min(g.dim, wg * 256 + 256) / 32;
+#pragma unroll 1
+        for (int c = wg * 8; c < c_end; ++c) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + c * 32, v);
+          tmem_ld_wait();
+          if (whole) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              *reinterpret_cast<float4*>(out + c * 32 + q) =
+                  make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
+                              __uint_as_float(v[q + 3]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              red_add_f32x4(out + c * 32 + q, __uint_as_float(v[q]), __uint_as_float(v[q + 1]),
+                            __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_ldr);
+        ++seg_iter;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // no CTA leaves while a peer may still touch its shared memory / TMEM pair
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ================================================================================================
 // Self-test kernel: one CTA, D[128][n] = A[128][k] * B^T with the operand forms the real kernels use.
 //   variant 0: A, B K-major from TMA tiles (the S product)
 //   variant 1: A K-major written by threads with the swizzle formula (the P tile), B MN-major TMA tiles
@@ -1148,6 +1762,65 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// variant 4: cta_group::2.  A cluster of two CTAs computes D[256][n] = A[256][k] * B[n][k]^T with ONE M = 256 MMA
+// stream issued by the leader: CTA r stages rows [128 r, +128) of A and rows [r n/2, +n/2) of B (all TMA loads count
+// on the leader's mbarrier), and reads its 128 accumulator rows back from its own TMEM.
+__global__ void __launch_bounds__(128, 1)
+selftest_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int n, int k,
+                    float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int nk = k / KC;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t a_s = base;                                   // nk chunks of [128][64]
+  const uint32_t b_s = a_s + nk * CHUNK_BYTES;                 // nk chunks of [n/2 rows][64]
+  const uint32_t bchunk = (uint32_t)(n / 2) * 128u;
+  const uint32_t bar = b_s + nk * bchunk;
+  const uint32_t done_bar = bar + 8;
+  const uint32_t tmem_slot = bar + 16;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(done_bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int r = threadIdx.x;
+
+  if (threadIdx.x == 0) {
+    const uint32_t leader_bar = mapa_cluster(bar, 0);
+    const uint32_t my_bytes = nk * CHUNK_BYTES + nk * bchunk;
+    if (rank == 0) mbar_arrive_expect_tx(bar, 2 * my_bytes);
+    for (int kc = 0; kc < nk; ++kc) {
+      tma_load_2d_2sm(a_s + kc * CHUNK_BYTES, &tmap_a, leader_bar, kc * KC, (int)rank * TM);
+      tma_load_2d_2sm(b_s + kc * bchunk, &tmap_b, leader_bar, kc * KC, (int)rank * (n / 2));
+    }
+    if (rank == 0) {
+      mbar_wait(bar, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_f16(256, n, 0, 0, 0, 0);
+      for (int kc = 0; kc < nk; ++kc)
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss_2sm(tmem_base, kmajor_desc(a_s + kc * CHUNK_BYTES) + kk * 2, kmajor_desc(b_s + kc * bchunk) + kk * 2,
+                      idesc, (kc | kk) ? 1u : 0u);
+      umma_commit_2sm(done_bar, (uint16_t)3);
+    }
+  }
+  mbar_wait(done_bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < n / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+    tmem_ld_wait();
+    for (int q = 0; q < 32; ++q) out[((size_t)rank * TM + r) * n + c * 32 + q] = __uint_as_float(v[q]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_2sm(tmem_base, 512);
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1166,8 +1839,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 matrix [rows][cols] (row-major) tiled into {64 cols, box_rows} boxes with 128-byte swizzle
-int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// fp16 matrix [rows][cols] (row-major) tiled into {64 cols, box_rows} boxes, 128-byte swizzle (or none)
+int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, bool swizzle = true) {
   // The driver-API encode needs a current context on THIS thread.  torch's autograd worker threads only get
   // one lazily (first runtime call), so bind the primary context here; cudaFree(nullptr) is the documented no-op
   // that does it.
@@ -1184,8 +1857,8 @@ int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols,
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CROSSCLR_ECUDA; }
   return CROSSCLR_OK;
 }
@@ -1203,18 +1876,52 @@ int sm_count() {
 
 constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;
 
-// CROSSCLR_BWD_VARIANT=1 forces the single-CTA slab kernel for D <= 512 (A/B measurements, tests); default 0.
+// CROSSCLR_BWD_VARIANT (A/B measurements, tests): 1 forces the single-CTA slab kernel, 2 the 1 S-CTA + G-CTA(s)
+// cluster kernel, 3 the cta_group::2 quad kernel (D <= 512, D % 128 == 0); default 0 = chosen by shape.
 int bwd_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CROSSCLR_BWD_VARIANT");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 0;
   }
   return v;
 }
 constexpr size_t kMaxSmem = 232448;      // 227 KiB opt-in dynamic shared memory per CTA
 
 }  // namespace
+
+// CROSSCLR_FWD_VARIANT=1 forces the single-CTA forward (A/B measurements, tests); default: cta_group::2 pairs.
+int fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CROSSCLR_FWD_VARIANT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+template <bool kResident>
+static int launch_fwd_tc2_t(const CUtensorMap& tmap, const Geometry& g, float* stats, cudaStream_t st) {
+  const int nk = g.dim / KC, ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
+  const int tiles = nrbp * ncb;
+  const size_t a_bytes = kResident ? (size_t)nk * CHUNK_BYTES : 0;
+  const size_t stage_bytes = (size_t)(kResident ? 1 : 2) * CHUNK_BYTES;
+  const int stages = (int)std::min<size_t>(MAX_SLOTS, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);
+  const size_t smem = 1024 + a_bytes + (size_t)stages * stage_bytes + kBarBytes;
+  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * std::min(tiles, sm_count() / 2));
+  cfg.blockDim = dim3(FWD2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  static const int exp_flags = getenv("CROSSCLR_FWD_EXP") ? atoi(getenv("CROSSCLR_FWD_EXP")) : 0;   // perf experiments only
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident>, tmap, g, stats, tiles, ncb, nk, stages, exp_flags));
+  return check_launch("fwd_tc2_kernel");
+}
 
 int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_t st) {
   CUtensorMap tmap;
@@ -1224,6 +1931,8 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   const int tiles = nrb * ncb;
   TimedLaunch timed(CROSSCLR_K_FWD, st);
   const bool resident = nk <= MAX_RES_CHUNKS;
+  if (fwd_variant() == 0)
+    return resident ? launch_fwd_tc2_t<true>(tmap, g, stats, st) : launch_fwd_tc2_t<false>(tmap, g, stats, st);
   const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
   const size_t stage_bytes = (size_t)(resident ? 2 : 3) * CHUNK_BYTES;
   const int stages = (int)std::min<size_t>(6, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);
@@ -1270,11 +1979,36 @@ size_t bwd_pair_scratch_bytes() { return (size_t)(sm_count() / 2) * PAIR_NSLOT *
 
 // cluster size for embedding dim `dim`: one G-CTA per 512 columns; 0 = use the single-CTA kernel
 static int pair_cluster_size(int dim) {
-  if (bwd_variant() == 1 || dim <= 256) return 0;
+  if (bwd_variant() == 1 || dim <= 256) return 0;   // (variants 0, 2, 3 fall through to the shape rule)
   const int csize = 1 + (dim + 511) / 512;
   if (csize > 4) return 0;
   const int resident = dim <= 512 ? pair_clusters_resident<true>(csize) : pair_clusters_resident<false>(csize);
   return resident * csize * 10 >= sm_count() * 8 ? csize : 0;     // needs >= 80 % of the SMs in clusters
+}
+
+// debug timeline of the role-specialised backward kernels: CROSSCLR_PAIR_TRACE=<file> makes cluster 0 stamp clock64
+// per role / tile / event; the launch then synchronises and writes the table (perf debugging only)
+static unsigned long long* trace_buffer(cudaStream_t st) {
+  static unsigned long long* trace = nullptr;
+  static const bool want_trace = getenv("CROSSCLR_PAIR_TRACE") != nullptr;
+  if (!want_trace) return nullptr;
+  if (trace == nullptr) cudaMalloc(&trace, 6 * 64 * 4 * 8);
+  cudaMemsetAsync(trace, 0, 6 * 64 * 4 * 8, st);
+  return trace;
+}
+static void trace_dump(unsigned long long* trace, cudaStream_t st) {
+  if (trace == nullptr) return;
+  static unsigned long long host[6 * 64 * 4];
+  cudaStreamSynchronize(st);
+  cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
+  FILE* f = fopen(getenv("CROSSCLR_PAIR_TRACE"), "w");
+  if (f) {
+    for (int role = 0; role < 6; ++role)
+      for (int t = 0; t < 64; ++t)
+        fprintf(f, "%d %d %llu %llu %llu %llu\n", role, t, host[(role * 64 + t) * 4], host[(role * 64 + t) * 4 + 1],
+                host[(role * 64 + t) * 4 + 2], host[(role * 64 + t) * 4 + 3]);
+    fclose(f);
+  }
 }
 
 template <bool kResident>
@@ -1293,10 +2027,7 @@ static int launch_bwd_pair_t(const CUtensorMap& tmap, const void* feat, const Ge
   const int nclusters = std::min(n_units, pair_clusters_resident<kResident>(csize));
   CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   static const int exp_flags = getenv("CROSSCLR_PAIR_EXP") ? atoi(getenv("CROSSCLR_PAIR_EXP")) : 0;
-  static unsigned long long* trace = nullptr;
-  static const bool want_trace = getenv("CROSSCLR_PAIR_TRACE") != nullptr;
-  if (want_trace && trace == nullptr) { cudaMalloc(&trace, 6 * 64 * 4 * 8); }
-  if (want_trace) cudaMemsetAsync(trace, 0, 6 * 64 * 4 * 8, st);
+  unsigned long long* trace = trace_buffer(st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(csize * nclusters);
   cfg.blockDim = dim3(PAIR_THREADS);
@@ -1308,20 +2039,72 @@ static int launch_bwd_pair_t(const CUtensorMap& tmap, const void* feat, const Ge
   cfg.attrs = &attr; cfg.numAttrs = 1;
   CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_pair_kernel<kResident>, tmap, tmap64, g, coef, scal, dfhat,
                                    (uint8_t*)scratch, n_units, ncb, nk, s_stages, exp_flags, trace));
-  if (want_trace) {
-    static unsigned long long host[6 * 64 * 4];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
-    FILE* f = fopen(getenv("CROSSCLR_PAIR_TRACE"), "w");
-    if (f) {
-      for (int role = 0; role < 6; ++role)
-        for (int t = 0; t < 64; ++t)
-          fprintf(f, "%d %d %llu %llu %llu %llu\n", role, t, host[(role * 64 + t) * 4], host[(role * 64 + t) * 4 + 1],
-                  host[(role * 64 + t) * 4 + 2], host[(role * 64 + t) * 4 + 3]);
-      fclose(f);
-    }
-  }
+  trace_dump(trace, st);
   return check_launch("bwd_pair_kernel");
+}
+
+// resident clusters of bwd_quad_kernel (4 CTAs, 227 KiB of shared memory each); queried once
+static int quad_clusters_resident() {
+  static int cached = -1;
+  if (cached < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * (sm_count() / 4));
+    cfg.blockDim = dim3(QUAD_THREADS);
+    cfg.dynamicSmemBytes = kMaxSmem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int c = 0;
+    cudaFuncSetAttribute(bwd_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (cudaOccupancyMaxActiveClusters(&c, bwd_quad_kernel, &cfg) != cudaSuccess || c < 0) {
+      (void)cudaGetLastError();
+      c = 0;
+    }
+    cached = std::min(c, sm_count() / 4);
+  }
+  return cached;
+}
+
+// The quad kernel halves the L2 -> SM operand traffic of the 1 S-CTA + 1 G-CTA kernel, which is what bounds that one
+// once the Gram matrix is large (measured on B200, D = 512: B = 16384 1.99 vs 2.28 ms, B = 32768 8.98 vs 9.39 ms; equal at
+// B = 8192, ~5 % slower at B = 4096 where its longer prologue and 4-CTA granularity show).  CROSSCLR_BWD_VARIANT=3 forces it.
+static bool use_quad(const Geometry& g) {
+  if (g.dim > 512 || g.dim % 128 != 0 || quad_clusters_resident() * 4 * 10 < sm_count() * 8) return false;
+  if (bwd_variant() == 3) return true;
+  return bwd_variant() == 0 && g.dim == 512 && g.rows >= 24576;
+}
+
+static int launch_bwd_quad(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
+                           const float* scal, float* dfhat, void* scratch, cudaStream_t st) {
+  CUtensorMap tmap64, tmap_p;             // [64 rows][64 cols] boxes of Fhat; whole 32 KiB P tiles of the scratch rings
+  int rc = make_tmap_f16(&tmap64, feat, (uint64_t)g.rows, (uint64_t)g.dim, 64);
+  if (rc) return rc;
+  const int nk = g.dim / KC, ncb = g.rows / PAIR_TN, nrbp = g.row_count / (2 * TM);
+  const long long n_units_ll = (long long)nrbp * ncb;
+  if (n_units_ll > 0x7fffffffLL) { set_error("crossclr_bwd: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
+  const int n_units = (int)n_units_ll;
+  const int nquads = std::min(n_units, quad_clusters_resident());
+  rc = make_tmap_f16(&tmap_p, scratch, (uint64_t)nquads * 2 * PAIR_NSLOT * 256, 64, 256, /*swizzle=*/false);
+  if (rc) return rc;
+  CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  const int s_stages = std::min((int)((kMaxSmem - QUAD_HDR - (size_t)nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS);
+  CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * nquads);
+  cfg.blockDim = dim3(QUAD_THREADS);
+  cfg.dynamicSmemBytes = kMaxSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  static const int exp_flags = getenv("CROSSCLR_PAIR_EXP") ? atoi(getenv("CROSSCLR_PAIR_EXP")) : 0;   // perf experiments only
+  unsigned long long* trace = trace_buffer(st);
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_quad_kernel, tmap, tmap64, tmap_p, g, coef, scal, dfhat, (uint8_t*)scratch,
+                                   n_units, ncb, nk, s_stages, exp_flags, trace));
+  trace_dump(trace, st);
+  return check_launch("bwd_quad_kernel");
 }
 
 int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const float* scal, float* dfhat,
@@ -1329,6 +2112,10 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
+  if (use_quad(g)) {                                   // S-pair + G-pair, cta_group::2 MMAs
+    TimedLaunch timed(CROSSCLR_K_BWD, st);
+    return launch_bwd_quad(tmap, feat, g, coef, scal, dfhat, scratch, st);
+  }
   if (const int csize = pair_cluster_size(g.dim)) {    // > 1 slab would recompute S: role-specialised CTA clusters
     TimedLaunch timed(CROSSCLR_K_BWD, st);
     return g.dim <= 512 ? launch_bwd_pair_t<true>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st)
@@ -1359,33 +2146,50 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
 }
 
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k) {
-  if (variant < 0 || variant > 3 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
-      (variant == 1 && n % 64 != 0)) {
+  if (variant < 0 || variant > 4 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
+      (variant == 1 && n % 64 != 0) || (variant == 4 && n % 64 != 0)) {
     set_error("crossclr_selftest: unsupported variant/shape (variant %d n %d k %d)", variant, n, k);
     return CROSSCLR_EINVAL;
   }
+  const int m = (variant == 4) ? 256 : 128;       // variant 4 (cta_group::2): a is [256][k], out [256][n]
   uint16_t *da = nullptr, *db = nullptr;
   float* dout = nullptr;
-  CC_CHECK_CUDA(cudaMalloc(&da, (size_t)128 * k * 2));
+  CC_CHECK_CUDA(cudaMalloc(&da, (size_t)m * k * 2));
   CC_CHECK_CUDA(cudaMalloc(&db, (size_t)n * k * 2));
-  CC_CHECK_CUDA(cudaMalloc(&dout, (size_t)128 * n * 4));
-  CC_CHECK_CUDA(cudaMemcpy(da, a, (size_t)128 * k * 2, cudaMemcpyHostToDevice));
+  CC_CHECK_CUDA(cudaMalloc(&dout, (size_t)m * n * 4));
+  CC_CHECK_CUDA(cudaMemcpy(da, a, (size_t)m * k * 2, cudaMemcpyHostToDevice));
   CC_CHECK_CUDA(cudaMemcpy(db, b, (size_t)n * k * 2, cudaMemcpyHostToDevice));
   CUtensorMap ta, tb;
-  int rc = make_tmap_f16(&ta, da, 128, (uint64_t)k, 128);
-  if (!rc) rc = (variant == 1) ? make_tmap_f16(&tb, db, (uint64_t)k, (uint64_t)n, (uint32_t)k)   // b is [k][n], box {64, k}
-                               : make_tmap_f16(&tb, db, (uint64_t)n, (uint64_t)k, (uint32_t)n);  // b is [n][k]
+  int rc = make_tmap_f16(&ta, da, (uint64_t)m, (uint64_t)k, 128);
+  if (!rc) {
+    if (variant == 1) rc = make_tmap_f16(&tb, db, (uint64_t)k, (uint64_t)n, (uint32_t)k);        // b is [k][n], box {64, k}
+    else if (variant == 4) rc = make_tmap_f16(&tb, db, (uint64_t)n, (uint64_t)k, (uint32_t)(n / 2));
+    else rc = make_tmap_f16(&tb, db, (uint64_t)n, (uint64_t)k, (uint32_t)n);                      // b is [n][k]
+  }
   if (!rc) {
     const size_t smem = 1024 + (size_t)(k / KC) * CHUNK_BYTES + (size_t)n * k * 2 + 64;
-    cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    selftest_kernel<<<1, 128, smem>>>(ta, tb, variant, n, k, da, dout);
-    rc = check_launch("selftest_kernel");
+    if (variant == 4) {
+      cudaFuncSetAttribute(selftest_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = nullptr;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+      cfg.attrs = &attr; cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, selftest_2sm_kernel, ta, tb, n, k, dout);
+      if (e != cudaSuccess) { (void)cudaGetLastError(); set_error("selftest_2sm launch failed: %s", cudaGetErrorString(e)); rc = CROSSCLR_ECUDA; }
+      else rc = check_launch("selftest_2sm_kernel");
+    } else {
+      cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      selftest_kernel<<<1, 128, smem>>>(ta, tb, variant, n, k, da, dout);
+      rc = check_launch("selftest_kernel");
+    }
     if (!rc) {
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { set_error("selftest kernel failed: %s", cudaGetErrorString(e)); rc = CROSSCLR_ECUDA; }
     }
     if (!rc) {
-      cudaError_t e = cudaMemcpy(out, dout, (size_t)128 * n * 4, cudaMemcpyDeviceToHost);
+      cudaError_t e = cudaMemcpy(out, dout, (size_t)m * n * 4, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) { set_error("selftest copy-back failed: %s", cudaGetErrorString(e)); rc = CROSSCLR_ECUDA; }
     }
   }

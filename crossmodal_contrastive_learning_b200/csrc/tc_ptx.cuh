@@ -144,6 +144,10 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -151,6 +155,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// non-blocking arrival on a named barrier (pairs with named_bar_sync of the waiting threads; counts include both)
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------
@@ -170,6 +179,16 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src,
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+
+// 1-D bulk copy shared -> global (bytes % 16 == 0, 16-byte aligned), tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk async-groups have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_group_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all of this thread's bulk async-groups have completed (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // whole warp
@@ -215,6 +234,45 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
+// ---- cta_group::2: one MMA spanning the two CTAs of a pair (cluster ranks 2k, 2k+1) --------------------------
+// Both CTAs allocate / free TMEM collectively (one warp each); CTA 2k ("leader") issues the MMAs and commits.
+// An M = 256 MMA takes rows [0,128) of A from the leader's shared memory and rows [128,256) from its peer's (same
+// descriptor offsets in both), the N rows of B half from each, and leaves each CTA's 128 accumulator rows in its
+// own TMEM.
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {   // whole warp, in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all earlier MMAs of this thread are done) on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on `cluster_bar`, an mbarrier of either
+// CTA of the pair (shared::cluster address, e.g. from mapa_cluster)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* m, uint32_t cluster_bar, int32_t c0,
+                                                int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 // TMEM -> registers: 32 lanes x 32 consecutive 32-bit columns (thread = lane/row)

@@ -168,8 +168,10 @@ CROSSCLR_API int crossclr_timing_read(int kernel, double* total_ms, int64_t* lau
 /*
  * Hardware self-test of the tcgen05/TMA building blocks (descriptor encodings, TMEM layouts).
  * `variant` selects the block under test (0: K-major x K-major, 1: swizzled thread-written A x MN-major
- * B with b given as [k][n], n == 64, 2: A from TMEM); host buffers hold fp16 bit patterns: a [128][k],
- * b [n][k] (variant 1: [k][n]), out [128][n] float.  Synchronous (allocates, copies, syncs); tests only.
+ * B with b given as [k][n], 2: A from TMEM, 3: un-swizzled thread-written A, 4: one cta_group::2 MMA stream over
+ * a cluster of two CTAs, M = 256); host buffers hold fp16 bit patterns: a [128][k] (variant 4: [256][k]),
+ * b [n][k] (variant 1: [k][n]), out [128][n] float (variant 4: [256][n]).  Synchronous (allocates, copies,
+ * syncs); tests only.
  */
 CROSSCLR_API int crossclr_selftest(int variant, const uint16_t* a_host, const uint16_t* b_host, float* out_host,
                       int32_t n, int32_t k);

@@ -59,14 +59,16 @@ TC_OK = [p for p in FULL if (lambda g: g["v"].shape[0] % 128 == 0 and g["v"].sha
 # ---------------------------------------------------------------------------------------------
 # tcgen05 / TMA building blocks
 @pytest.mark.parametrize("variant,n,k", [(0, 128, 64), (0, 128, 256), (0, 64, 128), (0, 256, 128), (1, 64, 128),
-                                         (1, 64, 64), (1, 128, 128), (1, 256, 128), (2, 128, 128), (3, 128, 128), (3, 64, 64)])
+                                         (1, 64, 64), (1, 128, 128), (1, 256, 128), (2, 128, 128), (3, 128, 128), (3, 64, 64),
+                                         (4, 256, 128), (4, 128, 64), (4, 64, 256)])
 def test_tc_selftest(variant, n, k):
     import ctypes
     lib = _mod().load_native()
     rng = np.random.default_rng(variant * 100 + n + k)
-    a = rng.standard_normal((128, k)).astype(np.float16)
+    m = 256 if variant == 4 else 128          # variant 4: one cta_group::2 MMA stream over a CTA pair
+    a = rng.standard_normal((m, k)).astype(np.float16)
     b = (rng.standard_normal((k, n)) if variant == 1 else rng.standard_normal((n, k))).astype(np.float16)
-    out = np.zeros((128, n), dtype=np.float32)
+    out = np.zeros((m, n), dtype=np.float32)
     rc = lib.crossclr_selftest(variant, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
                                out.ctypes.data_as(ctypes.c_void_p), n, k)
     assert rc == 0, lib.crossclr_last_error()
