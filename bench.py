@@ -5,13 +5,18 @@
 
 One step = one forward + one backward of the criterion over one synthetic [B, D] video/text batch
 (a "pair" = one (video_i, text_i) row pair).  N > 1 is launched by torchrun, one rank
-per GPU; the GLOBAL batch is sharded by rows (strong scaling: the global workload is fixed).
+per GPU; the GLOBAL batch is sharded by rows (strong scaling: the global workload is fixed and the same for every N).
 
 Workloads (BASELINE.json `configs`; tau = 0.03, w = 0.8):
-    c2  B=4096   D=512   bf16   (configs[1], default at N = 1)
+    c2  B=4096   D=512   bf16   (configs[1]; the default at EVERY N, so per-N values are comparable)
     c3  B=16384  D=1024  bf16   (configs[2])
-    c4  B=65536  D=512   bf16   (configs[3], default at N > 1; global batch)
+    c4  B=65536  D=512   bf16   (configs[3]; global batch -- the meaningful multi-GPU scaling experiment, --workload c4)
     c5  B=131072 D=1024  bf16   (configs[4]; global batch)
+
+At one GPU the step is replayed from CUDA graphs (`GraphedCrossCLR`, the package's public capture API; `--no-graph`
+times the eager module instead), and the end-to-end loop is double-buffered: step i+1's host-to-device copy runs on a
+copy stream under step i's kernels, the loss of step i is read back asynchronously.  Every step still pays its own H2D
+copy from pinned memory and its own D2H read inside the timed region.
 
 Printed JSON keys follow the bench contract: value (device-resident), e2e (pinned host buffers, H2D of the
 features and D2H of the loss inside the timed region), roofline (dominant kernel, per-kernel CUDA events from the
@@ -59,6 +64,13 @@ def ncu_traffic(workload):
             return json.load(f)[workload]["bytes"]
     except Exception:
         return None
+
+
+def bwd_kernel_name(D, rows):
+    """The backward kernel libcrossclr_b200 selects for this shape (csrc/tc_kernels.cu: launch_bwd_tc)."""
+    if D == 512 and rows >= 24576:
+        return "bwd_quad_kernel"
+    return "bwd_pair_kernel" if 256 < D <= 1536 else "bwd_tc_kernel"
 
 
 def cpu_model():
@@ -261,37 +273,106 @@ def run_b200_arm(args):
     v_dev = v_host.to(dev)
     t_dev = t_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def step_resident():
-        v = v_dev.detach().requires_grad_()
-        t = t_dev.detach().requires_grad_()
-        loss = crit(v, t)
-        loss.backward()
-        return loss
-
-    def step_e2e():
-        v_dev.copy_(v_host, non_blocking=True)
-        t_dev.copy_(t_host, non_blocking=True)
-        loss = step_resident()
-        loss_host.copy_(loss, non_blocking=True)
-        return loss
+    use_graph = (world == 1) and not args.no_graph
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    n_cap0 = M.launch_count()
+    if use_graph:
+        # two captured instances: the end-to-end loop alternates between them so that the H2D copy of the next step can
+        # land in one instance's static inputs while the other instance's kernels run
+        runners = [M.GraphedCrossCLR(crit, Bl, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        for r in runners:
+            r.video.detach().copy_(v_dev)
+            r.text.detach().copy_(t_dev)
+        # kernels per captured step = library launches during one capture (warm-up steps launch the same set)
+        kernels_per_step = (M.launch_count() - n_cap0) // (2 * 4)
+    else:
+        runners = None
+        kernels_per_step = None
+
+    def step_resident():
+        if use_graph:
+            r = runners[0]
+            r.video.grad = None
+            r.text.grad = None
+            loss = r(r.video, r.text)
+            loss.backward()
+            return loss
+        v = v_dev.detach().requires_grad_()
+        t = t_dev.detach().requires_grad_()
+        loss = crit(v, t)
+        loss.backward()
+        return loss
+
+    def timed_resident(steps):
         """Sum of per-step device times (CUDA events on the launching stream); L2 flushed between steps."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        for a, b in evs:
+        for a_, b_ in evs:
             flush.zero_()
-            a.record()
-            fn()
-            b.record()
+            a_.record()
+            step_resident()
+            b_.record()
         barrier()
-        total = sum(a.elapsed_time(b) for a, b in evs)
+        total = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        tt = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    loss_hosts = [torch.empty((), dtype=torch.float64).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def timed_e2e(steps):
+        """Device time of `steps` end-to-end steps: H2D of the step's inputs from pinned memory, fwd+bwd, D2H of the loss.
+        Graph mode: double-buffered (copy stream), one event pair around the whole loop; eager mode: serial steps."""
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not use_graph:
+            barrier()
+            e0.record()
+            for i in range(steps):
+                v_dev.copy_(v_host, non_blocking=True)
+                t_dev.copy_(t_host, non_blocking=True)
+                loss = step_resident()
+                loss_hosts[i & 1].copy_(loss.detach(), non_blocking=True)
+            e1.record()
+            barrier()
+        else:
+            h2d_done = [torch.cuda.Event() for _ in range(2)]
+            inputs_free = [torch.cuda.Event() for _ in range(2)]
+            barrier()
+            e0.record()
+            copy_stream.wait_stream(main)
+
+            def issue_h2d(i):
+                r = runners[i & 1]
+                with torch.cuda.stream(copy_stream):
+                    if i >= 2:
+                        copy_stream.wait_event(inputs_free[i & 1])      # step i-2 has consumed these buffers
+                    r.video.detach().copy_(v_host, non_blocking=True)
+                    r.text.detach().copy_(t_host, non_blocking=True)
+                    h2d_done[i & 1].record(copy_stream)
+
+            issue_h2d(0)
+            for i in range(steps):
+                if i + 1 < steps:
+                    issue_h2d(i + 1)
+                r = runners[i & 1]
+                main.wait_event(h2d_done[i & 1])
+                r.video.grad = None
+                r.text.grad = None
+                loss = r(r.video, r.text)
+                inputs_free[i & 1].record(main)                         # the pack kernel (first in the graph) read them;
+                loss.backward()                                         # recorded after the forward graph to be safe
+                loss_hosts[i & 1].copy_(loss.detach(), non_blocking=True)
+            e1.record()
+            barrier()
+        total = e0.elapsed_time(e1)
         tt = torch.tensor([total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -300,26 +381,28 @@ def run_b200_arm(args):
     clk = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes a moment to produce its first sample
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    for _ in range(3):
-        step_e2e()
+    timed_e2e(3)
     torch.cuda.synchronize()
 
     n0 = M.launch_count()
     if clk is not None:
         clk.begin()
-    total_ms = timed(step_resident, args.steps)
+    total_ms = timed_resident(args.steps)
     if clk is not None:
         clk.end()
-    launches = M.launch_count() - n0
-    e2e_ms = timed(step_e2e, args.steps)
-    loss_val = float(loss_host.detach())
+    launches = (kernels_per_step * args.steps) if use_graph else (M.launch_count() - n0)
+    e2e_ms = timed_e2e(args.steps)
+    loss_val = float(loss_hosts[(args.steps - 1) & 1])
 
-    # second pass with the library's per-kernel events on (its own stream-ordered cudaEvents)
+    # second pass, eager, with the library's per-kernel events on (its own stream-ordered cudaEvents)
+    v_e, t_e = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
+    crit(v_e, t_e).backward()
     NAT.timing_enable(True)
     barrier()
     for _ in range(args.steps):
         flush.zero_()
-        step_resident()
+        v_e, t_e = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
+        crit(v_e, t_e).backward()
     torch.cuda.synchronize()
     NAT.timing_enable(False)
     ktimes = NAT.timing_read()
@@ -346,13 +429,18 @@ def run_b200_arm(args):
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (bf16 features in, bf16 grads out)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "B_global": Bg, "B_per_gpu": Bl, "D": D,
-                       "temperature": TAU, "negative_weight": W, "l2": "flushed between steps (256 MiB write)",
+                       "temperature": TAU, "negative_weight": W,
+                       "l2": "value: flushed between steps (256 MiB write); e2e: each step's inputs arrive by H2D copy",
+                       "launch": ("CUDA graphs (GraphedCrossCLR: forward graph + backward graph per step)" if use_graph
+                                  else "eager module calls"),
                        "parallelism": f"row-sharded x{world}, NCCL all-gather of features + row stats" if world > 1 else "single GPU",
                        "loss": loss_val},
             "e2e": {"value": Bg / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8},
+                    "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8,
+                    "pipeline": ("double-buffered: H2D of step i+1 on a copy stream under step i's kernels; loss read back "
+                                 "asynchronously" if use_graph else "serial")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": ("bwd_pair_kernel" if 256 < D <= 1536 else "bwd_tc_kernel"),
+            "roofline": {"bound": "tensor", "kernel": bwd_kernel_name(D, 2 * Bg),
                          "achieved": achieved, "peak": burst,
                          "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": ncu_traffic(args.workload),
                          "peak_source": f"{src} bf16_tflops (burst; kernel timed alone with CUDA events)",
@@ -380,10 +468,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of CUDA-graph replays")
     ap.add_argument("--shape", default=None, help="experiment override B,D (not a BASELINE config)")
     args = ap.parse_args()
     if args.workload is None:
-        args.workload = "c2" if args.gpus == 1 else "c4"
+        args.workload = "c2"
     if args.shape:
         B, D = (int(x) for x in args.shape.split(","))
         WORKLOADS["x"] = dict(B=B, D=D, desc=f"experiment B={B} D={D} bf16")
