@@ -273,7 +273,8 @@ def run_b200_arm(args):
     v_dev = v_host.to(dev)
     t_dev = t_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
+    graph_note = None
 
     def barrier():
         if world > 1:
@@ -281,18 +282,27 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     n_cap0 = M.launch_count()
+    runners, kernels_per_step = None, None
     if use_graph:
         # two captured instances: the end-to-end loop alternates between them so that the H2D copy of the next step can
         # land in one instance's static inputs while the other instance's kernels run
-        runners = [M.GraphedCrossCLR(crit, Bl, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
-        for r in runners:
-            r.video.detach().copy_(v_dev)
-            r.text.detach().copy_(t_dev)
-        # kernels per captured step = library launches during one capture (warm-up steps launch the same set)
-        kernels_per_step = (M.launch_count() - n_cap0) // (2 * 4)
-    else:
-        runners = None
-        kernels_per_step = None
+        try:
+            runners = [M.GraphedCrossCLR(crit, Bl, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+            for r in runners:
+                r.video.detach().copy_(v_dev)
+                r.text.detach().copy_(t_dev)
+            # kernels per captured step = library launches during one capture (warm-up steps launch the same set)
+            kernels_per_step = (M.launch_count() - n_cap0) // (2 * 4)
+            ok = 1
+        except Exception as exc:          # e.g. a collective that cannot be captured on this stack: time the eager module
+            graph_note = f"capture failed ({type(exc).__name__}: {str(exc)[:120]})"
+            ok = 0
+        if world > 1:                     # all ranks must agree on the launch mode
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            use_graph, runners = False, None
 
     def step_resident():
         if use_graph:
@@ -431,8 +441,9 @@ def run_b200_arm(args):
             "config": {"workload": f"{args.workload}: {wl['desc']}", "B_global": Bg, "B_per_gpu": Bl, "D": D,
                        "temperature": TAU, "negative_weight": W,
                        "l2": "value: flushed between steps (256 MiB write); e2e: each step's inputs arrive by H2D copy",
-                       "launch": ("CUDA graphs (GraphedCrossCLR: forward graph + backward graph per step)" if use_graph
-                                  else "eager module calls"),
+                       "launch": ("CUDA graphs (GraphedCrossCLR: forward graph + backward graph per step"
+                                  + (", NCCL all-gathers captured" if world > 1 else "") + ")" if use_graph
+                                  else "eager module calls" + (f"; {graph_note}" if graph_note else "")),
                        "parallelism": f"row-sharded x{world}, NCCL all-gather of features + row stats" if world > 1 else "single GPU",
                        "loss": loss_val},
             "e2e": {"value": Bg / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
@@ -457,7 +468,14 @@ def run_b200_arm(args):
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured graphs hold NCCL kernels; tearing the communicator down under them hung at exit on this stack.  The
+        # result is printed: drop the graphs, make sure every rank is done, and leave without the teardown.
+        runners = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -13,8 +13,9 @@ uses) and replays them:
 
 Semantics are those of the eager module (same kernels, same numbers); what changes is ownership: the returned loss
 and the gradients are views of static buffers that the next call overwrites, and `temperature` / `negative_w` are
-frozen at capture time (re-capture after changing them).  Single-rank only: with a process group the two
-all-gathers sit between the kernels, and the eager path is used.
+frozen at capture time (re-capture after changing them).  With a process group the two NCCL all-gathers are captured
+with the kernels (every rank must construct and replay its `GraphedCrossCLR` in the same order, as with any
+collective).
 """
 from __future__ import annotations
 
@@ -50,8 +51,6 @@ class GraphedCrossCLR:
 
     def __init__(self, criterion: CrossCLR_onlyIntraModality, batch: int, dim: int, dtype=torch.bfloat16,
                  device=None, warmup: int = 3):
-        if criterion.process_group is not None:
-            raise RuntimeError("GraphedCrossCLR captures the single-rank criterion; use the eager module with a process group")
         if not torch.cuda.is_available():
             raise RuntimeError("GraphedCrossCLR needs a CUDA device (the criterion has no CPU path)")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
