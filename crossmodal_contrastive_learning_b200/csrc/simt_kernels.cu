@@ -372,15 +372,31 @@ int launch_bwd_simt(const Geometry& g, const float* feat, const float* coef, flo
 
 // ================================================================================================
 // finalize: loss (trainer/loss.py:60,:111-114) + backward coefficients from per-row statistics.
-// Single block; the cancellation-free form loss_g = log1p(X_g / 2^xpos_g) is evaluated in double.
-__global__ void __launch_bounds__(1024) finalize_kernel(Geometry g, const float* __restrict__ stats,
-                                                       float* __restrict__ coef, double* __restrict__ loss,
-                                                       float* __restrict__ scal) {
-  __shared__ double s_sum[32];
-  __shared__ float s_rho[32];
+// The cancellation-free form loss_g = log1p(X_g / 2^xpos_g) is evaluated per row in fp32 pieces and summed in double.
+// Several blocks share the rows; each leaves its partial (loss sum, max rho) in a slot of a small static device table,
+// takes a ticket, and the last block to finish reduces the partials in a fixed order (the result does not depend on the
+// block schedule) and resets the ticket.  Launches take slots round-robin, so finalize calls in flight on different
+// streams (or captured in different CUDA graphs) never share one; a launch re-using a slot is stream-ordered behind the
+// 15 launches in between only by convention -- kFinSlots bounds the concurrent finalize launches per process.
+constexpr int kFinBlocks = 32;
+constexpr int kFinSlots = 16;
+struct FinSlot {
+  double sum[kFinBlocks];
+  float rho[kFinBlocks];
+  unsigned int ticket;
+};
+__device__ FinSlot g_fin[kFinSlots];
+
+__global__ void __launch_bounds__(256) finalize_kernel(Geometry g, const float* __restrict__ stats,
+                                                      float* __restrict__ coef, double* __restrict__ loss,
+                                                      float* __restrict__ scal, int slot) {
+  FinSlot& fin = g_fin[slot];
+  __shared__ double s_sum[8];
+  __shared__ float s_rho[8];
+  __shared__ bool s_last;
   double lsum = 0.0;
   float rho_max = 0.f;
-  for (int i = threadIdx.x; i < g.rows; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.rows; i += gridDim.x * blockDim.x) {
     const float2 sx = reinterpret_cast<const float2*>(stats)[i];
     const float X = sx.x, xp = sx.y;
     const float e = exp2f(xp);
@@ -404,32 +420,46 @@ __global__ void __launch_bounds__(1024) finalize_kernel(Geometry g, const float*
   rho_max = warp_max(rho_max);
   if (lane == 0) { s_sum[wid] = lsum; s_rho[wid] = rho_max; }
   __syncthreads();
-  if (wid == 0) {
-    const int nw = blockDim.x >> 5;
-    lsum = lane < nw ? s_sum[lane] : 0.0;
-    rho_max = lane < nw ? s_rho[lane] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-    rho_max = warp_max(rho_max);
-    if (lane == 0) {
-      loss[0] = lsum / (double)g.rows;
-      // fp16 probability tiles hold sigma * 2^x (1/Z_g + 1/Z_j) kappa <= sigma * 2 rho_max max(1,|w|)
-      const float bound = 2.0f * rho_max * fmaxf(1.0f, fabsf(g.w));
-      int ex = 0;
-      if (bound > 0.f && isfinite(bound)) ex = 14 - (int)ceilf(log2f(bound));
-      ex = max(-100, min(100, ex));
-      scal[0] = exp2f((float)ex);
-      scal[1] = exp2f((float)-ex);
-      scal[2] = rho_max;
-      scal[3] = 0.f;
+  if (threadIdx.x == 0) {
+    double bs = 0.0;
+    float br = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { bs += s_sum[w]; br = fmaxf(br, s_rho[w]); }
+    fin.sum[blockIdx.x] = bs;
+    fin.rho[blockIdx.x] = br;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&fin.ticket, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double tot = 0.0;
+    float rmax = 0.f;
+    for (int bI = 0; bI < (int)gridDim.x; ++bI) {        // fixed order: the loss does not depend on the block schedule
+      tot += *(volatile double*)&fin.sum[bI];
+      rmax = fmaxf(rmax, *(volatile float*)&fin.rho[bI]);
     }
+    fin.ticket = 0;                                      // ready for the slot's next launch
+    loss[0] = tot / (double)g.rows;
+    // fp16 probability tiles hold sigma * 2^x (1/Z_g + 1/Z_j) kappa <= sigma * 2 rho_max max(1,|w|)
+    const float bound = 2.0f * rmax * fmaxf(1.0f, fabsf(g.w));
+    int ex = 0;
+    if (bound > 0.f && isfinite(bound)) ex = 14 - (int)ceilf(log2f(bound));
+    ex = max(-100, min(100, ex));
+    scal[0] = exp2f((float)ex);
+    scal[1] = exp2f((float)-ex);
+    scal[2] = rmax;
+    scal[3] = 0.f;
   }
 }
 
 int launch_finalize(const Geometry& g, const float* stats, float* coef, double* loss, float* scal,
                     cudaStream_t st) {
   TimedLaunch timed(CROSSCLR_K_FINALIZE, st);
-  finalize_kernel<<<1, 1024, 0, st>>>(g, stats, coef, loss, scal);
+  const int blocks = std::max(1, std::min(kFinBlocks, (g.rows + 255) / 256));
+  static std::atomic<unsigned int> next_slot{0};
+  const int slot = (int)(next_slot.fetch_add(1, std::memory_order_relaxed) % kFinSlots);
+  finalize_kernel<<<blocks, 256, 0, st>>>(g, stats, coef, loss, scal, slot);
   return check_launch("finalize_kernel");
 }
 
@@ -476,6 +506,92 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   }
 }
 
+// Vectorised form for the tensor-core path (fp16 stacked rows, dim = 256 NV <= 1024, 16-byte aligned rows): each lane
+// owns NV groups of 8 consecutive columns, read once (16-byte loads) and kept in registers between the dot-product
+// pass and the output pass.  HBM-bound: reads dfhat (4 B), the row and its partner (2 x 2 B), writes the gradient.
+template <typename TO, int NV>
+__global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const __half* __restrict__ F,
+                                                             const float* __restrict__ rn, const float* __restrict__ coef,
+                                                             const float* __restrict__ scal, bool use_sigma,
+                                                             const double* __restrict__ grad_out, float grad_scale,
+                                                             const float* __restrict__ dfhat, TO* __restrict__ dv,
+                                                             int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride) {
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (l >= g.row_count) return;
+  const int gr = g.row_begin + l;
+  const int pg = row_partner(gr, g.bseg);
+  const float rn_g = rn[l];
+  const float acc_scale = use_sigma ? scal[1] : 1.0f;
+  const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]);
+  const uint4* fg = reinterpret_cast<const uint4*>(F + (int64_t)gr * g.dim);
+  const uint4* fp = reinterpret_cast<const uint4*>(F + (int64_t)pg * g.dim);
+  const float4* dh = reinterpret_cast<const float4*>(dfhat + (int64_t)l * g.dim);
+  float h[NV][8], f[NV][8];
+  float dot = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int idx = lane + 32 * v;
+    const uint4 ug = __ldg(fg + idx), up = __ldg(fp + idx);
+    const float4 d0 = __ldg(dh + 2 * idx), d1 = __ldg(dh + 2 * idx + 1);
+    const __half2* hg = reinterpret_cast<const __half2*>(&ug);
+    const __half2* hp = reinterpret_cast<const __half2*>(&up);
+    const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 a = __half22float2(hg[q]), b = __half22float2(hp[q]);
+      f[v][2 * q] = a.x; f[v][2 * q + 1] = a.y;
+      h[v][2 * q] = fmaf(pos_coef, b.x, dd[2 * q] * acc_scale);
+      h[v][2 * q + 1] = fmaf(pos_coef, b.y, dd[2 * q + 1] * acc_scale);
+      dot = fmaf(h[v][2 * q], a.x, dot);
+      dot = fmaf(h[v][2 * q + 1], a.y, dot);
+    }
+  }
+  dot = warp_sum(dot);
+  if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
+  double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows;
+  if (grad_out != nullptr) m *= grad_out[0];
+  const float mult = (float)m * rn_g;
+  const int mod = row_modality(gr, g.bseg);
+  const int r = gr % g.bseg;
+  TO* out = mod == 0 ? dv + (int64_t)r * dv_stride : dt + (int64_t)r * dt_stride;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int idx = lane + 32 * v;
+    alignas(16) TO o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = from_float<TO>(mult * (h[v][q] - dot * f[v][q]));
+    if (sizeof(TO) == 2) {
+      reinterpret_cast<uint4*>(out)[idx] = *reinterpret_cast<const uint4*>(o);
+    } else {
+      reinterpret_cast<uint4*>(out)[2 * idx] = reinterpret_cast<const uint4*>(o)[0];
+      reinterpret_cast<uint4*>(out)[2 * idx + 1] = reinterpret_cast<const uint4*>(o)[1];
+    }
+  }
+}
+
+template <typename TO>
+static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
+                            const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
+                            const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, cudaStream_t st) {
+  const size_t osz = sizeof(TO);
+  if (g.dim % 256 != 0 || g.dim > 1024 || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
+      (dvs * osz) % 16 != 0 || (dts * osz) % 16 != 0)
+    return false;
+  dim3 block(256), grid((g.row_count + 7) / 8);
+#define CC_GFV(NV)                                                                                                     \
+  grad_finish_vec_kernel<TO, NV><<<grid, block, 0, st>>>(g, (const __half*)feat, rnorm, coef, scal, use_sigma, grad_out, \
+                                                        grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
+  switch (g.dim / 256) {
+    case 1: CC_GFV(1); break;
+    case 2: CC_GFV(2); break;
+    case 3: CC_GFV(3); break;
+    default: CC_GFV(4); break;
+  }
+#undef CC_GFV
+  return true;
+}
+
 template <typename TF>
 static int grad_finish_out(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
                            const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
@@ -503,6 +619,16 @@ int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, cons
   if (feat_dtype == CROSSCLR_F32)
     return grad_finish_out<float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
                                   dv_stride, dt, dt_stride, out_dtype, st);
+  if (feat_dtype == CROSSCLR_F16) {
+    bool done = false;
+    switch (out_dtype) {
+      case CROSSCLR_F32: done = grad_finish_vec<float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+      case CROSSCLR_F16: done = grad_finish_vec<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+      case CROSSCLR_BF16: done = grad_finish_vec<__nv_bfloat16>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+      default: break;
+    }
+    if (done) return check_launch("grad_finish_vec_kernel");
+  }
   if (feat_dtype == CROSSCLR_F16)
     return grad_finish_out<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat,
                                           dv, dv_stride, dt, dt_stride, out_dtype, st);

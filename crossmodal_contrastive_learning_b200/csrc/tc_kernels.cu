@@ -91,6 +91,22 @@ __device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float k, 
   }
 }
 
+// The 32-column chunk that holds the same-sample column (column r & 31 of the chunk): the masked intra-modal diagonal
+// counts as logit 0 (trainer/loss.py:65,96-97); the positive is kept out of X and written to stats[.,1].
+__device__ __forceinline__ void fwd_diag_chunk(const uint32_t (&v)[32], float k, float nshift, bool same_mod,
+                                               float diag_term, int r, int gi, float* __restrict__ stats, float (&rs)[4]) {
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const float x = fmaf(__uint_as_float(v[q]), k, nshift);
+    float e = fast_exp2(x);
+    if (q == (r & 31)) {
+      if (same_mod) e = diag_term;
+      else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }
+    }
+    rs[q & 3] += e;
+  }
+}
+
 // Epilogue of one 128-row x 256-column accumulator tile (thread = row r of the block): x = acc*k - shift, 2^x summed
 // into the thread-local row sums; the same-sample column is the masked intra-modal diagonal (logit 0,
 // trainer/loss.py:65,96-97) or the positive (kept out of X, written to stats[.,1]).
@@ -293,7 +309,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
 // ================================================================================================
 constexpr uint32_t kIdescS256x2 = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
-constexpr int FWD2_THREADS = 384;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-11: two epilogue warpgroups
+constexpr int FWD2_THREADS = 640;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-19: epilogue
 
 template <bool kResident>
 __global__ void __launch_bounds__(FWD2_THREADS, 1)
@@ -324,7 +340,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 16); }   // 8 warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32); }   // 16 warps x 2 CTAs
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
@@ -404,21 +420,26 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
       __syncwarp();
     }
   } else if (warp >= EPI_WARP0) {
-    // both epilogue warpgroups work on EVERY tile, group wg on its 128-column half: a TMEM buffer is held for
-    // MMA time + drain time, and with two buffers that sum has to stay under two MMA times -- halving the drain
-    // latency (instead of ping-ponging whole tiles between the groups) is what keeps the tensor pipe fed
-    const int quad = warp & 3, wg = (warp - EPI_WARP0) >> 2;
+    // Sixteen epilogue warps, four per TMEM lane quadrant: warp (quadrant q, slice s) owns rows [32 q, +32) x columns
+    // [64 s, +64) of EVERY tile.  Its 64 accumulators per row come out of TMEM with two back-to-back loads and the buffer
+    // is handed back as soon as they land, so a buffer is held for MMA time + read-out time (not + math time) and two
+    // buffers keep the tensor pipe busy; four warps per scheduler cover the ex2 latency.
+    const int quad = warp & 3, sl = (warp - EPI_WARP0) >> 2;
+    const int half = sl >> 1;                                        // the slice's 128-column half of the tile
     const int r = quad * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + sl * 64;
     int cur_ib = -1, gi = 0;
     BlockSeg bi{0, 0};
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     const float k_diag_term = fast_exp2(-g.shift);
     const float nshift = -g.shift;
     const uint32_t tempty_ldr0 = mapa_cluster(tempty_bar(0), 0), tempty_ldr1 = mapa_cluster(tempty_bar(1), 0);
+    // running tile coordinates (no divisions in the loop): row-block pair ib, column block jb, and the segment / offset
+    // of this slice's half of the column block
+    int ib = t_begin / ncb, jb = t_begin - ib * ncb;
+    int jseg = (jb * FWD_TN + half * TM) / g.bseg, joff = (jb * FWD_TN + half * TM) - jseg * g.bseg;
     uint32_t iter = 0;
     for (int t = t_begin; t < t_end; ++t, ++iter) {
-      const int ib = t / ncb, jb = t - ib * ncb;
       if (ib != cur_ib) {
         if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
         rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
@@ -427,17 +448,30 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
         gi = row0 + r;
         bi = block_seg(row0, g.bseg);
       }
+      const bool same_mod = ((jseg & 1) == bi.mod);
+      const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
+      const float k = same_mod ? g.k_intra : g.k_inter;
+      if (++jb == ncb) { jb = 0; ++ib; jseg = (half * TM) / g.bseg; joff = half * TM - jseg * g.bseg; }
+      else { joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
       const uint32_t buf = iter & 1;
-      const uint32_t tbase = lane_base + buf * FWD_TN;
+      const uint32_t tb = lane_base + buf * FWD_TN;
       mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
       tc_fence_after();
-      if (!(exp_flags & 1)) {
-        if (wg == 0) fwd_tile_epilogue<0, 1>(tbase, jb, bi, r, gi, g, k_diag_term, nshift, rs, stats);
-        else fwd_tile_epilogue<1, 2>(tbase, jb, bi, r, gi, g, k_diag_term, nshift, rs, stats);
-      }
-      tc_fence_before();
+      uint32_t va[32], vb[32];
+      tmem_ld32(tb, va);
+      tmem_ld32(tb + 32, vb);
+      tmem_ld_wait();
+      tc_fence_before();                                             // this warp's part of the tile is in registers
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(buf ? tempty_ldr1 : tempty_ldr0);
+      if (!(exp_flags & 1)) {
+        // 32-column chunk c of the slice is chunk (2 (sl & 1) + c) of its half; the same-sample column r of a diagonal
+        // half sits in chunk r >> 5 = quad
+        if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk(va, k, nshift, rs);
+        else fwd_diag_chunk(va, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
+        if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk(vb, k, nshift, rs);
+        else fwd_diag_chunk(vb, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
+      }
     }
     if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
   }
