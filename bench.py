@@ -68,7 +68,7 @@ def ncu_traffic(workload):
 
 def bwd_kernel_name(D, rows):
     """The backward kernel libcrossclr_b200 selects for this shape (csrc/tc_kernels.cu: launch_bwd_tc)."""
-    if D == 512 and rows >= 24576:
+    if D == 512 and rows >= 12288:
         return "bwd_quad_kernel"
     return "bwd_pair_kernel" if 256 < D <= 1536 else "bwd_tc_kernel"
 

@@ -1261,9 +1261,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 // Barriers live at the same offsets in all four CTAs; "leader" barriers collect TMA bytes / arrivals of the pair,
 // tcgen05.commit multicasts hand buffers back to both CTAs of a pair (mask 0b0011 = S-pair, 0b1100 = G-pair).
 // ================================================================================================
-constexpr int QUAD_THREADS = 640;        // warps 0-3: producer / MMA / TMEM alloc / signaller-loader; warps 4-19: epilogue
+constexpr int QUAD_THREADS = 384;        // warps 0-3: producer / MMA / signallers-loaders (2, 3; 2 also owns TMEM); warps 4-11: epilogue
 constexpr uint16_t kMaskS = 0x3, kMaskG = 0xC;
-constexpr int QUAD_HDR = 1024 + 16 * 2 * 64 * 4 + 1024;   // barriers | per-warp column coefficients | pad: 10 KiB, 1 KiB aligned
+constexpr int QUAD_HDR = 1024 + 8 * 2 * 128 * 4 + 1024;   // barriers | per-warp column coefficients | pad: 10 KiB, 1 KiB aligned
 
 struct QuadSeg { int ib, j0, j1; bool last_of_ib; };     // ib = index of the 256-row block pair
 using QuadWalk = PairWalk;
@@ -1293,7 +1293,7 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t acc_full = base + 480u, acc_empty = base + 488u;
   const uint32_t tmem_slot = base + 496u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 496);
-  float* cvw = reinterpret_cast<float*>(smem_raw + 1024);           // S-CTA: [16 epilogue warps][2 tile parities][64]
+  float* cvw = reinterpret_cast<float*>(smem_raw + 1024);           // S-CTA: [8 epilogue warps][2 tile parities][128]
 
   const uint32_t rank = cluster_ctarank();
   const bool is_s = rank < 2;
@@ -1310,9 +1310,9 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 32); }    // 16 warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 16); }    // 8 warps x 2 CTAs
     for (int b = 0; b < PAIR_NSLOT; ++b) {
-      mbar_init(staged_bar(b), 8); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), 1);   // staged: 8 warps per P tile
+      mbar_init(staged_bar(b), 4); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), 1);   // staged: 4 warps per P tile
     }
     for (int b = 0; b < PAIR_PBUF; ++b) { mbar_init(pbfull_bar(b), 1); mbar_init(pbempty_bar(b), 1); }
     mbar_init(acc_full, 1); mbar_init(acc_empty, 16);                                             // 8 warps x 2 CTAs
@@ -1423,36 +1423,45 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         __syncwarp();
       }
     } else if (warp >= EPI_WARP0) {
-      // Sixteen epilogue warps, four per TMEM lane quadrant: warp (quadrant q, slice s) owns rows [32 q, +32) x columns
-      // [64 s, +64) of EVERY S tile.  Its 64 accumulators per row come out of TMEM with two back-to-back loads and the
-      // buffer is released as soon as they land (~tile read-out time, not the math time), so two TMEM buffers keep the
-      // tensor pipe busy; four warps per scheduler hide the ex2 / convert latencies that two could not.
-      // Slices 0,1 form P tile 2t of this channel, slices 2,3 P tile 2t + 1.
-      const int quadw = warp & 3, sl = (warp - EPI_WARP0) >> 2;
+      // Eight epilogue warps, two per TMEM lane quadrant: warp (quadrant q, half wg) owns rows [32 q, +32) x columns
+      // [128 wg, +128) of EVERY S tile = rows of P tile 2t + wg of this channel, as four 32-column chunks.
+      // The chunks run through a two-register-buffer software pipeline that does not stop at tile boundaries: while chunk c
+      // is turned into fp16 P values, chunk c + 1 -- or chunk 0 of the next tile, if its MMAs are already done -- is on its
+      // way out of TMEM.  So the TMEM read-out (~1.7k cycles per tile, port-bound) hides under the ex2 / store work instead
+      // of adding to it, and a TMEM buffer is released as soon as its fourth chunk has been read (3/4 into the tile).
+      const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;
       const int r = quadw * 32 + lane;
-      const int half = sl >> 1;                                     // which 128-column P tile of the S tile
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16) + sl * 64;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16) + wg * TM;
       const float sigma = scal[0];
       const float nshift = -g.shift;
       const uint32_t sempty_ldr0 = mapa_cluster(sempty_bar(0), leader), sempty_ldr1 = mapa_cluster(sempty_bar(1), leader);
       // scratch P tile layout = the no-swizzle K-major operand layout: [16 column chunks of 8][128 rows][16 bytes]
-      uint8_t* const p_scratch = scratch + (size_t)channel * PAIR_NSLOT * PTILE_BYTES + (size_t)r * 16 +
-                                 (size_t)(sl & 1) * 8 * (TM * 16);
+      uint8_t* const p_scratch = scratch + (size_t)channel * PAIR_NSLOT * PTILE_BYTES + (size_t)r * 16;
       const int n_tiles = u_end - u_begin;
       const bool no_store = (exp_flags & 1) != 0;                   // perf experiment without the stores
       int cur_ib = -1, gi = 0;
       BlockSeg bi{0, 0};
       float iz_i = 0.f;
-      // column coefficients kappa*sigma / Z_j of the slice's 64 columns: every warp keeps a private copy in shared memory
-      // (lane l publishes columns l and 32 + l, fetched one tile ahead), so the epilogue warps never wait for each other
-      float* const cv_warp = cvw + (warp - EPI_WARP0) * 128;        // [tile parity][64]
+      // column coefficients kappa*sigma / Z_j of the warp's 128 columns: every warp keeps a private copy in shared memory
+      // (lane l publishes columns l, 32 + l, 64 + l, 96 + l, fetched one tile ahead): the epilogue warps never wait for
+      // each other
+      float* const cv_warp = cvw + (warp - EPI_WARP0) * 256;        // [tile parity][128]
       // running tile coordinates (no divisions in the loop): block pair ib, column block j, and the segment / offset of
       // this warp's 128-column half of the column block
       int ib = u_begin / ncb, j = u_begin - ib * ncb;
-      int jseg = (j * PAIR_TN + half * TM) / g.bseg, joff = (j * PAIR_TN + half * TM) - jseg * g.bseg;
-      const float* const coef_col = coef + 2 * (int64_t)(sl * 64 + lane);
-      float izj0 = 0.f, izj1 = 0.f;
-      if (n_tiles > 0) { izj0 = coef_col[2 * (int64_t)j * PAIR_TN]; izj1 = coef_col[2 * ((int64_t)j * PAIR_TN + 32)]; }
+      int jseg = (j * PAIR_TN + wg * TM) / g.bseg, joff = (j * PAIR_TN + wg * TM) - jseg * g.bseg;
+      const float* const coef_col = coef + 2 * (int64_t)(wg * TM + lane);
+      float izj[4] = {0.f, 0.f, 0.f, 0.f};
+      if (n_tiles > 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) izj[q] = coef_col[2 * ((int64_t)j * PAIR_TN + 32 * q)];
+      }
+      uint32_t va[32], vb[32];
+      if (n_tiles > 0) {                                            // prologue of the pipeline: chunk 0 of tile 0
+        mbar_wait(sfull_bar(0), 0);
+        tc_fence_after();
+        tmem_ld32(lane_base, va);
+      }
       for (int t = 0; t < n_tiles; ++t) {
         if (ib != cur_ib) {
           cur_ib = ib;
@@ -1465,37 +1474,31 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
         const float k = same_mod ? g.k_intra : g.k_inter;
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
-        float* cv = cv_warp + (t & 1) * 64;
-        cv[lane] = izj0 * ks;
-        cv[32 + lane] = izj1 * ks;
+        float* cv = cv_warp + (t & 1) * TM;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cv[32 * q + lane] = izj[q] * ks;
         // advance to the next unit; fetch its column coefficients now, a whole tile ahead of their use
-        if (++j == ncb) { j = 0; ++ib; jseg = (half * TM) / g.bseg; joff = half * TM - jseg * g.bseg; }
+        if (++j == ncb) { j = 0; ++ib; jseg = (wg * TM) / g.bseg; joff = wg * TM - jseg * g.bseg; }
         else { joff += PAIR_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
-        if (t + 1 < n_tiles) { izj0 = coef_col[2 * (int64_t)j * PAIR_TN]; izj1 = coef_col[2 * ((int64_t)j * PAIR_TN + 32)]; }
+        if (t + 1 < n_tiles) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) izj[q] = coef_col[2 * ((int64_t)j * PAIR_TN + 32 * q)];
+        }
         __syncwarp();
         const float a_i = iz_i * ks;
         const uint32_t buf = (uint32_t)t & 1;
         const uint32_t tb = lane_base + buf * PAIR_TN;
-        const uint32_t th = 2u * (uint32_t)t + half;               // P tile index of this channel
+        const uint32_t tb_next = lane_base + (buf ^ 1) * PAIR_TN;
+        const uint32_t th = 2u * (uint32_t)t + wg;                 // P tile index of this channel
         const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
-        if (r == 0 && sl == 0) TR(1 + sub, t, 0);
-        mbar_wait(sfull_bar(buf), ((uint32_t)t >> 1) & 1);
-        if (r == 0 && sl == 0) TR(1 + sub, t, 1);
-        tc_fence_after();
-        uint32_t va[32], vb[32];
-        tmem_ld32(tb, va);
-        tmem_ld32(tb + 32, vb);
+        if (r == 0 && wg == 0) TR(1 + sub, t, 0);
         if (!(exp_flags & 2)) mbar_wait(pempty_bar(slot), (use & 1) ^ 1);   // the dF MMAs that read this scratch slot are done
+        if (r == 0 && wg == 0) TR(1 + sub, t, 1);
         uint8_t* const prow = p_scratch + (size_t)slot * PTILE_BYTES;
-        tmem_ld_wait();
-        tc_fence_before();                                          // this warp's part of the S tile is in registers
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(buf ? sempty_ldr1 : sempty_ldr0);
-        if (r == 0 && sl == 0) TR(1 + sub, t, 2);
         // 32 columns of this thread's row -> 16 packed fp16 pairs -> four 16-byte stores.  The same-sample column
         // (handled in grad_finish) is cleared after packing, in the one chunk of a diagonal tile that holds it, so the
         // hot loop carries no per-element predicate.
-        auto p_chunk = [&](const uint32_t (&v)[32], int c) {       // c: 32-column chunk of the slice (0 / 1)
+        auto p_chunk = [&](const uint32_t (&v)[32], int c) {       // c: 32-column chunk of the warp's half (0..3)
           uint32_t packed[16];
           const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
@@ -1509,7 +1512,7 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
             packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
-          if (diag_tile && ((sl & 1) * 2 + c) == quadw) {          // warp-uniform: this chunk holds column r of the P tile
+          if (diag_tile && c == quadw) {                            // warp-uniform: this chunk holds column r of the P tile
             const int pi = (r & 31) >> 1;
             const uint32_t keep = (r & 1) ? 0x0000ffffu : 0xffff0000u;
 #pragma unroll
@@ -1523,8 +1526,28 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                            packed[ch * 4 + 3]);
           }
         };
+        tmem_ld_wait();                          // chunk 0 (va)
+        tmem_ld32(tb + 32, vb);
         p_chunk(va, 0);
+        tmem_ld_wait();                          // chunk 1 (vb)
+        tmem_ld32(tb + 64, va);
         p_chunk(vb, 1);
+        tmem_ld_wait();                          // chunk 2 (va)
+        tmem_ld32(tb + 96, vb);
+        p_chunk(va, 2);
+        tmem_ld_wait();                          // chunk 3 (vb): this warp's part of the S tile is in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf ? sempty_ldr1 : sempty_ldr0);
+        if (r == 0 && wg == 0) TR(1 + sub, t, 2);
+        // chunk 0 of the next tile, if its MMAs are already done (usually): its read-out runs under chunk 3's math
+        bool prefetched = false;
+        if (t + 1 < n_tiles && mbar_try_wait(sfull_bar(buf ^ 1), (((uint32_t)t + 1) >> 1) & 1)) {
+          tc_fence_after();
+          tmem_ld32(tb_next, va);
+          prefetched = true;
+        }
+        p_chunk(vb, 3);
         // No proxy fence here: the arrive releases these generic-proxy stores (cta scope), the signaller's gpu-scope
         // fence is cumulative over them, and the reading side fences generic -> async before its TMA load.
         // (Measured alternatives, both slower: staging P in shared memory and writing it with bulk copies -- eight 512-byte
@@ -1532,7 +1555,12 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         // engine and starves the MMAs.)
         __syncwarp();
         if (lane == 0) mbar_arrive(staged_bar(slot));
-        if (r == 0 && sl == 0) TR(1 + sub, t, 3);
+        if (r == 0 && wg == 0) TR(1 + sub, t, 3);
+        if (t + 1 < n_tiles && !prefetched) {
+          mbar_wait(sfull_bar(buf ^ 1), (((uint32_t)t + 1) >> 1) & 1);
+          tc_fence_after();
+          tmem_ld32(tb_next, va);
+        }
       }
     }
   } else {
@@ -1633,7 +1661,7 @@ bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         __syncwarp();
         ++seg_iter;
       }
-    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 8) {
+    } else if (warp >= EPI_WARP0) {
       const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;     // wg: which 256-column half of D
       const int r = quadw * 32 + lane;
       const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16);
@@ -2101,12 +2129,12 @@ static int quad_clusters_resident() {
 }
 
 // The quad kernel halves the L2 -> SM operand traffic of the 1 S-CTA + 1 G-CTA kernel, which is what bounds that one
-// once the Gram matrix is large (measured on B200, D = 512: B = 16384 1.99 vs 2.28 ms, B = 32768 8.98 vs 9.39 ms; equal at
-// B = 8192, ~5 % slower at B = 4096 where its longer prologue and 4-CTA granularity show).  CROSSCLR_BWD_VARIANT=3 forces it.
+// (measured on B200, D = 512, quad vs pair: B = 4096 146 vs 146 us, B = 8192 0.449 vs 0.491 ms, B = 16384 1.87 vs
+// 2.28 ms, B = 32768 8.98 vs 9.39 ms).  Used from 12288 stacked rows up; CROSSCLR_BWD_VARIANT=3 forces it.
 static bool use_quad(const Geometry& g) {
   if (g.dim > 512 || g.dim % 128 != 0 || quad_clusters_resident() * 4 * 10 < sm_count() * 8) return false;
   if (bwd_variant() == 3) return true;
-  return bwd_variant() == 0 && g.dim == 512 && g.rows >= 24576;
+  return bwd_variant() == 0 && g.dim == 512 && g.rows >= 12288;
 }
 
 static int launch_bwd_quad(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
