@@ -311,7 +311,88 @@ constexpr uint32_t kIdescS256x2 = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
 constexpr int FWD2_THREADS = 640;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-19: epilogue
 
-template <bool kResident>
+// Tiles (row-block pair ib, column block jb) of a linear range, row-major.  Symmetric mode (single rank: the owned rows
+// are all rows, so the Gram matrix is square and symmetric): only jb >= ib, i.e. the upper triangle of 256 x 256 pair
+// tiles including the diagonal -- an off-diagonal tile then feeds the row sums of its rows AND, through its column sums,
+// the row sums of its columns' rows.
+struct FwdTileWalk {
+  int ib, jb, ncb;
+  bool sym;
+  __device__ FwdTileWalk(int t0, int ncb_, bool sym_) : ncb(ncb_), sym(sym_) {
+    if (!sym) { ib = t0 / ncb; jb = t0 - ib * ncb; }
+    else {
+      ib = 0;
+      int rem = t0;
+      while (rem >= ncb - ib) { rem -= ncb - ib; ++ib; }
+      jb = ib + rem;
+    }
+  }
+  __device__ __forceinline__ void next() {
+    if (++jb == ncb) { ++ib; jb = sym ? ib : 0; }
+  }
+  __device__ __forceinline__ int next_ib() const { return (jb + 1 == ncb) ? ib + 1 : ib; }
+};
+
+// as fwd_sum_chunk, but leaves the exponentials in v (bit patterns) for the column sums
+__device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float k, float nshift, float (&rs)[4]) {
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const float e = fast_exp2(fmaf(__uint_as_float(v[q]), k, nshift));
+    rs[q & 3] += e;
+    v[q] = __float_as_uint(e);
+  }
+}
+__device__ __forceinline__ void fwd_diag_chunk_keep(uint32_t (&v)[32], float k, float nshift, bool same_mod, float diag_term,
+                                                    int r, int gi, int partner, float* __restrict__ stats, float (&rs)[4]) {
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const float x = fmaf(__uint_as_float(v[q]), k, nshift);
+    float e = fast_exp2(x);
+    if (q == (r & 31)) {
+      if (same_mod) e = diag_term;
+      else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; stats[2 * (int64_t)partner + 1] = x; }   // the mirrored tile is skipped
+    }
+    rs[q & 3] += e;
+    v[q] = __float_as_uint(e);
+  }
+}
+
+// Column sums of a warp's 32 rows x 64 columns (a: columns 0..31, b: 32..63 of the slice; thread = row) by a butterfly
+// transpose-reduce: five exchange steps halve the columns a lane is responsible for, 62 shuffles in all; lane l ends up
+// with the sums of columns 2 l and 2 l + 1.
+__device__ __forceinline__ void warp_column_sums(const uint32_t (&a)[32], const uint32_t (&b)[32], int lane, float& c0, float& c1) {
+  float y[32];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float lo = __uint_as_float(a[i]), hi = __uint_as_float(b[i]);
+    const float recv = __shfl_xor_sync(0xffffffffu, b4 ? lo : hi, 16);
+    y[i] = (b4 ? hi : lo) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, b3 ? y[i] : y[i + 16], 8);
+    y[i] = (b3 ? y[i + 16] : y[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, b2 ? y[i] : y[i + 8], 4);
+    y[i] = (b2 ? y[i + 8] : y[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, b1 ? y[i] : y[i + 4], 2);
+    y[i] = (b1 ? y[i + 4] : y[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float recv = __shfl_xor_sync(0xffffffffu, b0 ? y[i] : y[i + 2], 1);
+    y[i] = (b0 ? y[i + 2] : y[i]) + recv;
+  }
+  c0 = y[0]; c1 = y[1];
+}
+
+template <bool kResident, bool kSym>
 __global__ void __launch_bounds__(FWD2_THREADS, 1)
 fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __restrict__ stats, int tiles_total,
                int ncb, int nk, int num_stages, int exp_flags) {
@@ -356,8 +437,9 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
     int cur_ib = -1;
     uint32_t a_cnt = 0;
     const uint32_t a_full_ldr = mapa_cluster(a_full, 0);
-    for (int t = t_begin; t < t_end; ++t) {
-      const int ib = t / ncb, jb = t - ib * ncb;
+    FwdTileWalk w(t_begin, ncb, kSym);
+    for (int t = t_begin; t < t_end; ++t, w.next()) {
+      const int ib = w.ib, jb = w.jb;
       const int row0 = g.row_begin + (2 * ib + (int)rank) * TM, col0 = jb * FWD_TN + (int)rank * TM;
       if (kResident && ib != cur_ib) {
         mbar_wait(a_empty, (a_cnt & 1) ^ 1);
@@ -386,8 +468,9 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
     Ring ring(num_stages);
     int cur_ib = -1;
     uint32_t a_cnt = 0, iter = 0;
-    for (int t = t_begin; t < t_end; ++t, ++iter) {
-      const int ib = t / ncb;
+    FwdTileWalk w(t_begin, ncb, kSym);
+    for (int t = t_begin; t < t_end; ++t, ++iter, w.next()) {
+      const int ib = w.ib;
       const uint32_t buf = iter & 1;
       mbar_wait_cluster(tempty_bar(buf), ((iter >> 1) & 1) ^ 1);
       if (kResident && ib != cur_ib) {
@@ -412,7 +495,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
         __syncwarp();
         ring.advance();
       }
-      const bool last_of_block = (t + 1 == t_end) || ((t + 1) / ncb != ib);
+      const bool last_of_block = (t + 1 == t_end) || (w.next_ib() != ib);
       if (elect_one()) {
         umma_commit_2sm(tfull_bar(buf), (uint16_t)3);
         if (kResident && last_of_block) umma_commit_2sm(a_empty, (uint16_t)3);
@@ -436,7 +519,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
     const uint32_t tempty_ldr0 = mapa_cluster(tempty_bar(0), 0), tempty_ldr1 = mapa_cluster(tempty_bar(1), 0);
     // running tile coordinates (no divisions in the loop): row-block pair ib, column block jb, and the segment / offset
     // of this slice's half of the column block
-    int ib = t_begin / ncb, jb = t_begin - ib * ncb;
+    FwdTileWalk w(t_begin, ncb, kSym);
+    int ib = w.ib, jb = w.jb;
     int jseg = (jb * FWD_TN + half * TM) / g.bseg, joff = (jb * FWD_TN + half * TM) - jseg * g.bseg;
     uint32_t iter = 0;
     for (int t = t_begin; t < t_end; ++t, ++iter) {
@@ -451,8 +535,11 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
       const bool same_mod = ((jseg & 1) == bi.mod);
       const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
       const float k = same_mod ? g.k_intra : g.k_inter;
-      if (++jb == ncb) { jb = 0; ++ib; jseg = (half * TM) / g.bseg; joff = half * TM - jseg * g.bseg; }
-      else { joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
+      const bool col_sums = kSym && jb != ib;                        // off-diagonal tile of the symmetric walk
+      const int col_row0 = jb * FWD_TN + sl * 64;                    // stacked row of the slice's first column
+      w.next();
+      if (w.ib != ib) { ib = w.ib; jb = w.jb; jseg = (jb * FWD_TN + half * TM) / g.bseg; joff = (jb * FWD_TN + half * TM) - jseg * g.bseg; }
+      else { jb = w.jb; joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
       const uint32_t buf = iter & 1;
       const uint32_t tb = lane_base + buf * FWD_TN;
       mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
@@ -467,10 +554,23 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
       if (!(exp_flags & 1)) {
         // 32-column chunk c of the slice is chunk (2 (sl & 1) + c) of its half; the same-sample column r of a diagonal
         // half sits in chunk r >> 5 = quad
-        if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk(va, k, nshift, rs);
-        else fwd_diag_chunk(va, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
-        if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk(vb, k, nshift, rs);
-        else fwd_diag_chunk(vb, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
+        if (!col_sums) {
+          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk(va, k, nshift, rs);
+          else fwd_diag_chunk(va, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
+          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk(vb, k, nshift, rs);
+          else fwd_diag_chunk(vb, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
+        } else {
+          const int partner = row_partner(gi, g.bseg);
+          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk_keep(va, k, nshift, rs);
+          else fwd_diag_chunk_keep(va, k, nshift, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk_keep(vb, k, nshift, rs);
+          else fwd_diag_chunk_keep(vb, k, nshift, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          // the mirrored tile (jb, ib) is never computed: its row sums are this tile's column sums
+          float c0, c1;
+          warp_column_sums(va, vb, lane, c0, c1);
+          atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane)], c0);
+          atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane + 1)], c1);
+        }
       }
     }
     if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
@@ -1962,15 +2062,25 @@ int fwd_variant() {
   return v;
 }
 
-template <bool kResident>
+// CROSSCLR_FWD_SYM=0 disables the symmetric (upper-triangle) walk of the single-rank forward (A/B measurements).
+static bool fwd_sym_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CROSSCLR_FWD_SYM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <bool kResident, bool kSym>
 static int launch_fwd_tc2_t(const CUtensorMap& tmap, const Geometry& g, float* stats, cudaStream_t st) {
   const int nk = g.dim / KC, ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
-  const int tiles = nrbp * ncb;
+  const int tiles = kSym ? ncb * (ncb + 1) / 2 : nrbp * ncb;
   const size_t a_bytes = kResident ? (size_t)nk * CHUNK_BYTES : 0;
   const size_t stage_bytes = (size_t)(kResident ? 1 : 2) * CHUNK_BYTES;
   const int stages = (int)std::min<size_t>(MAX_SLOTS, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);
   const size_t smem = 1024 + a_bytes + (size_t)stages * stage_bytes + kBarBytes;
-  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident, kSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * std::min(tiles, sm_count() / 2));
   cfg.blockDim = dim3(FWD2_THREADS);
@@ -1981,7 +2091,7 @@ static int launch_fwd_tc2_t(const CUtensorMap& tmap, const Geometry& g, float* s
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   static const int exp_flags = getenv("CROSSCLR_FWD_EXP") ? atoi(getenv("CROSSCLR_FWD_EXP")) : 0;   // perf experiments only
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident>, tmap, g, stats, tiles, ncb, nk, stages, exp_flags));
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym>, tmap, g, stats, tiles, ncb, nk, stages, exp_flags));
   return check_launch("fwd_tc2_kernel");
 }
 
@@ -1993,8 +2103,12 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   const int tiles = nrb * ncb;
   TimedLaunch timed(CROSSCLR_K_FWD, st);
   const bool resident = nk <= MAX_RES_CHUNKS;
-  if (fwd_variant() == 0)
-    return resident ? launch_fwd_tc2_t<true>(tmap, g, stats, st) : launch_fwd_tc2_t<false>(tmap, g, stats, st);
+  if (fwd_variant() == 0) {
+    // single rank: all rows are owned, the Gram matrix is square and symmetric -> upper triangle of pair tiles only
+    const bool sym = g.row_count == g.rows && g.row_begin == 0 && fwd_sym_enabled();
+    if (sym) return resident ? launch_fwd_tc2_t<true, true>(tmap, g, stats, st) : launch_fwd_tc2_t<false, true>(tmap, g, stats, st);
+    return resident ? launch_fwd_tc2_t<true, false>(tmap, g, stats, st) : launch_fwd_tc2_t<false, false>(tmap, g, stats, st);
+  }
   const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
   const size_t stage_bytes = (size_t)(resident ? 2 : 3) * CHUNK_BYTES;
   const int stages = (int)std::min<size_t>(6, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);

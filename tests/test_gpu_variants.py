@@ -1,6 +1,7 @@
 """Every tensor-core kernel variant against the oracle.  The library picks a forward / backward kernel by shape; the
 CROSSCLR_*_VARIANT environment switches (read once per process, hence the child processes) force the others so that the
-kernels a given shape would not select stay covered: single-CTA forward, single-CTA slab backward, 1 S-CTA + G-CTA(s)
+kernels a given shape would not select stay covered: single-CTA forward, full-Gram (non-symmetric) paired forward,
+single-CTA slab backward, 1 S-CTA + G-CTA(s)
 cluster backward, cta_group::2 quad backward."""
 import os
 import subprocess
@@ -14,11 +15,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.parametrize("env,B,D", [
     ({"CROSSCLR_FWD_VARIANT": "1"}, 512, 512), ({"CROSSCLR_FWD_VARIANT": "1"}, 256, 1024),
+    ({"CROSSCLR_FWD_SYM": "0"}, 512, 512), ({"CROSSCLR_FWD_SYM": "0"}, 384, 1024),
     ({"CROSSCLR_BWD_VARIANT": "1"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "2"}, 512, 512),
     ({"CROSSCLR_BWD_VARIANT": "2"}, 384, 1024), ({"CROSSCLR_BWD_VARIANT": "3"}, 512, 512),
     ({"CROSSCLR_BWD_VARIANT": "3"}, 640, 256), ({"CROSSCLR_BWD_VARIANT": "3"}, 384, 384),
     ({"CROSSCLR_BWD_VARIANT": "3"}, 256, 128),
-], ids=lambda x: "-".join(f"{k[9:]}{v}" for k, v in x.items()) if isinstance(x, dict) else str(x))
+], ids=lambda x: "-".join(f"{k[9:]}{v}" for k, v in x.items()) if isinstance(x, dict) else str(x))  # noqa: E501
 def test_forced_variant_matches_oracle(env, B, D):
     e = dict(os.environ, **env)
     p = subprocess.run([sys.executable, os.path.join(HERE, "_variant_check.py"), str(B), str(D)], env=e,
