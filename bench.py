@@ -436,7 +436,7 @@ def run_b200_arm(args):
         line = {
             "metric": METRIC, "value": Bg / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (bf16 features in, bf16 grads out)",
+            "vs_baseline": None, "dtype": "f16 (tensor-core operands; f32 accumulate; bf16 features in, bf16 grads out)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "B_global": Bg, "B_per_gpu": Bl, "D": D,
                        "temperature": TAU, "negative_weight": W,
