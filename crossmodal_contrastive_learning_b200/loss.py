@@ -135,8 +135,9 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     rows = 2 * world * B
     feat_all = torch.empty((2 * world, B, D), dtype=feat_dtype, device=dev)
     rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
-    small = torch.empty(4 * rows + 4, dtype=torch.float32, device=dev)      # stats | coef | scal
-    stats, coef, scal = small[:2 * rows].view(rows, 2), small[2 * rows:4 * rows].view(rows, 2), small[4 * rows:]
+    stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+    coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)          # separate allocations: the custom op returns
+    scal = torch.empty(4, dtype=torch.float32, device=dev)                  # coef and scal, and outputs must not alias
     loss = torch.empty((), dtype=torch.float64, device=dev)
     if world == 1:
         ops.forward_single(prob, code, v, t, feat_all, rnorm, stats, coef, scal, loss)
@@ -198,6 +199,101 @@ class _CrossCLRFunction(torch.autograd.Function):
         return dv, dt, None, None, None, None, None
 
 
+# ---------------------------------------------------------------------------------------------------
+# torch.library registration: the single-rank criterion as two opaque custom ops, so that
+# torch.compile traces straight through it (no graph break at the ctypes calls) and AMP / functorch see ordinary ops.
+#   crossclr_b200::forward(video, text, temperature, negative_weight, path) -> (loss, feat, rnorm, coef, scal)
+#   crossclr_b200::backward(feat, rnorm, coef, scal, grad_out, batch, dim, temperature, negative_weight, path,
+#                           grad_scale, out_dtype) -> (dvideo, dtext)
+# Multi-rank calls (process_group=...) keep using the autograd.Function above: a ProcessGroup is not an op argument.
+_OUT_DTYPE = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}
+
+
+def _plan_py(B, D, path):
+    """The path libcrossclr_b200 picks (csrc/api.cu: crossclr_choose_path), for shape inference without the library."""
+    tc = (B % 128 == 0) and (D % 64 == 0) and path != "simt"
+    return (N.PATH_TC, torch.float16) if tc else (N.PATH_SIMT, torch.float32)
+
+
+@torch.library.custom_op("crossclr_b200::forward", mutates_args=())
+def _op_forward(video: torch.Tensor, text: torch.Tensor, temperature: float, negative_weight: float,
+                path: str) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    _check_inputs(video, text)
+    v, t = _rowmajor(video.detach()), _rowmajor(text.detach())
+    with torch.cuda.device(v.device):
+        loss, _, _, (feat_all, rnorm, coef, scal) = _forward_impl(_ops(), v, t, temperature, negative_weight, path, None)
+    return loss, feat_all, rnorm, coef, scal
+
+
+@_op_forward.register_fake
+def _(video, text, temperature, negative_weight, path):
+    B, D = video.shape
+    _, fdt = _plan_py(B, D, path)
+    dev = video.device
+    return (torch.empty((), dtype=torch.float64, device=dev), torch.empty((2, B, D), dtype=fdt, device=dev),
+            torch.empty(2 * B, dtype=torch.float32, device=dev), torch.empty((2 * B, 2), dtype=torch.float32, device=dev),
+            torch.empty(4, dtype=torch.float32, device=dev))
+
+
+@torch.library.custom_op("crossclr_b200::backward", mutates_args=())
+def _op_backward(feat: torch.Tensor, rnorm: torch.Tensor, coef: torch.Tensor, scal: torch.Tensor, grad_out: torch.Tensor,
+                 batch: int, dim: int, temperature: float, negative_weight: float, path: str, grad_scale: float,
+                 out_dtype: int) -> tuple[torch.Tensor, torch.Tensor]:
+    prob = N.Problem(2, batch, dim, 0, 2 * batch, float(temperature), float(negative_weight))
+    code, _ = _plan_py(batch, dim, path)
+    with torch.cuda.device(feat.device):
+        return _backward_impl(_ops(), prob, code, (feat, rnorm, coef, scal), grad_out, grad_scale,
+                              _OUT_DTYPE[out_dtype])
+
+
+@_op_backward.register_fake
+def _(feat, rnorm, coef, scal, grad_out, batch, dim, temperature, negative_weight, path, grad_scale, out_dtype):
+    dt = _OUT_DTYPE[out_dtype]
+    return (torch.empty((batch, dim), dtype=dt, device=feat.device), torch.empty((batch, dim), dtype=dt, device=feat.device))
+
+
+def _op_setup_context(ctx, inputs, output):
+    video, _, temperature, negative_weight, path = inputs
+    _, feat, rnorm, coef, scal = output
+    ctx.save_for_backward(feat, rnorm, coef, scal)
+    ctx.meta = (int(video.shape[0]), int(video.shape[1]), float(temperature), float(negative_weight), path,
+                _DTYPE_CODE[video.dtype])
+
+
+def _op_backward_formula(ctx, g_loss, g_feat, g_rnorm, g_coef, g_scal):
+    feat, rnorm, coef, scal = ctx.saved_tensors
+    B, D, tau, w, path, dcode = ctx.meta
+    dv, dt = torch.ops.crossclr_b200.backward(feat, rnorm, coef, scal, g_loss, B, D, tau, w, path, 1.0, dcode)
+    return dv, dt, None, None, None
+
+
+_op_forward.register_autograd(_op_backward_formula, setup_context=_op_setup_context)
+
+
+def _criterion(video, text, temperature, negative_weight, path, group, grad_scale):
+    """Dispatch: custom ops on a single rank (traceable), the autograd.Function with a process group."""
+    if group is not None:
+        return _CrossCLRFunction.apply(video, text, temperature, negative_weight, path, group, grad_scale)
+    _check_inputs(video, text)
+    if video.dtype == torch.float64:          # kernels compute in fp32; autograd casts the gradients back
+        video, text = video.float(), text.float()
+    loss = torch.ops.crossclr_b200.forward(video, text, float(temperature), float(negative_weight), path)[0]
+    return loss if grad_scale == 1.0 else _ScaleGrad.apply(loss, float(grad_scale))
+
+
+class _ScaleGrad(torch.autograd.Function):
+    """identity forward, gradient times `scale` (the grad_scale knob on a single rank)"""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.scale, None
+
+
 class CrossCLR_onlyIntraModality(nn.Module):
     """CrossCLR Loss between 2 groups of embeddings - Only Intra Modality alignment.
 
@@ -231,12 +327,11 @@ class CrossCLR_onlyIntraModality(nn.Module):
         Returns: 0-dim float64 loss (trainer/loss.py:114)
         """
         # temperature / negative_w are read per call (trainer/loss.py:90-93, :99-100)
-        return _CrossCLRFunction.apply(video_features, text_features, self.temperature, self.negative_w, self.path,
-                                       self.process_group, self.grad_scale)
+        return _criterion(video_features, text_features, self.temperature, self.negative_w, self.path,
+                          self.process_group, self.grad_scale)
 
 
 def crossclr_loss(video_features, text_features, temperature=0.03, negative_weight=0.8, *, process_group=None,
                   grad_scale=1.0, path="auto"):
     """Functional form of `CrossCLR_onlyIntraModality.forward`."""
-    return _CrossCLRFunction.apply(video_features, text_features, temperature, negative_weight, path, process_group,
-                                   grad_scale)
+    return _criterion(video_features, text_features, temperature, negative_weight, path, process_group, grad_scale)

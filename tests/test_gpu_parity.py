@@ -289,6 +289,33 @@ def test_cuda_graph_replay_matches_eager_and_oracle():
         step(vd[:256], td[:256])
 
 
+def test_custom_op_registration_and_torch_compile():
+    """The single-rank criterion is two torch.library custom ops: opcheck passes (schema, fake kernel, autograd
+    registration) and torch.compile traces through it with fullgraph=True, giving the eager numbers."""
+    M = _mod()
+    v, t = _seeded(256, 128, 5, aligned=2.0)
+    vd = torch.from_numpy(v).cuda().requires_grad_()
+    td = torch.from_numpy(t).cuda().requires_grad_()
+    torch.library.opcheck(torch.ops.crossclr_b200.forward.default, (vd.detach(), td.detach(), 0.03, 0.8, "auto"),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    crit = M.CrossCLR_onlyIntraModality(0.03, 0.8).cuda()
+    le = crit(vd, td)
+    le.backward()
+    ref_dv = vd.grad.clone()
+
+    @torch.compile(fullgraph=True, backend="aot_eager")
+    def f(a, b):
+        return crit(a * 1.0, b * 1.0) * 2.0
+
+    vc = torch.from_numpy(v).cuda().requires_grad_()
+    tc = torch.from_numpy(t).cuda().requires_grad_()
+    lc = f(vc, tc)
+    lc.backward()
+    # two runs differ by the order of fp32 atomics in the row sums (1e-8 relative) and what that does to fp16 roundings
+    assert abs(lc.item() - 2.0 * le.item()) <= 1e-6 * abs(le.item())
+    assert (vc.grad - 2.0 * ref_dv).norm() <= 1e-4 * ref_dv.norm()
+
+
 def test_launch_counter_moves():
     M = _mod()
     n0 = M.launch_count()
