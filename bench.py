@@ -68,7 +68,7 @@ def ncu_traffic(workload):
 
 def bwd_kernel_name(D, rows):
     """The backward kernel libcrossclr_b200 selects for this shape (csrc/tc_kernels.cu: launch_bwd_tc)."""
-    if D == 512 and rows >= 12288:
+    if D == 512 and rows >= 8192:
         return "bwd_quad_kernel"
     return "bwd_pair_kernel" if 256 < D <= 1536 else "bwd_tc_kernel"
 
@@ -226,7 +226,8 @@ class ClockSampler:
         use = clocks or allclocks
         use.sort()
         out.update(sm_mhz=(use[len(use) // 2] if use else None), reasons=sorted(reasons), samples=len(clocks),
-                   window_ms=round((self.t1 - self.t0) * 1e3, 1) if self.t0 else None)
+                   window_ms=round((self.t1 - self.t0) * 1e3, 1) if self.t0 else None,
+                   window="value + e2e timed regions + 0.4 s of the same step (untimed) so that nvidia-smi yields samples")
         return out
 
 
@@ -400,6 +401,13 @@ def run_b200_arm(args):
     total_ms = timed_resident(args.steps)
     launches = (kernels_per_step * args.steps) if use_graph else (M.launch_count() - n0)
     e2e_ms = timed_e2e(args.steps)
+    # nvidia-smi delivers a sample every ~15 ms whatever -lms asks for, and the two timed regions together last a few tens
+    # of ms at this step time: keep the same step running (untimed) until the window is long enough to hold samples
+    t_probe = time.time()
+    while time.time() - t_probe < 0.4:
+        for _ in range(50):
+            step_resident()
+        torch.cuda.synchronize()
     if clk is not None:
         clk.end()
     loss_val = float(loss_hosts[(args.steps - 1) & 1])

@@ -2243,12 +2243,13 @@ static int quad_clusters_resident() {
 }
 
 // The quad kernel halves the L2 -> SM operand traffic of the 1 S-CTA + 1 G-CTA kernel, which is what bounds that one
-// (measured on B200, D = 512, quad vs pair: B = 4096 146 vs 146 us, B = 8192 0.449 vs 0.491 ms, B = 16384 1.87 vs
-// 2.28 ms, B = 32768 8.98 vs 9.39 ms).  Used from 12288 stacked rows up; CROSSCLR_BWD_VARIANT=3 forces it.
+// (measured on B200, D = 512, quad vs pair: B = 4096 148-150 vs 150-154 us in three back-to-back A/B runs, B = 8192 0.449
+// vs 0.491 ms, B = 16384 1.87 vs 2.28 ms, B = 32768 8.98 vs 9.39 ms).  Used from 8192 stacked rows up (below that the
+// 4-CTA granularity leaves SMs idle); CROSSCLR_BWD_VARIANT=3 forces it, 2 forces the pair kernel.
 static bool use_quad(const Geometry& g) {
   if (g.dim > 512 || g.dim % 128 != 0 || quad_clusters_resident() * 4 * 10 < sm_count() * 8) return false;
   if (bwd_variant() == 3) return true;
-  return bwd_variant() == 0 && g.dim == 512 && g.rows >= 12288;
+  return bwd_variant() == 0 && g.dim == 512 && g.rows >= 8192;
 }
 
 static int launch_bwd_quad(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CROSSCLR_VERSION 100          /* 0.1.0 */
+#define CROSSCLR_VERSION 110          /* 0.1.1 */
 
 /* error codes */
 #define CROSSCLR_OK            0
