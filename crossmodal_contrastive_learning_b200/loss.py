@@ -256,6 +256,7 @@ def _op_setup_context(ctx, inputs, output):
     video, _, temperature, negative_weight, path = inputs
     _, feat, rnorm, coef, scal = output
     ctx.save_for_backward(feat, rnorm, coef, scal)
+    ctx.set_materialize_grads(False)          # no zero-filled gradients for the four saved-state outputs
     ctx.meta = (int(video.shape[0]), int(video.shape[1]), float(temperature), float(negative_weight), path,
                 _DTYPE_CODE[video.dtype])
 
@@ -263,6 +264,8 @@ def _op_setup_context(ctx, inputs, output):
 def _op_backward_formula(ctx, g_loss, g_feat, g_rnorm, g_coef, g_scal):
     feat, rnorm, coef, scal = ctx.saved_tensors
     B, D, tau, w, path, dcode = ctx.meta
+    if g_loss is None:                        # the loss itself was not used downstream
+        return None, None, None, None, None
     dv, dt = torch.ops.crossclr_b200.backward(feat, rnorm, coef, scal, g_loss, B, D, tau, w, path, 1.0, dcode)
     return dv, dt, None, None, None
 
