@@ -8,6 +8,7 @@ The compute lives in libcrossclr_b200.so (csrc/, C ABI in include/crossclr_b200.
 """
 from .loss import CrossCLR_onlyIntraModality, crossclr_loss  # noqa: F401
 from .graph import GraphedCrossCLR  # noqa: F401
+from .maxmargin import MaxMargin_coot, cosine_sim  # noqa: F401
 from ._native import NativeLibraryError, launch_count, load as load_native  # noqa: F401
 
-__all__ = ["CrossCLR_onlyIntraModality", "crossclr_loss", "GraphedCrossCLR", "NativeLibraryError", "launch_count", "load_native"]
+__all__ = ["CrossCLR_onlyIntraModality", "crossclr_loss", "GraphedCrossCLR", "MaxMargin_coot", "cosine_sim", "NativeLibraryError", "launch_count", "load_native"]

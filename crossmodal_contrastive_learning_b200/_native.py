@@ -22,6 +22,7 @@ EXPORTS = (
     "crossclr_feature_dtype", "crossclr_workspace_bytes", "crossclr_pack", "crossclr_fwd",
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
+    "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
 
@@ -82,6 +83,14 @@ def _declare(lib):
     lib.crossclr_timing_read.argtypes = [c.c_int, c.POINTER(c.c_double), c.POINTER(c.c_int64)]
     lib.crossclr_selftest.restype = c.c_int
     lib.crossclr_selftest.argtypes = [c.c_int, vp, vp, vp, c.c_int32, c.c_int32]
+    lib.crossclr_maxmargin_workspace_bytes.restype = c.c_size_t
+    lib.crossclr_maxmargin_workspace_bytes.argtypes = [c.c_int32]
+    lib.crossclr_maxmargin_fwd.restype = c.c_int
+    lib.crossclr_maxmargin_fwd.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_float, vp,
+                                           c.c_size_t, vp, vp]
+    lib.crossclr_maxmargin_bwd.restype = c.c_int
+    lib.crossclr_maxmargin_bwd.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_float, vp, vp,
+                                           vp, c.c_int64, vp, c.c_int64, c.c_int, vp]
 
 
 def load(build_if_missing: bool = True):

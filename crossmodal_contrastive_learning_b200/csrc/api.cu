@@ -202,6 +202,36 @@ int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const 
                             dv_row_stride, dt, dt_row_stride, out_dtype, st);
 }
 
+size_t crossclr_maxmargin_workspace_bytes(int32_t batch) {
+  return batch >= 1 ? maxmargin_workspace_bytes(batch) : 0;
+}
+
+int crossclr_maxmargin_fwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
+                           int32_t batch, int32_t dim, float margin, void* workspace, size_t workspace_bytes,
+                           double* loss_out, void* stream) {
+  CC_REQUIRE(im && s && workspace && loss_out, "crossclr_maxmargin_fwd: NULL pointer");
+  CC_REQUIRE(batch >= 1 && dim >= 1 && im_row_stride >= dim && s_row_stride >= dim, "crossclr_maxmargin_fwd: bad shape/stride");
+  CC_REQUIRE((int64_t)batch * batch < ((int64_t)1 << 40), "crossclr_maxmargin_fwd: batch too large");
+  if (workspace_bytes < maxmargin_workspace_bytes(batch)) {
+    set_error("crossclr_maxmargin_fwd: workspace too small (%zu < %zu)", workspace_bytes, maxmargin_workspace_bytes(batch));
+    return CROSSCLR_EWORKSPACE;
+  }
+  return launch_maxmargin_fwd(im, im_row_stride, s, s_row_stride, dtype, batch, dim, margin, workspace, loss_out,
+                              (cudaStream_t)stream);
+}
+
+int crossclr_maxmargin_bwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
+                           int32_t batch, int32_t dim, float margin, const void* workspace, const double* grad_out,
+                           void* d_im, int64_t d_im_row_stride, void* d_s, int64_t d_s_row_stride, int out_dtype,
+                           void* stream) {
+  CC_REQUIRE(im && s && workspace && d_im && d_s, "crossclr_maxmargin_bwd: NULL pointer");
+  CC_REQUIRE(batch >= 1 && dim >= 1 && im_row_stride >= dim && s_row_stride >= dim && d_im_row_stride >= dim &&
+                 d_s_row_stride >= dim, "crossclr_maxmargin_bwd: bad shape/stride");
+  CC_REQUIRE((size_t)dim * 32 * sizeof(float) <= 200 * 1024, "crossclr_maxmargin_bwd: dim %d too large for this path", dim);
+  return launch_maxmargin_bwd(im, im_row_stride, s, s_row_stride, dtype, batch, dim, margin, workspace, grad_out, d_im,
+                              d_im_row_stride, d_s, d_s_row_stride, out_dtype, (cudaStream_t)stream);
+}
+
 int crossclr_timing_enable(int on) {
   g_timing_on.store(on ? 1 : 0);
   return CROSSCLR_OK;

@@ -149,4 +149,12 @@ int launch_bwd_tc(const Geometry& g, const void* feat_f16, const float* coef, co
 size_t bwd_pair_scratch_bytes();   // global-memory P-tile rings of the paired backward (D <= 512)
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k);
 
+// maxmargin.cu (MaxMargin_coot, trainer/loss.py:17-41)
+size_t maxmargin_workspace_bytes(int B);
+int launch_maxmargin_fwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
+                         float margin, void* workspace, double* loss, cudaStream_t st);
+int launch_maxmargin_bwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
+                         float margin, const void* workspace, const double* grad_out, void* d_im, int64_t d_im_stride,
+                         void* d_s, int64_t d_s_stride, int out_dtype, cudaStream_t st);
+
 }  // namespace crossclr

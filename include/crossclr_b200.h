@@ -166,6 +166,24 @@ CROSSCLR_API int crossclr_timing_enable(int on);
 CROSSCLR_API int crossclr_timing_read(int kernel, double* total_ms, int64_t* launches);
 
 /*
+ * MaxMargin_coot (trainer/loss.py:17-41; SURVEY.md section 8 row f1 -- beside the CrossCLR hot path).  First correct
+ * path: fp32 CUDA-core kernels, any batch / dim (dim <= 1600), no batch x batch array stored.
+ *   loss_out[0] (double) = (1/B^2) sum_{i != j} [max(0, m + s_ij - s_ii) + max(0, m + s_ij - s_jj)],  s = im s^T
+ * `im`, `s`: [batch][dim] device arrays of `dtype`, row strides in elements.  The forward leaves the diagonal and the
+ * hinge counts in `workspace` (crossclr_maxmargin_workspace_bytes(batch) bytes), which the backward reads; `grad_out`
+ * is a DEVICE pointer to the upstream scalar gradient (double) or NULL for 1.0.
+ * Replaces: trainer/loss.py:29-41 (forward) and its autograd backward.
+ */
+CROSSCLR_API size_t crossclr_maxmargin_workspace_bytes(int32_t batch);
+CROSSCLR_API int crossclr_maxmargin_fwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
+                           int32_t batch, int32_t dim, float margin, void* workspace, size_t workspace_bytes,
+                           double* loss_out, void* stream);
+CROSSCLR_API int crossclr_maxmargin_bwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
+                           int32_t batch, int32_t dim, float margin, const void* workspace, const double* grad_out,
+                           void* d_im, int64_t d_im_row_stride, void* d_s, int64_t d_s_row_stride, int out_dtype,
+                           void* stream);
+
+/*
  * Hardware self-test of the tcgen05/TMA building blocks (descriptor encodings, TMEM layouts).
  * `variant` selects the block under test (0: K-major x K-major, 1: swizzled thread-written A x MN-major
  * B with b given as [k][n], 2: A from TMEM, 3: un-swizzled thread-written A, 4: one cta_group::2 MMA stream over
