@@ -1198,6 +1198,10 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           mbar_arrive(staged_bar(slot));
           if (r == 0) TR(1 + wg, t >> 1, 2 + h);
         }
+        // every warp of the group is done reading this tile's column coefficients before any of them writes the next
+        // tile's (cv is one buffer per group; without this a warp running ahead could overwrite its slice under a
+        // slower warp's last chunks)
+        named_bar_sync(1 + wg, EPI_THREADS);
       }
     }
   } else {
