@@ -65,10 +65,8 @@ class _MaxMarginFunction(torch.autograd.Function):
 
 
 class MaxMargin_coot(nn.Module):
-    """Regular Contrastive Loss between 2 groups of embeddings
-    inputs shape (batch, embed_dim)
-    Ref: COOT: Cooperative Hierarchical Transformer for Video-Text Representation Learning, NeurIPS 2020
-    """
+    """Bidirectional max-margin (hinge) ranking loss over the B x B score matrix of two [B, D] embedding blocks (the COOT
+    loss); drop-in for the reference class of the same name (`trainer/loss.py:17-41`)."""
 
     def __init__(self, use_cuda: bool, margin: float = 0.1):
         super().__init__()                        # (the reference's super(ContrastiveLoss_coot, ...) is a NameError)
