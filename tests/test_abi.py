@@ -74,3 +74,25 @@ def test_module_surface_on_cpu():
         crit(torch.randn(2, 4, 8), torch.randn(2, 4, 8))
     with pytest.raises(ValueError):
         CrossCLR_onlyIntraModality(path="cpu")
+
+
+def test_header_is_plain_c_and_the_c_host_example_links():
+    """include/crossclr_b200.h compiles as C99 and examples/c_host.c links against the in-tree library (no torch, no
+    Python in the signatures): the boundary a non-Python host binds."""
+    import shutil
+    import subprocess
+    import tempfile
+    root = ROOT
+    gcc = shutil.which("gcc")
+    cuda = "/usr/local/cuda"
+    if gcc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    from crossmodal_contrastive_learning_b200 import _native as N
+    N.load()                                               # make sure the library is built
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+               os.path.join(root, "examples", "c_host.c"), "-L", os.path.join(root, "crossmodal_contrastive_learning_b200"),
+               "-lcrossclr_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,--allow-shlib-undefined",
+               "-o", os.path.join(tmp, "c_host")]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
