@@ -23,6 +23,7 @@ EXPORTS = (
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
     "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
+    "crossclr_bwd_kernel_name",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
 
@@ -75,6 +76,8 @@ def _declare(lib):
                                  c.c_int, vp, c.c_size_t, vp]
     lib.crossclr_shift.restype = c.c_float
     lib.crossclr_shift.argtypes = [P]
+    lib.crossclr_bwd_kernel_name.restype = c.c_char_p
+    lib.crossclr_bwd_kernel_name.argtypes = [P, c.c_int]
     lib.crossclr_launch_count.restype = c.c_int64
     lib.crossclr_launch_count.argtypes = []
     lib.crossclr_timing_enable.restype = c.c_int

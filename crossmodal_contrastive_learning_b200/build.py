@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "simt_kernels.cu", "tc_kernels.cu", "maxmargin.cu"]
-HEADERS = ["common.cuh", "tc_ptx.cuh", os.path.join(ROOT, "include", "crossclr_b200.h")]
+SOURCES = ["api.cu", "simt_kernels.cu", "tc_kernels.cu", "flow_kernels.cu", "maxmargin.cu"]
+HEADERS = ["common.cuh", "tc_ptx.cuh", "tc_common.cuh", os.path.join(ROOT, "include", "crossclr_b200.h")]
 LIB = os.path.join(HERE, "libcrossclr_b200.so")
 
 

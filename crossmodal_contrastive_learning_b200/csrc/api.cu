@@ -1,6 +1,7 @@
 // extern "C" entry points of libcrossclr_b200 (see include/crossclr_b200.h for the contract).
 #include "common.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -97,7 +98,9 @@ int crossclr_feature_dtype(int path) {
 }
 
 static size_t workspace_bytes(const crossclr_problem_t* p, int path) {
-  return dfhat_bytes(p) + (path == CROSSCLR_PATH_TC ? bwd_pair_scratch_bytes() : 0);   // + P-tile scratch rings
+  if (path != CROSSCLR_PATH_TC) return dfhat_bytes(p);
+  // + P-tile scratch of the role-specialised backward kernels (cluster rings, or the dataflow kernel's pool + control words)
+  return dfhat_bytes(p) + std::max(bwd_pair_scratch_bytes(), bwd_flow_scratch_bytes(p->nseg * p->bseg, p->row_count));
 }
 
 size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {
@@ -106,6 +109,13 @@ size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {
 }
 
 float crossclr_shift(const crossclr_problem_t* p) { return problem_shift(p); }
+
+const char* crossclr_bwd_kernel_name(const crossclr_problem_t* p, int path) {
+  if (validate_problem(p)) return "";
+  if (path == CROSSCLR_PATH_SIMT) return "bwd_simt_kernel";
+  if (path != CROSSCLR_PATH_TC || !tc_shape_ok(p)) return "";
+  return bwd_tc_kernel_name(make_geometry(p));
+}
 
 int64_t crossclr_launch_count(void) { return g_launches.load(); }
 

@@ -147,6 +147,12 @@ int launch_fwd_tc(const Geometry& g, const void* feat_f16, float* stats, cudaStr
 int launch_bwd_tc(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
                   void* scratch, cudaStream_t st);
 size_t bwd_pair_scratch_bytes();   // global-memory P-tile rings of the paired backward (D <= 512)
+const char* bwd_tc_kernel_name(const Geometry& g);   // the backward kernel launch_bwd_tc picks for this problem
+// flow_kernels.cu: dataflow backward (producer pairs -> P-tile pool -> consumer pairs), D <= 512
+size_t bwd_flow_scratch_bytes(int rows, int row_count);
+bool bwd_flow_applies(const Geometry& g);
+int launch_bwd_flow(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
+                    void* scratch, cudaStream_t st);
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k);
 
 // maxmargin.cu (MaxMargin_coot, trainer/loss.py:17-41)

@@ -15,64 +15,13 @@
 //   warp 2      TMEM allocator
 //   warps 4..7  epilogue       : tcgen05.ld 32x32b (thread = row), exp2 / row sums (fwd) or fp16 P tile (bwd)
 // Synchronisation is mbarrier-only: full/empty per ring stage, full/empty per TMEM accumulator buffer.
-#include "common.cuh"
-#include "tc_ptx.cuh"
-
-#include <cstdlib>
-#include <mutex>
+#include "tc_common.cuh"
 
 namespace crossclr {
 using namespace ptx;
 
 namespace {
 
-constexpr int TM = 128;                 // tile rows (TMEM lanes)
-constexpr int KC = 64;                  // K chunk: 64 fp16 = one 128-byte swizzle row
-constexpr int CHUNK_BYTES = TM * KC * 2;   // 16 KiB: a [128 rows][64 elems] box
-constexpr int MAX_RES_CHUNKS = 8;       // A row block stays resident for D <= 512
-constexpr int FWD_TN = 256;             // forward similarity tile columns (one N=256 MMA)
-constexpr int BWD_TN = 128;             // backward similarity / probability tile columns
-constexpr int SLAB = 256;               // dFhat columns per backward work item (TMEM columns)
-constexpr int MAX_SLOTS = 12;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_WARP0 = 4;
-constexpr int EPI_THREADS = 128;
-
-constexpr uint32_t kIdescS256 = make_idesc_f16(128, 256, 0, 0, 0, 0);   // S = A(K-major) * B(K-major)^T, N = 256
-constexpr uint32_t kIdescS128 = make_idesc_f16(128, 128, 0, 0, 0, 0);   // ... N = 128
-constexpr uint32_t kIdescG128 = make_idesc_f16(128, 128, 0, 0, 0, 1);   // dF += P(K-major) * F_J(MN-major), N = 128
-constexpr uint32_t kIdescG64 = make_idesc_f16(128, 64, 0, 0, 0, 1);     // ... N = 64 (odd chunk counts)
-
-__device__ __forceinline__ uint64_t kmajor_desc(uint32_t addr) { return make_smem_desc_sw128(addr, 1024, 0); }
-
-struct Ring {
-  int stage = 0;
-  uint32_t phase = 0;
-  int n;
-  __device__ explicit Ring(int n_) : n(n_) {}
-  __device__ __forceinline__ void advance() {
-    if (++stage == n) { stage = 0; phase ^= 1; }
-  }
-};
-
-// The 4 K=16 MMAs of one 64-wide K chunk into a 128 x N accumulator (A, B K-major 128-byte-swizzled boxes).
-__device__ __forceinline__ void issue_s_chunk(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
-                                              bool first_chunk) {
-  const uint64_t ad = kmajor_desc(a_addr), bd = kmajor_desc(b_addr);
-#pragma unroll
-  for (int k = 0; k < KC / 16; ++k)
-    umma_ss(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (first_chunk && k == 0) ? 0u : 1u);
-}
-
-// segment bookkeeping of a 128-aligned block of stacked rows starting at `r0`
-struct BlockSeg {
-  int mod;      // modality of the block (0 video / 1 text)
-  int samp0;    // sample index of its first row
-};
-__device__ __forceinline__ BlockSeg block_seg(int r0, int bseg) {
-  const int seg = r0 / bseg;
-  return BlockSeg{seg & 1, (seg >> 1) * bseg + (r0 - seg * bseg)};
-}
 
 // ================================================================================================
 // Forward.  Tile = 128 rows x 256 columns of the stacked Gram matrix; persistent, one CTA per SM.
@@ -932,9 +881,7 @@ constexpr int PAIR_EPI_THREADS = 256;
 constexpr int PAIR_TN = 256;             // S tile columns in the S-CTA
 constexpr int PAIR_PBUF = 3;             // 128-column P tiles in flight in the G-CTA's shared memory
 constexpr int PAIR_NSLOT = 8;            // scratch P tiles per pair in global memory (ring)
-constexpr int PTILE_BYTES = TM * BWD_TN * 2;   // 32 KiB
 constexpr int PAIR_GGROUPS = 4;          // G-CTA ring: groups of four [64 j][64 d] boxes
-constexpr int GBOX_BYTES = 64 * KC * 2;  // 8 KiB
 constexpr int PAIR_HDR = 3072;
 
 struct PairSeg { int ib, j0, j1; bool last_of_ib; };
@@ -1861,6 +1808,16 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     fence_proxy_async_smem();
   }
+  if (variant == 5) {
+    // A in the layout the dataflow backward reads TRANSPOSED: element (m, kk) at (m/8) * (k*16) + kk*16 + (m%8)*2, i.e.
+    // 16-byte chunks of 8 consecutive m, K rows 16 bytes apart: an MN-major operand without swizzle
+    for (int kk = 0; kk < k; ++kk) {
+      const uint16_t val = a_gmem[(size_t)r * k + kk];
+      const uint32_t addr = a_s + (r >> 3) * (k * 16) + kk * 16 + (r & 7) * 2;
+      asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(val) : "memory");
+    }
+    fence_proxy_async_smem();
+  }
   if (variant == 2) {
     // A -> TMEM columns [256, 256 + k/2): lane = row, column c holds elements (2c, 2c+1)
     for (int c0 = 0; c0 < k / 2; c0 += 16) {
@@ -1905,6 +1862,11 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
       for (int k16 = 0; k16 < k / 16; ++k16)
         umma_ss(tmem_base, make_smem_desc_nosw(a_s + k16 * 2 * 2048, 2048, 128),
+                kmajor_desc(b_s + (k16 >> 2) * bchunk) + (k16 & 3) * 2, idesc, k16 ? 1u : 0u);
+    } else if (variant == 5) {
+      const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 1, 0);      // A MN-major: LBO = 8-deep K groups, SBO = MN chunks
+      for (int k16 = 0; k16 < k / 16; ++k16)
+        umma_ss(tmem_base, make_smem_desc_nosw(a_s + k16 * 256, 128, (uint32_t)k * 16u),
                 kmajor_desc(b_s + (k16 >> 2) * bchunk) + (k16 & 3) * 2, idesc, k16 ? 1u : 0u);
     } else {
       const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
@@ -1987,58 +1949,6 @@ selftest_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-// ---- host side ----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// fp16 matrix [rows][cols] (row-major) tiled into {64 cols, box_rows} boxes, 128-byte swizzle (or none)
-int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, bool swizzle = true) {
-  // The driver-API encode needs a current context on THIS thread.  torch's autograd worker threads only get
-  // one lazily (first runtime call), so bind the primary context here; cudaFree(nullptr) is the documented no-op
-  // that does it.
-  static thread_local int bound_dev = -1;
-  int dev = -1;
-  if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_dev) {
-    cudaFree(nullptr);
-    bound_dev = dev;
-  }
-  EncodeTiledFn fn = get_encode_fn();
-  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return CROSSCLR_ECUDA; }
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CROSSCLR_ECUDA; }
-  return CROSSCLR_OK;
-}
-
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
 
 constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;
 
@@ -2052,7 +1962,6 @@ int bwd_variant() {
   }
   return v;
 }
-constexpr size_t kMaxSmem = 232448;      // 227 KiB opt-in dynamic shared memory per CTA
 
 }  // namespace
 
@@ -2288,11 +2197,22 @@ static int launch_bwd_quad(const CUtensorMap& tmap, const void* feat, const Geom
   return check_launch("bwd_quad_kernel");
 }
 
+const char* bwd_tc_kernel_name(const Geometry& g) {
+  if (bwd_flow_applies(g)) return "bwd_flow_kernel";
+  if (use_quad(g)) return "bwd_quad_kernel";
+  if (pair_cluster_size(g.dim)) return "bwd_pair_kernel";
+  return "bwd_tc_kernel";
+}
+
 int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const float* scal, float* dfhat,
                   void* scratch, cudaStream_t st) {
   CUtensorMap tmap;
   int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
   if (rc) return rc;
+  if (bwd_flow_applies(g)) {                           // producer pairs -> P-tile pool -> consumer pairs (flow_kernels.cu)
+    TimedLaunch timed(CROSSCLR_K_BWD, st);
+    return launch_bwd_flow(g, feat, coef, scal, dfhat, scratch, st);
+  }
   if (use_quad(g)) {                                   // S-pair + G-pair, cta_group::2 MMAs
     TimedLaunch timed(CROSSCLR_K_BWD, st);
     return launch_bwd_quad(tmap, feat, g, coef, scal, dfhat, scratch, st);
@@ -2327,7 +2247,7 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
 }
 
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k) {
-  if (variant < 0 || variant > 4 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
+  if (variant < 0 || variant > 5 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
       (variant == 1 && n % 64 != 0) || (variant == 4 && n % 64 != 0)) {
     set_error("crossclr_selftest: unsupported variant/shape (variant %d n %d k %d)", variant, n, k);
     return CROSSCLR_EINVAL;

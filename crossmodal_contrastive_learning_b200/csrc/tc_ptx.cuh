@@ -45,7 +45,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > 200000000u) {            // each failed try_wait suspends for up to ~1 us: seconds in total
+    if (++polls > 20000000u) {             // each failed try_wait suspends for up to ~1 us: seconds in total
 #ifdef CROSSCLR_DEBUG_SYNC
       printf("crossclr: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
 #endif
@@ -128,7 +128,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   if (mbar_try_wait_cluster(bar, parity)) return;
   uint32_t polls = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++polls > 200000000u) __trap();
+    if (++polls > 20000000u) __trap();
   }
 }
 // generic-proxy writes (any shared window, local or remote) -> visible to the async proxy

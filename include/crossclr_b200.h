@@ -147,6 +147,10 @@ CROSSCLR_API int crossclr_bwd(const crossclr_problem_t* p, int path, const void*
 /* The constant log2-domain shift used by fwd/bwd for this problem: max(0, log2e*max(1,|w|)/tau - 96). */
 CROSSCLR_API float crossclr_shift(const crossclr_problem_t* p);
 
+/* Name of the backward similarity/gradient kernel crossclr_bwd launches for this problem and path on the CURRENT device
+ * (bench.py's roofline.kernel); "" if the path does not apply.  Static storage. */
+CROSSCLR_API const char* crossclr_bwd_kernel_name(const crossclr_problem_t* p, int path);
+
 /* Number of kernel launches issued so far by this library in this process (bench.py's gpu_launches). */
 CROSSCLR_API int64_t crossclr_launch_count(void);
 
@@ -187,7 +191,7 @@ CROSSCLR_API int crossclr_maxmargin_bwd(const void* im, const void* s, int dtype
  * Hardware self-test of the tcgen05/TMA building blocks (descriptor encodings, TMEM layouts).
  * `variant` selects the block under test (0: K-major x K-major, 1: swizzled thread-written A x MN-major
  * B with b given as [k][n], 2: A from TMEM, 3: un-swizzled thread-written A, 4: one cta_group::2 MMA stream over
- * a cluster of two CTAs, M = 256); host buffers hold fp16 bit patterns: a [128][k] (variant 4: [256][k]),
+ * a cluster of two CTAs, M = 256, 5: un-swizzled MN-major A = the transposed read of a probability tile); host buffers hold fp16 bit patterns: a [128][k] (variant 4: [256][k]),
  * b [n][k] (variant 1: [k][n]), out [128][n] float (variant 4: [256][n]).  Synchronous (allocates, copies,
  * syncs); tests only.
  */
