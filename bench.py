@@ -8,19 +8,20 @@ One step = one forward + one backward of the criterion over one synthetic [B, D]
 per GPU; the GLOBAL batch is sharded by rows (strong scaling: the global workload is fixed and the same for every N).
 
 Workloads (BASELINE.json `configs`; tau = 0.03, w = 0.8):
-    c2  B=4096   D=512   bf16   (configs[1]; the default at EVERY N, so per-N values are comparable)
-    c3  B=16384  D=1024  bf16   (configs[2])
-    c4  B=65536  D=512   bf16   (configs[3]; global batch -- the meaningful multi-GPU scaling experiment, --workload c4)
-    c5  B=131072 D=1024  bf16   (configs[4]; global batch)
+    c2  B=4096   D=512   bf16   (configs[1]; the headline `value` / `e2e` at EVERY N, the config the reference arm can run)
+    c3  B=16384  D=1024  bf16   (configs[2]; recorded under `workloads` at N = 1)
+    c4  B=65536  D=512   bf16   (configs[3]; global batch, recorded under `workloads` at every N)
+    c5  B=131072 D=1024  bf16   (configs[4]; global batch, recorded under `workloads` at every N)
 
-At one GPU the step is replayed from CUDA graphs (`GraphedCrossCLR`, the package's public capture API; `--no-graph`
-times the eager module instead), and the end-to-end loop is double-buffered: step i+1's host-to-device copy runs on a
-copy stream under step i's kernels, the loss of step i is read back asynchronously.  Every step still pays its own H2D
-copy from pinned memory and its own D2H read inside the timed region.
+The step is ONE CUDA-graph launch (`HostFedCrossCLR`, the package's public capture API; `--no-graph` times the eager
+module instead).  `value`: inputs resident in HBM, graph = pack + forward + backward.  `e2e`: the same step fed from pinned
+host memory -- the H2D copy of step i+1 is captured on a second stream beside step i's kernels and the loss is copied back
+to pinned memory inside the graph, so every step pays its own H2D and D2H inside the timed region.
 
-Printed JSON keys follow the bench contract: value (device-resident), e2e (pinned host buffers, H2D of the
-features and D2H of the loss inside the timed region), roofline (dominant kernel, per-kernel CUDA events from the
-library's timing hooks), cpu_baseline (the reference criterion on this box's host cores), clocks, gpu_launches.
+Printed JSON keys follow the bench contract: value, e2e, roofline (dominant kernel = the backward kernel, named by the
+library, per-kernel CUDA events from the library's timing hooks), cpu_baseline (the reference criterion on this box's host
+cores), clocks, gpu_launches; plus `parity` (each rank's loss / gradients against the CPU oracle, MAX over ranks) and
+`workloads` (the other BASELINE configs, measured in the same process).
 
 `--impl reference` times the reference's own CPU implementation (baseline/_ref/trainer/loss.py, an untracked
 verbatim copy, when present; else the numpy oracle port) on the host cores; nothing of the product runs there.
@@ -57,20 +58,15 @@ def measured_peaks():
         return 1590.0, 1400.0, "fallback"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this workload (or None)."""
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of this workload -- only if
+    that capture is of the kernel the library launches now (else None)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f)[workload]["bytes"]
+            rec = json.load(f)[workload]
+        return rec["bytes"] if rec.get("kernel") == kernel else None
     except Exception:
         return None
-
-
-def bwd_kernel_name(D, rows):
-    """The backward kernel libcrossclr_b200 selects for this shape (csrc/tc_kernels.cu: launch_bwd_tc)."""
-    if D == 512 and rows >= 8192:
-        return "bwd_quad_kernel"
-    return "bwd_pair_kernel" if 256 < D <= 1536 else "bwd_tc_kernel"
 
 
 def cpu_model():
@@ -153,10 +149,10 @@ def run_reference_arm(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    cb, mean, n = time_reference(wl["B"], wl["D"], args.steps, min(args.warmup, 1))
+    cb, mean, n = time_reference(wl["B"], wl["D"], args.steps, args.warmup, max_seconds=900.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": min(args.warmup, 1), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']} (reference CPU path, fp32 features)", "B": wl["B"],
                    "D": wl["D"], "temperature": TAU, "negative_weight": W},
@@ -231,6 +227,130 @@ class ClockSampler:
         return out
 
 
+def synthetic_shard(Bg, D, lo, hi, seed=0):
+    """Rows [lo, hi) of the global synthetic batch (same seed on every rank), bf16, pinned."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(2):
+        dst = torch.empty(hi - lo, D, dtype=torch.bfloat16).pin_memory()
+        chunk = 8192
+        for r0 in range(0, Bg, chunk):
+            blk = torch.randn(min(chunk, Bg - r0), D, generator=g)
+            a, b = max(r0, lo), min(r0 + blk.shape[0], hi)
+            if a < b:
+                dst[a - lo:b - lo] = blk[a - r0:b - r0].to(torch.bfloat16)
+        out.append(dst)
+    return out
+
+
+def kernel_times_eager(crit, v_dev, t_dev, steps, flush, NAT, torch):
+    """Per-kernel device time of eager steps (the library's own stream-ordered cudaEvents, recorded around each launch
+    after all host-side preparation)."""
+    v_e, t_e = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
+    crit(v_e, t_e).backward()
+    torch.cuda.synchronize()
+    NAT.timing_read()
+    NAT.timing_enable(True)
+    for _ in range(steps):
+        flush.zero_()
+        v_e, t_e = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
+        crit(v_e, t_e).backward()
+    torch.cuda.synchronize()
+    NAT.timing_enable(False)
+    return NAT.timing_read()
+
+
+def run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush, steps=3, warmup=2):
+    """One of the other BASELINE configs, eager module calls (host overhead is noise at these sizes): ms/step (device,
+    max over ranks), pairs/s, per-kernel ms, step fraction of the measured sustained bf16 peak."""
+    wl = WORKLOADS[name]
+    Bg, D = wl["B"], wl["D"]
+    Bl = Bg // world
+    need = 26 * Bl * D + 2 * Bg * D * 2 + 40 * Bg + (160 << 20)        # inputs, grads, stacked rows, fp32 accumulator, pool
+    free, _ = torch.cuda.mem_get_info()
+    if free < need:
+        return {"skipped": f"needs ~{need >> 20} MiB of device memory, {free >> 20} MiB free"}
+    v_host, t_host = synthetic_shard(Bg, D, rank * Bl, (rank + 1) * Bl, seed=1)
+    v_dev, t_dev = v_host.to(dev), t_host.to(dev)
+    del v_host, t_host
+    crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group).to(dev)
+
+    def step():
+        v, t = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
+        loss = crit(v, t)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    loss = None
+    for a_, b_ in evs:
+        flush.zero_()
+        a_.record()
+        loss = step()
+        b_.record()
+    torch.cuda.synchronize()
+    per_step = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
+    tt = torch.tensor([per_step[len(per_step) // 2]], dtype=torch.float64, device=dev)      # median step, max over ranks
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    kt = kernel_times_eager(crit, v_dev, t_dev, 2, flush, NAT, torch)
+    _, sustained, _ = measured_peaks()
+    alg = 14.0 * Bg * Bg * D / world
+    name_bwd = bwd_kernel_from_library(M, NAT, world, rank, Bl, D)
+    out = {"workload": wl["desc"], "B_global": Bg, "D": D, "ms_per_step": ms, "pairs_per_s": Bg / (ms * 1e-3), "steps": steps,
+           "ms_per_step_is": "median of the timed eager steps (device events), max over ranks", "ms_steps_this_rank": per_step,
+           "loss": float(loss.item()), "bwd_kernel": name_bwd,
+           "kernel_ms_per_step": {k: v[0] / 2 for k, v in kt.items()},
+           "step_tflops_alg_per_gpu": alg / (ms * 1e-3) / 1e12, "step_frac_of_sustained": alg / (ms * 1e-3) / 1e12 / sustained,
+           "bwd_frac_of_burst": None}
+    bms, bn = kt["bwd"]
+    if bn:
+        burst, _, _ = measured_peaks()
+        out["bwd_frac_of_burst"] = 8.0 * Bg * Bg * D / world / (bms / bn * 1e-3) / 1e12 / burst
+    del v_dev, t_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def bwd_kernel_from_library(M, NAT, world, rank, Bl, D):
+    import ctypes
+    lib = M.load_native()
+    prob = NAT.Problem(2 * world, Bl, D, 2 * rank * Bl, 2 * Bl, TAU, W)
+    code = lib.crossclr_choose_path(ctypes.byref(prob), NAT.BF16, 0)
+    return lib.crossclr_bwd_kernel_name(ctypes.byref(prob), code).decode() if code > 0 else ""
+
+
+def parity_vs_oracle(crit, v_dev, t_dev, v_all, t_all, lo, torch, dist, world, dev, max_rows=256):
+    """This rank's loss and gradients (eager module, fp32 gradients out of bf16-representable fp32 inputs) against the CPU
+    oracle on the concatenated batch, on a sample of the rank's own rows; MAX over ranks.  Checker use of oracle/ only."""
+    import numpy as np
+    from oracle import crossclr_oracle as O
+    v = v_dev.float().detach().requires_grad_()
+    t = t_dev.float().detach().requires_grad_()
+    loss = crit(v, t)
+    loss.backward()
+    torch.cuda.synchronize()
+    Bl = v.shape[0]
+    sel = np.unique(np.linspace(0, Bl - 1, min(max_rows, Bl)).astype(np.int64))
+    rl, rdv, rdt = O.loss_and_grads(v_all, t_all, TAU, W, rows=lo + sel, row_block=1024)
+    dv = v.grad.double().cpu().numpy()[sel]
+    dt = t.grad.double().cpu().numpy()[sel]
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    vals = torch.tensor([abs(loss.item() - rl) / abs(rl), rel(dv, rdv), rel(dt, rdt)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    return {"loss_rel": float(vals[0]), "dv_rel": float(vals[1]), "dt_rel": float(vals[2]), "rows_checked_per_rank": int(len(sel)),
+            "checker": "oracle/crossclr_oracle.py (fp64 restatement pinned by reference-generated goldens) on the concatenated batch",
+            "tolerance": 1e-3, "inputs": "bf16-representable fp32 features, fp32 gradients"}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -256,19 +376,8 @@ def run_b200_arm(args):
     Bg, D = wl["B"], wl["D"]
     assert Bg % world == 0
     Bl = Bg // world
-    g = torch.Generator().manual_seed(0)
     lo, hi = rank * Bl, (rank + 1) * Bl
-    # same seed on every rank; rank r keeps its rows.  Generated in row chunks.
-    v_host = torch.empty(Bl, D, dtype=torch.bfloat16).pin_memory()
-    t_host = torch.empty(Bl, D, dtype=torch.bfloat16).pin_memory()
-    chunk = 8192
-    for name, dst in (("v", v_host), ("t", t_host)):
-        for r0 in range(0, Bg, chunk):
-            blk = torch.randn(min(chunk, Bg - r0), D, generator=g)
-            a, b = max(r0, lo), min(r0 + blk.shape[0], hi)
-            if a < b:
-                dst[a - lo:b - lo] = blk[a - r0:b - r0].to(torch.bfloat16)
-    loss_host = torch.empty((), dtype=torch.float64).pin_memory()
+    v_host, t_host = synthetic_shard(Bg, D, lo, hi)
 
     crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group).to(dev)
     v_dev = v_host.to(dev)
@@ -283,17 +392,21 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
 
     n_cap0 = M.launch_count()
-    runners, kernels_per_step = None, None
+    resident, pipe, kernels_per_step = None, None, None
     if use_graph:
-        # two captured instances: the end-to-end loop alternates between them so that the H2D copy of the next step can
-        # land in one instance's static inputs while the other instance's kernels run
+        # The whole step is ONE graph launch (HostFedCrossCLR, the package's public capture API): `resident` = forward +
+        # backward on device-resident inputs; `pipe` = the same plus, on a second captured stream, the H2D copy of the next
+        # step's inputs from pinned memory and the D2H copy of the loss.
         try:
-            runners = [M.GraphedCrossCLR(crit, Bl, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
-            for r in runners:
-                r.video.detach().copy_(v_dev)
-                r.text.detach().copy_(t_dev)
-            # kernels per captured step = library launches during one capture (warm-up steps launch the same set)
-            kernels_per_step = (M.launch_count() - n_cap0) // (2 * 4)
+            resident = M.HostFedCrossCLR(crit, Bl, D, dtype=torch.bfloat16, device=dev, feed="device")
+            n_cap1 = M.launch_count()
+            kernels_per_step = (n_cap1 - n_cap0) // (2 * 4)      # 3 warm-up steps + 1 capture, for each of two buffer sets
+            pipe = M.HostFedCrossCLR(crit, Bl, D, dtype=torch.bfloat16, device=dev, feed="host")
+            for s in range(2):
+                resident.video[s].detach().copy_(v_dev)
+                resident.text[s].detach().copy_(t_dev)
+                pipe.host_video[s].copy_(v_host)
+                pipe.host_text[s].copy_(t_host)
             ok = 1
         except Exception as exc:          # e.g. a collective that cannot be captured on this stack: time the eager module
             graph_note = f"capture failed ({type(exc).__name__}: {str(exc)[:120]})"
@@ -303,16 +416,12 @@ def run_b200_arm(args):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             ok = int(flag.item())
         if not ok:
-            use_graph, runners = False, None
+            use_graph, resident, pipe = False, None, None
 
     def step_resident():
         if use_graph:
-            r = runners[0]
-            r.video.grad = None
-            r.text.grad = None
-            loss = r(r.video, r.text)
-            loss.backward()
-            return loss
+            resident.step()
+            return None
         v = v_dev.detach().requires_grad_()
         t = t_dev.detach().requires_grad_()
         loss = crit(v, t)
@@ -335,64 +444,39 @@ def run_b200_arm(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    loss_hosts = [torch.empty((), dtype=torch.float64).pin_memory() for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    loss_host_eager = torch.empty((), dtype=torch.float64).pin_memory()
 
     def timed_e2e(steps):
-        """Device time of `steps` end-to-end steps: H2D of the step's inputs from pinned memory, fwd+bwd, D2H of the loss.
-        Graph mode: double-buffered (copy stream), one event pair around the whole loop; eager mode: serial steps."""
-        main = torch.cuda.current_stream()
+        """Device time of `steps` end-to-end steps through the public API: every step's inputs cross PCIe from pinned host
+        memory and its loss is read back, all inside the timed region.  Graph mode: one launch per step, the upload of step
+        i+1 captured beside the kernels of step i; eager mode: serial copy, step, read-back."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if not use_graph:
-            barrier()
-            e0.record()
-            for i in range(steps):
+        barrier()
+        e0.record()
+        if use_graph:
+            pipe.prime()
+            for _ in range(steps):
+                pipe.step()
+            pipe.drain()
+        else:
+            for _ in range(steps):
                 v_dev.copy_(v_host, non_blocking=True)
                 t_dev.copy_(t_host, non_blocking=True)
                 loss = step_resident()
-                loss_hosts[i & 1].copy_(loss.detach(), non_blocking=True)
-            e1.record()
-            barrier()
-        else:
-            h2d_done = [torch.cuda.Event() for _ in range(2)]
-            inputs_free = [torch.cuda.Event() for _ in range(2)]
-            barrier()
-            e0.record()
-            copy_stream.wait_stream(main)
-
-            def issue_h2d(i):
-                r = runners[i & 1]
-                with torch.cuda.stream(copy_stream):
-                    if i >= 2:
-                        copy_stream.wait_event(inputs_free[i & 1])      # step i-2 has consumed these buffers
-                    r.video.detach().copy_(v_host, non_blocking=True)
-                    r.text.detach().copy_(t_host, non_blocking=True)
-                    h2d_done[i & 1].record(copy_stream)
-
-            issue_h2d(0)
-            for i in range(steps):
-                if i + 1 < steps:
-                    issue_h2d(i + 1)
-                r = runners[i & 1]
-                main.wait_event(h2d_done[i & 1])
-                r.video.grad = None
-                r.text.grad = None
-                loss = r(r.video, r.text)
-                inputs_free[i & 1].record(main)                         # the pack kernel (first in the graph) read them;
-                loss.backward()                                         # recorded after the forward graph to be safe
-                loss_hosts[i & 1].copy_(loss.detach(), non_blocking=True)
-            e1.record()
-            barrier()
+                loss_host_eager.copy_(loss.detach(), non_blocking=True)
+        e1.record()
+        barrier()
         total = e0.elapsed_time(e1)
         tt = torch.tensor([total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    warm = max(args.warmup, 3)
     clk = ClockSampler(local_rank) if rank == 0 else None   # started early: nvidia-smi takes a moment to produce its first sample
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         step_resident()
-    timed_e2e(3)
+    timed_e2e(warm)
     torch.cuda.synchronize()
 
     n0 = M.launch_count()
@@ -410,21 +494,29 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
     if clk is not None:
         clk.end()
-    loss_val = float(loss_hosts[(args.steps - 1) & 1])
+    loss_val = float(pipe.loss_host[(pipe._k - 1) & 1]) if use_graph else float(loss_host_eager)
 
-    # second pass, eager, with the library's per-kernel events on (its own stream-ordered cudaEvents)
-    v_e, t_e = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
-    crit(v_e, t_e).backward()
-    NAT.timing_enable(True)
+    # per-kernel device times: eager steps behind a spin kernel (no host gaps inside the event brackets)
+    ktimes = kernel_times_eager(crit, v_dev, t_dev, args.steps, flush, NAT, torch)
     barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        v_e, t_e = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
-        crit(v_e, t_e).backward()
-    torch.cuda.synchronize()
-    NAT.timing_enable(False)
-    ktimes = NAT.timing_read()
-    barrier()
+
+    parity = None
+    if not args.no_parity:
+        # every rank regenerates the global batch (same seed) for the checker
+        va, ta = synthetic_shard(Bg, D, 0, Bg)
+        parity = parity_vs_oracle(crit, v_dev, t_dev, va.float().numpy(), ta.float().numpy(), lo, torch, dist, world, dev)
+        del va, ta
+
+    extras = {}
+    if not args.no_extras:
+        for name in (["c3"] if world == 1 else []) + ["c4", "c5"]:
+            if name == args.workload:
+                continue
+            try:
+                extras[name] = run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush)
+            except Exception as exc:
+                extras[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            barrier()
 
     cb = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -441,29 +533,33 @@ def run_b200_arm(args):
         alg_bwd = 8.0 * Bg * Bg * D / world
         alg_fwd = 6.0 * Bg * Bg * D / world
         achieved = alg_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
+        kname = bwd_kernel_from_library(M, NAT, world, rank, Bl, D)
+        traffic = ncu_traffic(args.workload, kname)
         line = {
             "metric": METRIC, "value": Bg / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16 (tensor-core operands; f32 accumulate; bf16 features in, bf16 grads out)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {wl['desc']}", "B_global": Bg, "B_per_gpu": Bl, "D": D,
                        "temperature": TAU, "negative_weight": W,
                        "l2": "value: flushed between steps (256 MiB write); e2e: each step's inputs arrive by H2D copy",
-                       "launch": ("CUDA graphs (GraphedCrossCLR: forward graph + backward graph per step"
+                       "launch": ("one CUDA graph launch per step (HostFedCrossCLR: pack + forward + backward"
                                   + (", NCCL all-gathers captured" if world > 1 else "") + ")" if use_graph
                                   else "eager module calls" + (f"; {graph_note}" if graph_note else "")),
                        "parallelism": f"row-sharded x{world}, NCCL all-gather of features + row stats" if world > 1 else "single GPU",
                        "loss": loss_val},
             "e2e": {"value": Bg / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8,
-                    "pipeline": ("double-buffered: H2D of step i+1 on a copy stream under step i's kernels; loss read back "
-                                 "asynchronously" if use_graph else "serial")},
+                    "pipeline": ("one graph launch per step (pack + forward + backward); the H2D copy of step i+1 and the D2H copy of "
+                                 "step i-1's loss run on a copy stream beside step i's kernels" if use_graph else "serial")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": bwd_kernel_name(D, 2 * Bg),
+            "roofline": {"bound": "tensor", "kernel": kname,
                          "achieved": achieved, "peak": burst,
-                         "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": ncu_traffic(args.workload),
+                         "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": traffic,
                          "peak_source": f"{src} bf16_tflops (burst; kernel timed alone with CUDA events)",
                          "algorithmic_flops_per_launch": alg_bwd, "avg_launch_ms": bwd_ms, "launches_timed": bwd_n,
+                         "timing": "library cudaEvents on the launching stream around the backward launch (control-word memset + "
+                                   "kernel), recorded after all host-side preparation; eager steps",
                          "fwd_kernel": {"avg_launch_ms": fwd_ms, "algorithmic_flops_per_launch": alg_fwd,
                                         "achieved": (alg_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None)},
                          "step": {"algorithmic_flops": 14.0 * Bg * Bg * D / world,
@@ -472,13 +568,17 @@ def run_b200_arm(args):
                          "kernel_ms_per_step": {k: ms / args.steps for k, (ms, n) in ktimes.items()}},
             "clocks": clk.summary(),
         }
+        if parity is not None:
+            line["parity"] = parity
+        if extras:
+            line["workloads"] = extras
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
         # Captured graphs hold NCCL kernels; tearing the communicator down under them hung at exit on this stack.  The
         # result is printed: drop the graphs, make sure every rank is done, and leave without the teardown.
-        runners = None
+        resident = pipe = None
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
@@ -495,6 +595,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of CUDA-graph replays")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (c3 / c4 / c5 records)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the per-rank oracle check of the headline workload")
     ap.add_argument("--shape", default=None, help="experiment override B,D (not a BASELINE config)")
     args = ap.parse_args()
     if args.workload is None:

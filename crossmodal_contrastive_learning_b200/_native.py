@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libcrossclr_b200.so")
 # element types / paths (mirror include/crossclr_b200.h)
 F32, F16, BF16 = 0, 1, 2
 PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+ROW_TAIL = 64      # CROSSCLR_ROW_TAIL: extra elements per stacked row on the tensor-core paths (residual scale)
 
 EXPORTS = (
     "crossclr_version", "crossclr_last_error", "crossclr_device_supported", "crossclr_choose_path",
@@ -23,7 +24,7 @@ EXPORTS = (
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
     "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
-    "crossclr_bwd_kernel_name",
+    "crossclr_bwd_kernel_name", "crossclr_feature_pitch",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
 
@@ -59,6 +60,8 @@ def _declare(lib):
     lib.crossclr_choose_path.argtypes = [P, c.c_int, c.c_int]
     lib.crossclr_feature_dtype.restype = c.c_int
     lib.crossclr_feature_dtype.argtypes = [c.c_int]
+    lib.crossclr_feature_pitch.restype = c.c_int64
+    lib.crossclr_feature_pitch.argtypes = [c.c_int, c.c_int32]
     lib.crossclr_workspace_bytes.restype = c.c_size_t
     lib.crossclr_workspace_bytes.argtypes = [P, c.c_int]
     lib.crossclr_pack.restype = c.c_int

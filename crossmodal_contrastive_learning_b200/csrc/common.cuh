@@ -65,6 +65,7 @@ inline int check_launch(const char* what) {
 struct Geometry {
   int nseg, bseg, dim, rows;       // rows = nseg * bseg
   int row_begin, row_count;
+  int pitch;                       // row pitch of the stacked matrix in elements (dim, or dim + CROSSCLR_ROW_TAIL on the TC path)
   float k_inter;                   // log2e / tau
   float k_intra;                   // w * log2e / tau
   float shift;                     // log2-domain shift
@@ -78,10 +79,13 @@ inline float problem_shift(const crossclr_problem_t* p) {
   return fmaxf(0.0f, lmax - kShiftHeadroom);
 }
 
-inline Geometry make_geometry(const crossclr_problem_t* p) {
+inline bool path_is_tc(int path) { return path == CROSSCLR_PATH_TC; }
+
+inline Geometry make_geometry(const crossclr_problem_t* p, int path = CROSSCLR_PATH_SIMT) {
   Geometry g;
   g.nseg = p->nseg; g.bseg = p->bseg; g.dim = p->dim; g.rows = p->nseg * p->bseg;
   g.row_begin = p->row_begin; g.row_count = p->row_count;
+  g.pitch = path_is_tc(path) ? p->dim + CROSSCLR_ROW_TAIL : p->dim;
   g.inv_tau = 1.0f / p->temperature;
   g.k_inter = kLog2e / p->temperature;
   g.k_intra = p->negative_weight * kLog2e / p->temperature;
@@ -131,19 +135,27 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(f
 
 // ---- entry points implemented per translation unit --------------------------------------------
 // simt_kernels.cu
+// out pitch: dim (fp32 rows) or dim + CROSSCLR_ROW_TAIL (16-bit rows with the residual scale in the tail)
 int launch_pack(const void* x, int in_dtype, int64_t stride, int rows, int dim, void* out, int out_dtype,
                 float* rnorm, cudaStream_t st);
+// stats_zero / ticket_zero (optional): the [2 rows][2] row statistics and the forward's finalize ticket, zeroed in the same
+// launch (or by memsets when the generic kernels run)
 int launch_pack2(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int dim, void* out,
-                 int out_dtype, float* rnorm, cudaStream_t st);
+                 int out_dtype, float* rnorm, cudaStream_t st, float* stats_zero = nullptr,
+                 unsigned int* ticket_zero = nullptr);
 int launch_fwd_simt(const Geometry& g, const float* feat, float* stats, cudaStream_t st);
 int launch_bwd_simt(const Geometry& g, const float* feat, const float* coef, float* dfhat, cudaStream_t st);
 int launch_finalize(const Geometry& g, const float* stats, float* coef, double* loss, float* scal, cudaStream_t st);
+// feat_dtype CROSSCLR_F32: plain normalised rows (pitch dim); CROSSCLR_F16 / BF16: (f, q) rows of the TC paths
 int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm_owned,
                        const float* coef, const float* scal, bool use_sigma, const double* grad_out,
                        float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,
                        int64_t dt_stride, int out_dtype, cudaStream_t st);
 // tc_kernels.cu
-int launch_fwd_tc(const Geometry& g, const void* feat_f16, float* stats, cudaStream_t st);
+// fused finalize (single rank, all rows owned): the last CTA of the forward writes coef / loss / scal; `ticket` must be 0
+struct FwdFinalize { float* coef; double* loss; float* scal; unsigned int* ticket; };
+bool fwd_tc_can_finalize(const Geometry& g);
+int launch_fwd_tc(const Geometry& g, const void* feat_f16, float* stats, cudaStream_t st, const FwdFinalize* fin = nullptr);
 int launch_bwd_tc(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
                   void* scratch, cudaStream_t st);
 size_t bwd_pair_scratch_bytes();   // global-memory P-tile rings of the paired backward (D <= 512)

@@ -36,9 +36,8 @@ constexpr int FLOW_PBUF = 3;             // 32 KiB P sub-tiles in flight in a co
 constexpr int FLOW_GGROUPS = 4;          // consumer ring: groups of dim/128 [64 j][64 d] boxes
 constexpr int FLOW_DQ = 8;               // descriptors in flight inside a consumer CTA
 constexpr int FLOW_TN = 256;             // S tile columns
-constexpr int FLOW_HDR = 1024 + 8 * 2 * 128 * 4 + 1024;   // barriers | per-warp column coefficients | pad: 10 KiB
+constexpr int FLOW_HDR = 1024 + 8 * 2 * 128 * 8 + 1024;   // barriers | per-warp column coefficient pairs | pad: 18 KiB
 constexpr uint16_t kMaskPair = 0x3;
-constexpr uint32_t kIdescS256x2f = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
 struct FlowParams {
   int n_g, n_s;          // consumer pairs, producer pairs
@@ -157,8 +156,8 @@ struct FlowProdWalk {
 
 __global__ void __launch_bounds__(FLOW_THREADS, 1)
 bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
-                const __grid_constant__ CUtensorMap tmap_p, Geometry g, const float* __restrict__ coef,
-                const float* __restrict__ scal, float* __restrict__ dfhat, FlowParams P) {
+                const __grid_constant__ CUtensorMap tmap_p, const uint8_t* __restrict__ feat, Geometry g,
+                const float* __restrict__ coef, const float* __restrict__ scal, float* __restrict__ dfhat, FlowParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
@@ -177,7 +176,8 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t tmem_slot = base + 560u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 560);
   volatile uint32_t* dq = reinterpret_cast<volatile uint32_t*>(smem_raw + 576);   // consumer: [FLOW_DQ] descriptor words
-  float* cvw = reinterpret_cast<float*>(smem_raw + 1024);           // producer: [8 epilogue warps][2 tile parities][128]
+  float2* cvw = reinterpret_cast<float2*>(smem_raw + 1024);         // producer: [8 epilogue warps][2 tile parities][128] (q_j, w_j)
+  const uint32_t idesc_s = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
   // debug timeline: producer 0 and consumer 0 (leader CTAs) stamp %globaltimer per tile / event
   auto TR = [&](int role, uint32_t tile, int ev) {
@@ -273,7 +273,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             const uint64_t bd = kmajor_desc(ring_base + ring.stage * CHUNK_BYTES);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
-              umma_ss_2sm(tmem_base + buf * FLOW_TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdescS256x2f,
+              umma_ss_2sm(tmem_base + buf * FLOW_TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s,
                           (kc == 0 && k == 0) ? 0u : 1u);
             umma_commit_2sm(empty_bar(ring.stage), kMaskPair);
           }
@@ -357,19 +357,22 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const uint32_t sempty_ldr0 = mapa_cluster(sempty_bar(0), 0), sempty_ldr1 = mapa_cluster(sempty_bar(1), 0);
       // un-swizzled K-major operand layout of a sub-tile: [16 column chunks of 8][128 rows][16 bytes]
       uint8_t* const p_pool = P.pool + ((size_t)prod * FLOW_NSLOT * 4 + sub * 2 + wg) * PTILE_BYTES + (size_t)r * 16;
-      float* const cv_warp = cvw + (warp - EPI_WARP0) * 256;        // [tile parity][128], private to the warp
+      float2* const cv_warp = cvw + (warp - EPI_WARP0) * 256;       // [tile parity][128], private to the warp
       const float* const coef_col = coef + 2 * (int64_t)(wg * TM + lane);
       FlowProdWalk walk(P, prod);
       FlowTile tl, nx;
       bool have = walk.next(tl);
       int cur_I = -1, gi = 0;
       BlockSeg bi{0, 0};
-      float iz_i = 0.f;
-      float izj[4] = {0.f, 0.f, 0.f, 0.f};
+      float iz_i = 0.f, q_i = 1.f, nshift_i = nshift;
+      float izj[4] = {0.f, 0.f, 0.f, 0.f}, qj[4] = {1.f, 1.f, 1.f, 1.f};
       uint32_t va[32], vb[32];
       if (have) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) izj[q] = coef_col[2 * ((int64_t)tl.J * FLOW_TN + 32 * q)];
+        for (int q = 0; q < 4; ++q) {
+          izj[q] = coef_col[2 * ((int64_t)tl.J * FLOW_TN + 32 * q)];
+          qj[q] = row_q(feat, g, (int64_t)tl.J * FLOW_TN + wg * TM + lane + 32 * q);
+        }
         mbar_wait(sfull_bar(0), 0);                                  // prologue of the pipeline: chunk 0 of tile 0
         tc_fence_after();
         tmem_ld32(lane_base, va);
@@ -383,19 +386,24 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           gi = row0 + r;
           bi = block_seg(row0, g.bseg);
           iz_i = coef[2 * (int64_t)gi];
-        }
+          q_i = row_q(feat, g, gi);
+          nshift_i = nshift + log2f(q_i);                // the tile is P q_g q_j -- symmetric, so that its transposed read is
+        }                                                // valid; q_g rides in the exponent, grad_finish divides it out
         const int jrow0 = tl.J * FLOW_TN + wg * TM;
         const BlockSeg bj = block_seg(jrow0, g.bseg);
         const bool same_mod = (bj.mod == bi.mod);
         const bool diag_tile = (bj.samp0 == bi.samp0);
-        const float k = same_mod ? g.k_intra : g.k_inter;
+        const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;   // row part of the logit scale
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
-        float* cv = cv_warp + (t & 1) * TM;
+        float2* cv = cv_warp + (t & 1) * TM;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cv[32 * q + lane] = izj[q] * ks;
+        for (int q = 0; q < 4; ++q) cv[32 * q + lane] = make_float2(qj[q], izj[q] * ks * qj[q]);   // q_j, q_j kappa sigma / Z_j
         if (have_next) {                                             // next tile's column coefficients, a whole tile ahead
 #pragma unroll
-          for (int q = 0; q < 4; ++q) izj[q] = coef_col[2 * ((int64_t)nx.J * FLOW_TN + 32 * q)];
+          for (int q = 0; q < 4; ++q) {
+            izj[q] = coef_col[2 * ((int64_t)nx.J * FLOW_TN + 32 * q)];
+            qj[q] = row_q(feat, g, (int64_t)nx.J * FLOW_TN + wg * TM + lane + 32 * q);
+          }
         }
         __syncwarp();
         const float a_i = iz_i * ks;
@@ -419,15 +427,13 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           uint32_t packed[16];
           const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 cc = cv4[q >> 2];
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
-            const float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
-            const float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
-            __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
-            packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
-            packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+          for (int q = 0; q < 32; q += 2) {
+            const float4 cc = cv4[q >> 1];                         // (q_j, w_j) of columns q, q + 1
+            // P~ = 2^x (1/Z_g + 1/Z_j) kappa sigma q_g q_j,  x = (f_g . f_j) (k q_g) q_j - shift     (q_g dF_g = sum_j P~ f_j)
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]) * k, cc.x, nshift_i)) * fmaf(a_i, cc.x, cc.y);
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]) * k, cc.z, nshift_i)) * fmaf(a_i, cc.z, cc.w);
+            __half2 h0 = __floats2half2_rn(e0, e1);
+            packed[q >> 1] = *reinterpret_cast<uint32_t*>(&h0);
           }
           if (diag_tile && c == quadw) {                              // warp-uniform: this chunk holds column r of the sub-tile
             const int pi = (r & 31) >> 1;                             // same-sample pair: handled in grad_finish
@@ -787,9 +793,9 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   const FlowPlan f = flow_plan(g, pairs);
   if (!f.ok) { set_error("crossclr_bwd: the dataflow kernel does not apply to this problem"); return CROSSCLR_EINVAL; }
   CUtensorMap tmap, tmap64, tmap_p;
-  int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
+  int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
-  rc = make_tmap_f16(&tmap64, feat, (uint64_t)g.rows, (uint64_t)g.dim, 64);
+  rc = CC_FEAT_TMAP(&tmap64, feat, g, 64);
   if (rc) return rc;
   const size_t ctl_bytes = flow_control_bytes(f.nrb, f.nb, sm_count() / 2);
   uint8_t* pool = (uint8_t*)scratch + ctl_bytes;
@@ -807,6 +813,7 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   static const int exp_flags = env_int("CROSSCLR_FLOW_EXP", 0);
   P.exp = exp_flags;
   CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+  TimedLaunch timed(CROSSCLR_K_BWD, st);               // after the host-side preparation: the bracket holds device work only
   CC_CHECK_CUDA(cudaMemsetAsync(scratch, 0, ctl_bytes, st));
   if (f.parts > 1) CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   cudaLaunchConfig_t cfg = {};
@@ -818,7 +825,7 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_flow_kernel, tmap, tmap64, tmap_p, g, coef, scal, dfhat, P));
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_flow_kernel, tmap, tmap64, tmap_p, (const uint8_t*)feat, g, coef, scal, dfhat, P));
   flow_trace_dump(P.trace, st, f);
   return check_launch("bwd_flow_kernel");
 }

@@ -4,78 +4,71 @@
 //     on-device cross-check for the tcgen05 path).
 // Math follows trainer/loss.py:79-114 of the reference as restated in SURVEY.md App. A.
 #include "common.cuh"
+#include "finalize.cuh"
 
 namespace crossclr {
 
 // ================================================================================================
-// pack: L2-normalise one modality block into its segment of the stacked matrix (trainer/loss.py:79-80,
-// F.normalize with eps 1e-12) and keep the reciprocal norms for the backward.  One warp per row.
-template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ x, int64_t stride, int rows, int dim,
-                                                  Tout* __restrict__ out, float* __restrict__ rnorm) {
+// pack: one modality block -> its segment of the stacked matrix (trainer/loss.py:79-80, F.normalize with eps 1e-12) and
+// the reciprocal norms for the backward.  One warp per row.  Two row formats (include/crossclr_b200.h):
+//   fp32 rows (SIMT path), pitch dim: x / max(||x||, eps)
+//   16-bit rows (TC paths), pitch dim + CROSSCLR_ROW_TAIL, the fp32 residual scale q in the first tail word:
+//       16-bit inputs: f = fp16(x * 2^-e) (exact, also for bf16: 8 significant bits below 1), q = 2^e / max(||x||, eps)
+//       fp32 inputs:   f = fp16(x / max(||x||, eps)), q = 1                                (the normalised row is q * f)
+// Power-of-two split of the reciprocal norm: rn = q * pow2 with ||x * pow2|| in [1, 2) and q in (1/2, 1], so that the
+// symmetric probability tile P q_g q_j of the backward never exceeds P.  Rows inside the eps clamp (||x|| < 1e-12, among
+// them all-zero rows) are stored normalised instead (x * 1e12, rounded to fp16, q = 1): their logits are ~0 either way.
+__device__ __forceinline__ void split_rnorm(float norm, float rn, float& pow2, float& q) {
+  if (!(norm >= kEps)) { pow2 = rn; q = 1.0f; return; }
+  int e = 0;
+  (void)frexpf(norm, &e);                                  // norm = m * 2^e, m in [1/2, 1)
+  e = min(127, e);
+  pow2 = exp2f((float)(1 - e));
+  q = rn * exp2f((float)(e - 1));
+}
+
+template <typename Tin, typename Tout, bool kRaw>
+__global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ xv, const Tin* __restrict__ xt, int64_t sv,
+                                                  int64_t st_, int rows, int nmod, int dim, Tout* __restrict__ out,
+                                                  int64_t pitch, float* __restrict__ rnorm, float2* __restrict__ stats_zero,
+                                                  unsigned int* __restrict__ ticket_zero) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const Tin* src = x + (int64_t)row * stride;
-  Tout* dst = out + (int64_t)row * dim;
+  if (row >= nmod * rows) return;
+  if (stats_zero != nullptr && lane == 0) stats_zero[row] = make_float2(0.f, 0.f);   // the forward accumulates into it
+  if (ticket_zero != nullptr && row == 0 && lane == 0) *ticket_zero = 0u;
+  const Tin* src = row < rows ? xv + (int64_t)row * sv : xt + (int64_t)(row - rows) * st_;
+  Tout* dst = out + (int64_t)row * pitch;
   float ss = 0.f;
   for (int d = lane; d < dim; d += 32) {
     const float f = to_float<Tin>(src[d]);
     ss = fmaf(f, f, ss);
   }
   ss = warp_sum(ss);
-  const float rn = 1.0f / fmaxf(sqrtf(ss), kEps);
-  for (int d = lane; d < dim; d += 32) dst[d] = from_float<Tout>(to_float<Tin>(src[d]) * rn);
-  if (lane == 0) rnorm[row] = rn;
+  const float norm = sqrtf(ss);
+  const float rn = 1.0f / fmaxf(norm, kEps);
+  float mul = rn, q = 1.0f;
+  if (kRaw) split_rnorm(norm, rn, mul, q);
+  for (int d = lane; d < dim; d += 32) dst[d] = from_float<Tout>(to_float<Tin>(src[d]) * mul);
+  if (lane == 0) {
+    rnorm[row] = rn;
+    if (pitch > dim) *reinterpret_cast<float*>(dst + dim) = q;
+  }
 }
 
-// bf16 -> fp16 fast path: 16-byte vectors (requires dim % 8 == 0, 16B-aligned rows)
-__global__ void __launch_bounds__(256) pack_bf16_f16_vec_kernel(const uint4* __restrict__ x, int64_t stride_vec,
-                                                               int rows, int dim_vec, uint4* __restrict__ out,
-                                                               float* __restrict__ rnorm) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const uint4* src = x + (int64_t)row * stride_vec;
-  uint4* dst = out + (int64_t)row * dim_vec;
-  float ss = 0.f;
-  for (int d = lane; d < dim_vec; d += 32) {
-    const uint4 u = __ldg(src + d);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      ss = fmaf(f.x, f.x, ss);
-      ss = fmaf(f.y, f.y, ss);
-    }
-  }
-  ss = warp_sum(ss);
-  const float rn = 1.0f / fmaxf(sqrtf(ss), kEps);
-  for (int d = lane; d < dim_vec; d += 32) {
-    const uint4 u = __ldg(src + d);     // second pass hits L1/L2
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-    uint4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      oh[i] = __floats2half2_rn(f.x * rn, f.y * rn);
-    }
-    dst[d] = o;
-  }
-  if (lane == 0) rnorm[row] = rn;
-}
-
-// Both modalities of one rank in one launch (rows [0, rows) from xv, [rows, 2 rows) from xt), bf16 -> fp16, rows
-// cached in registers between the norm and the scale pass (dim <= 1024).  out: [2 rows][dim], rnorm: [2 rows].
-__global__ void __launch_bounds__(256) pack2_bf16_f16_kernel(const uint4* __restrict__ xv, const uint4* __restrict__ xt,
+// bf16 -> fp16 rows, both modalities of one rank in one launch, 16-byte vectors held in registers between the norm and the
+// scale pass (dim <= 1024, dim % 8 == 0).  The rescale is exact: a power of two.
+__global__ void __launch_bounds__(256) pack2_bf16_raw_kernel(const uint4* __restrict__ xv, const uint4* __restrict__ xt,
                                                             int64_t sv_vec, int64_t st_vec, int rows, int dim_vec,
-                                                            uint4* __restrict__ out, float* __restrict__ rnorm) {
+                                                            uint4* __restrict__ out, int64_t pitch_vec, float* __restrict__ rnorm,
+                                                            float2* __restrict__ stats_zero, unsigned int* __restrict__ ticket_zero) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= 2 * rows) return;
+  if (stats_zero != nullptr && lane == 0) stats_zero[row] = make_float2(0.f, 0.f);
+  if (ticket_zero != nullptr && row == 0 && lane == 0) *ticket_zero = 0u;
   const uint4* src = row < rows ? xv + (int64_t)row * sv_vec : xt + (int64_t)(row - rows) * st_vec;
-  uint4* dst = out + (int64_t)row * dim_vec;
+  uint4* dst = out + (int64_t)row * pitch_vec;
   uint4 u[4];
   float ss = 0.f;
 #pragma unroll
@@ -93,7 +86,10 @@ __global__ void __launch_bounds__(256) pack2_bf16_f16_kernel(const uint4* __rest
     }
   }
   ss = warp_sum(ss);
-  const float rn = 1.0f / fmaxf(sqrtf(ss), kEps);
+  const float norm = sqrtf(ss);
+  const float rn = 1.0f / fmaxf(norm, kEps);
+  float mul, q;
+  split_rnorm(norm, rn, mul, q);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int d = lane + 32 * i;
@@ -102,64 +98,63 @@ __global__ void __launch_bounds__(256) pack2_bf16_f16_kernel(const uint4* __rest
       uint4 o;
       __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = __bfloat1622float2(h[q]);
-        oh[q] = __floats2half2_rn(f.x * rn, f.y * rn);
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        oh[k] = __floats2half2_rn(f.x * mul, f.y * mul);
       }
       dst[d] = o;
     }
   }
-  if (lane == 0) rnorm[row] = rn;
-}
-
-int launch_pack2(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int dim, void* out,
-                 int out_dtype, float* rnorm, cudaStream_t st) {
-  if (rows == 0) return CROSSCLR_OK;
-  const size_t esz = out_dtype == CROSSCLR_F32 ? 4 : 2;
-  if (in_dtype == CROSSCLR_BF16 && out_dtype == CROSSCLR_F16 && dim % 8 == 0 && dim <= 1024 && sv % 8 == 0 &&
-      st_ % 8 == 0 && ((uintptr_t)xv % 16 == 0) && ((uintptr_t)xt % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
-    TimedLaunch timed(CROSSCLR_K_PACK, st);
-    dim3 block(256), grid((2 * rows + 7) / 8);
-    pack2_bf16_f16_kernel<<<grid, block, 0, st>>>((const uint4*)xv, (const uint4*)xt, sv / 8, st_ / 8, rows, dim / 8,
-                                                  (uint4*)out, rnorm);
-    return check_launch("pack2_bf16_f16_kernel");
+  if (lane == 0) {
+    rnorm[row] = rn;
+    *reinterpret_cast<float*>(dst + dim_vec) = q;
   }
-  int rc = launch_pack(xv, in_dtype, sv, rows, dim, out, out_dtype, rnorm, st);
-  if (rc) return rc;
-  return launch_pack(xt, in_dtype, st_, rows, dim, (char*)out + (size_t)rows * dim * esz, out_dtype, rnorm + rows, st);
 }
 
 template <typename Tin>
-static int pack_dispatch_out(const void* x, int64_t stride, int rows, int dim, void* out, int out_dtype,
-                             float* rnorm, cudaStream_t st) {
-  dim3 block(256), grid((rows + 7) / 8);
-  if (out_dtype == CROSSCLR_F32) {
-    pack_kernel<Tin, float><<<grid, block, 0, st>>>((const Tin*)x, stride, rows, dim, (float*)out, rnorm);
-  } else if (out_dtype == CROSSCLR_F16) {
-    pack_kernel<Tin, __half><<<grid, block, 0, st>>>((const Tin*)x, stride, rows, dim, (__half*)out, rnorm);
-  } else {
-    set_error("crossclr_pack: unsupported stacked dtype %d", out_dtype);
-    return CROSSCLR_EINVAL;
-  }
+static int pack_dispatch(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int nmod, int dim,
+                         void* out, int out_dtype, float* rnorm, cudaStream_t st, float* stats_zero, unsigned int* ticket_zero) {
+  dim3 block(256), grid((nmod * rows + 7) / 8);
+  const int64_t pitch = out_dtype == CROSSCLR_F32 ? dim : dim + CROSSCLR_ROW_TAIL;
+#define CC_PACK(Tout, kRaw)                                                                                                \
+  pack_kernel<Tin, Tout, kRaw><<<grid, block, 0, st>>>((const Tin*)xv, (const Tin*)xt, sv, st_, rows, nmod, dim, (Tout*)out, \
+                                                       pitch, rnorm, (float2*)stats_zero, ticket_zero)
+  if (out_dtype == CROSSCLR_F32) CC_PACK(float, false);
+  else if (out_dtype == CROSSCLR_F16 && in_dtype != CROSSCLR_F32) CC_PACK(__half, true);     // 16-bit inputs: exact rescale
+  else if (out_dtype == CROSSCLR_F16) CC_PACK(__half, false);
+  else { set_error("crossclr_pack: unsupported stacked dtype %d", out_dtype); return CROSSCLR_EINVAL; }
+#undef CC_PACK
   return check_launch("pack_kernel");
+}
+
+static int pack_any(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int nmod, int dim,
+                    void* out, int out_dtype, float* rnorm, cudaStream_t st, float* stats_zero, unsigned int* ticket_zero) {
+  if (rows == 0) return CROSSCLR_OK;
+  TimedLaunch timed(CROSSCLR_K_PACK, st);
+  if (nmod == 2 && in_dtype == CROSSCLR_BF16 && out_dtype == CROSSCLR_F16 && dim % 8 == 0 && dim <= 1024 && sv % 8 == 0 &&
+      st_ % 8 == 0 && ((uintptr_t)xv % 16 == 0) && ((uintptr_t)xt % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
+    dim3 block(256), grid((2 * rows + 7) / 8);
+    pack2_bf16_raw_kernel<<<grid, block, 0, st>>>((const uint4*)xv, (const uint4*)xt, sv / 8, st_ / 8, rows, dim / 8,
+                                                  (uint4*)out, (dim + CROSSCLR_ROW_TAIL) / 8, rnorm, (float2*)stats_zero,
+                                                  ticket_zero);
+    return check_launch("pack2_bf16_raw_kernel");
+  }
+  switch (in_dtype) {
+    case CROSSCLR_F32: return pack_dispatch<float>(xv, xt, in_dtype, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
+    case CROSSCLR_F16: return pack_dispatch<__half>(xv, xt, in_dtype, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
+    case CROSSCLR_BF16: return pack_dispatch<__nv_bfloat16>(xv, xt, in_dtype, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
+    default: set_error("crossclr_pack: unsupported input dtype %d", in_dtype); return CROSSCLR_EINVAL;
+  }
+}
+
+int launch_pack2(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int dim, void* out,
+                 int out_dtype, float* rnorm, cudaStream_t st, float* stats_zero, unsigned int* ticket_zero) {
+  return pack_any(xv, xt, in_dtype, sv, st_, rows, 2, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
 }
 
 int launch_pack(const void* x, int in_dtype, int64_t stride, int rows, int dim, void* out, int out_dtype,
                 float* rnorm, cudaStream_t st) {
-  if (rows == 0) return CROSSCLR_OK;
-  TimedLaunch timed(CROSSCLR_K_PACK, st);
-  if (in_dtype == CROSSCLR_BF16 && out_dtype == CROSSCLR_F16 && dim % 8 == 0 && stride % 8 == 0 &&
-      ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
-    dim3 block(256), grid((rows + 7) / 8);
-    pack_bf16_f16_vec_kernel<<<grid, block, 0, st>>>((const uint4*)x, stride / 8, rows, dim / 8, (uint4*)out, rnorm);
-    return check_launch("pack_bf16_f16_vec_kernel");
-  }
-  switch (in_dtype) {
-    case CROSSCLR_F32: return pack_dispatch_out<float>(x, stride, rows, dim, out, out_dtype, rnorm, st);
-    case CROSSCLR_F16: return pack_dispatch_out<__half>(x, stride, rows, dim, out, out_dtype, rnorm, st);
-    case CROSSCLR_BF16: return pack_dispatch_out<__nv_bfloat16>(x, stride, rows, dim, out, out_dtype, rnorm, st);
-    default: set_error("crossclr_pack: unsupported input dtype %d", in_dtype); return CROSSCLR_EINVAL;
-  }
+  return pack_any(x, x, in_dtype, stride, stride, rows, 1, dim, out, out_dtype, rnorm, st, nullptr, nullptr);
 }
 
 // ================================================================================================
@@ -371,95 +366,21 @@ int launch_bwd_simt(const Geometry& g, const float* feat, const float* coef, flo
 }
 
 // ================================================================================================
-// finalize: loss (trainer/loss.py:60,:111-114) + backward coefficients from per-row statistics.
-// The cancellation-free form loss_g = log1p(X_g / 2^xpos_g) is evaluated per row in fp32 pieces and summed in double.
-// Several blocks share the rows; each leaves its partial (loss sum, max rho) in a slot of a small static device table,
-// takes a ticket, and the last block to finish reduces the partials in a fixed order (the result does not depend on the
-// block schedule) and resets the ticket.  Launches take slots round-robin, so finalize calls in flight on different
-// streams (or captured in different CUDA graphs) never share one; a launch re-using a slot is stream-ordered behind the
-// 15 launches in between only by convention -- kFinSlots bounds the concurrent finalize launches per process.
-constexpr int kFinBlocks = 32;
-constexpr int kFinSlots = 16;
-struct FinSlot {
-  double sum[kFinBlocks];
-  float rho[kFinBlocks];
-  unsigned int ticket;
-};
-__device__ FinSlot g_fin[kFinSlots];
-
-__global__ void __launch_bounds__(256) finalize_kernel(Geometry g, const float* __restrict__ stats,
-                                                      float* __restrict__ coef, double* __restrict__ loss,
-                                                      float* __restrict__ scal, int slot) {
-  FinSlot& fin = g_fin[slot];
-  __shared__ double s_sum[8];
-  __shared__ float s_rho[8];
-  __shared__ bool s_last;
-  double lsum = 0.0;
-  float rho_max = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.rows; i += gridDim.x * blockDim.x) {
-    const float2 sx = reinterpret_cast<const float2*>(stats)[i];
-    const float X = sx.x, xp = sx.y;
-    const float e = exp2f(xp);
-    const float Z = X + e;
-    const float iz = 1.0f / Z;
-    const float rho = X / Z;
-    reinterpret_cast<float2*>(coef)[i] = make_float2(iz, rho);
-    // loss_g = log1p(X 2^-xp) = ln2 * log2(1 + 2^t), t = log2 X - xp; fp32 pieces (1e-7 relative), double sum.
-    // The direct form keeps converged rows exact (log1p(y) ~ y); the log-domain form covers y beyond fp32 range.
-    const float t = log2f(X) - xp;
-    float lg;
-    if (t < 100.f) lg = log1pf(xp > -120.f ? X * exp2f(-xp) : exp2f(t));
-    else lg = 0.6931471805599453f * t;                 // log2(1 + 2^t) - t < 2^-100
-    if (!(X > 0.f)) lg = 0.f;
-    lsum += (double)lg;
-    rho_max = fmaxf(rho_max, rho);
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-  rho_max = warp_max(rho_max);
-  if (lane == 0) { s_sum[wid] = lsum; s_rho[wid] = rho_max; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double bs = 0.0;
-    float br = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { bs += s_sum[w]; br = fmaxf(br, s_rho[w]); }
-    fin.sum[blockIdx.x] = bs;
-    fin.rho[blockIdx.x] = br;
-    __threadfence();
-    const unsigned int ticket = atomicAdd(&fin.ticket, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_last && threadIdx.x == 0) {
-    __threadfence();
-    double tot = 0.0;
-    float rmax = 0.f;
-    for (int bI = 0; bI < (int)gridDim.x; ++bI) {        // fixed order: the loss does not depend on the block schedule
-      tot += *(volatile double*)&fin.sum[bI];
-      rmax = fmaxf(rmax, *(volatile float*)&fin.rho[bI]);
-    }
-    fin.ticket = 0;                                      // ready for the slot's next launch
-    loss[0] = tot / (double)g.rows;
-    // fp16 probability tiles hold sigma * 2^x (1/Z_g + 1/Z_j) kappa <= sigma * 2 rho_max max(1,|w|)
-    const float bound = 2.0f * rmax * fmaxf(1.0f, fabsf(g.w));
-    int ex = 0;
-    if (bound > 0.f && isfinite(bound)) ex = 14 - (int)ceilf(log2f(bound));
-    ex = max(-100, min(100, ex));
-    scal[0] = exp2f((float)ex);
-    scal[1] = exp2f((float)-ex);
-    scal[2] = rmax;
-    scal[3] = 0.f;
-  }
+// finalize: loss (trainer/loss.py:60,:111-114) + backward coefficients from per-row statistics -- finalize.cuh, one block.
+__global__ void __launch_bounds__(1024) finalize_kernel(Geometry g, const float* __restrict__ stats,
+                                                       float* __restrict__ coef, double* __restrict__ loss,
+                                                       float* __restrict__ scal) {
+  __shared__ double s_sum[32];
+  __shared__ float s_rho[32];
+  finalize_block<false>(g, stats, coef, loss, scal, s_sum, s_rho);
+  if (threadIdx.x == 0) scal[3] = 0.f;
 }
 
 int launch_finalize(const Geometry& g, const float* stats, float* coef, double* loss, float* scal,
                     cudaStream_t st) {
   TimedLaunch timed(CROSSCLR_K_FINALIZE, st);
-  const int blocks = std::max(1, std::min(kFinBlocks, (g.rows + 255) / 256));
-  static std::atomic<unsigned int> next_slot{0};
-  const int slot = (int)(next_slot.fetch_add(1, std::memory_order_relaxed) % kFinSlots);
-  finalize_kernel<<<blocks, 256, 0, st>>>(g, stats, coef, loss, scal, slot);
+  const int threads = std::max(32, std::min(1024, ((g.rows + 31) / 32) * 32));
+  finalize_kernel<<<1, threads, 0, st>>>(g, stats, coef, loss, scal);
   return check_launch("finalize_kernel");
 }
 
@@ -469,7 +390,13 @@ int launch_finalize(const Geometry& g, const float* stats, float* coef, double* 
 //   dF_g     = rnorm_g (dFhat_g - (dFhat_g . Fhat_g) Fhat_g)      (no projection if ||F_g|| < eps)
 // `F` holds the normalised rows (fp32 or fp16); `rn` the reciprocal norms of the owned rows.
 // One warp per owned row.
-template <typename TF, typename TO>
+// kTail: the rows are (f, q) rows of the TC paths (pitch dim + tail, normalised row = q * f); else plain normalised rows.
+template <typename TF, bool kTail>
+__device__ __forceinline__ float row_scale(const TF* row, int dim) {
+  return kTail ? *reinterpret_cast<const float*>(row + dim) : 1.0f;
+}
+
+template <typename TF, typename TO, bool kTail>
 __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* __restrict__ F,
                                                          const float* __restrict__ rn, const float* __restrict__ coef,
                                                          const float* __restrict__ scal, bool use_sigma,
@@ -482,17 +409,18 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   const int gr = g.row_begin + l;
   const int pg = row_partner(gr, g.bseg);
   const float rn_g = rn[l];                    // reciprocal norms of the OWNED rows only
-  const float acc_scale = use_sigma ? scal[1] : 1.0f;
-  const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]);
-  const TF* fg = F + (int64_t)gr * g.dim;
-  const TF* fp = F + (int64_t)pg * g.dim;
+  const TF* fg = F + (int64_t)gr * g.pitch;
+  const TF* fp = F + (int64_t)pg * g.pitch;
+  const float qg = row_scale<TF, kTail>(fg, g.dim), qp = row_scale<TF, kTail>(fp, g.dim);
+  const float acc_scale = (use_sigma ? scal[1] : 1.0f) / qg;       // TC paths accumulate sum_j (P q_g q_j) f_j = q_g dFhat_g
+  const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]) * qp;
   const float* dh = dfhat + (int64_t)l * g.dim;
   float dot = 0.f;
   for (int d = lane; d < g.dim; d += 32) {
     const float h = dh[d] * acc_scale + pos_coef * to_float<TF>(fp[d]);
     dot = fmaf(h, to_float<TF>(fg[d]), dot);
   }
-  dot = warp_sum(dot);
+  dot = warp_sum(dot) * qg * qg;        // (h . Fhat_g) Fhat_g with Fhat_g = q_g f_g
   if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
   double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows;
   if (grad_out != nullptr) m *= grad_out[0];
@@ -506,26 +434,34 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   }
 }
 
-// Vectorised form for the tensor-core path (fp16 stacked rows, dim = 256 NV <= 1024, 16-byte aligned rows): each lane
+// Vectorised form for the tensor-core paths (16-bit (f, q) rows, dim = 256 NV <= 1024, 16-byte aligned rows): each lane
 // owns NV groups of 8 consecutive columns, read once (16-byte loads) and kept in registers between the dot-product
 // pass and the output pass.  HBM-bound: reads dfhat (4 B), the row and its partner (2 x 2 B), writes the gradient.
-template <typename TO, int NV>
-__global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const __half* __restrict__ F,
+template <typename TF> struct Half2Of;
+template <> struct Half2Of<__half> { using type = __half2; static __device__ __forceinline__ float2 cvt(__half2 h) { return __half22float2(h); } };
+template <> struct Half2Of<__nv_bfloat16> { using type = __nv_bfloat162; static __device__ __forceinline__ float2 cvt(__nv_bfloat162 h) { return __bfloat1622float2(h); } };
+
+template <typename TF, typename TO, int NV>
+__global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const TF* __restrict__ F,
                                                              const float* __restrict__ rn, const float* __restrict__ coef,
                                                              const float* __restrict__ scal, bool use_sigma,
                                                              const double* __restrict__ grad_out, float grad_scale,
                                                              const float* __restrict__ dfhat, TO* __restrict__ dv,
                                                              int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride) {
+  using H2 = typename Half2Of<TF>::type;
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (l >= g.row_count) return;
   const int gr = g.row_begin + l;
   const int pg = row_partner(gr, g.bseg);
   const float rn_g = rn[l];
-  const float acc_scale = use_sigma ? scal[1] : 1.0f;
-  const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]);
-  const uint4* fg = reinterpret_cast<const uint4*>(F + (int64_t)gr * g.dim);
-  const uint4* fp = reinterpret_cast<const uint4*>(F + (int64_t)pg * g.dim);
+  const TF* rowg = F + (int64_t)gr * g.pitch;
+  const TF* rowp = F + (int64_t)pg * g.pitch;
+  const float qg = *reinterpret_cast<const float*>(rowg + g.dim), qp = *reinterpret_cast<const float*>(rowp + g.dim);
+  const float acc_scale = (use_sigma ? scal[1] : 1.0f) / qg;       // the kernels accumulate sum_j (P q_g q_j) f_j = q_g dFhat_g
+  const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]) * qp;
+  const uint4* fg = reinterpret_cast<const uint4*>(rowg);
+  const uint4* fp = reinterpret_cast<const uint4*>(rowp);
   const float4* dh = reinterpret_cast<const float4*>(dfhat + (int64_t)l * g.dim);
   float h[NV][8], f[NV][8];
   float dot = 0.f;
@@ -534,12 +470,12 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
     const int idx = lane + 32 * v;
     const uint4 ug = __ldg(fg + idx), up = __ldg(fp + idx);
     const float4 d0 = __ldg(dh + 2 * idx), d1 = __ldg(dh + 2 * idx + 1);
-    const __half2* hg = reinterpret_cast<const __half2*>(&ug);
-    const __half2* hp = reinterpret_cast<const __half2*>(&up);
+    const H2* hg = reinterpret_cast<const H2*>(&ug);
+    const H2* hp = reinterpret_cast<const H2*>(&up);
     const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 a = __half22float2(hg[q]), b = __half22float2(hp[q]);
+      const float2 a = Half2Of<TF>::cvt(hg[q]), b = Half2Of<TF>::cvt(hp[q]);
       f[v][2 * q] = a.x; f[v][2 * q + 1] = a.y;
       h[v][2 * q] = fmaf(pos_coef, b.x, dd[2 * q] * acc_scale);
       h[v][2 * q + 1] = fmaf(pos_coef, b.y, dd[2 * q + 1] * acc_scale);
@@ -547,7 +483,7 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
       dot = fmaf(h[v][2 * q + 1], a.y, dot);
     }
   }
-  dot = warp_sum(dot);
+  dot = warp_sum(dot) * qg * qg;        // (h . Fhat_g) Fhat_g with Fhat_g = q_g f_g
   if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
   double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows;
   if (grad_out != nullptr) m *= grad_out[0];
@@ -570,18 +506,18 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
   }
 }
 
-template <typename TO>
+template <typename TF, typename TO>
 static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
                             const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
                             const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, cudaStream_t st) {
   const size_t osz = sizeof(TO);
   if (g.dim % 256 != 0 || g.dim > 1024 || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
-      (dvs * osz) % 16 != 0 || (dts * osz) % 16 != 0)
+      (dvs * osz) % 16 != 0 || (dts * osz) % 16 != 0 || (g.pitch * sizeof(TF)) % 16 != 0)
     return false;
   dim3 block(256), grid((g.row_count + 7) / 8);
-#define CC_GFV(NV)                                                                                                     \
-  grad_finish_vec_kernel<TO, NV><<<grid, block, 0, st>>>(g, (const __half*)feat, rnorm, coef, scal, use_sigma, grad_out, \
-                                                        grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
+#define CC_GFV(NV)                                                                                                      \
+  grad_finish_vec_kernel<TF, TO, NV><<<grid, block, 0, st>>>(g, (const TF*)feat, rnorm, coef, scal, use_sigma, grad_out, \
+                                                            grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
   switch (g.dim / 256) {
     case 1: CC_GFV(1); break;
     case 2: CC_GFV(2); break;
@@ -592,15 +528,15 @@ static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rn
   return true;
 }
 
-template <typename TF>
+template <typename TF, bool kTail>
 static int grad_finish_out(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
                            const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
                            const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, int out_dtype,
                            cudaStream_t st) {
   dim3 block(256), grid((g.row_count + 7) / 8);
-#define CC_GF(TO)                                                                                             \
-  grad_finish_kernel<TF, TO><<<grid, block, 0, st>>>(g, (const TF*)feat, rnorm, coef, scal, use_sigma, grad_out, \
-                                                    grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
+#define CC_GF(TO)                                                                                                    \
+  grad_finish_kernel<TF, TO, kTail><<<grid, block, 0, st>>>(g, (const TF*)feat, rnorm, coef, scal, use_sigma, grad_out, \
+                                                           grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
   switch (out_dtype) {
     case CROSSCLR_F32: CC_GF(float); break;
     case CROSSCLR_F16: CC_GF(__half); break;
@@ -611,27 +547,33 @@ static int grad_finish_out(const Geometry& g, const void* feat, const float* rno
   return check_launch("grad_finish_kernel");
 }
 
+template <typename TF>
+static int grad_finish_16(const Geometry& g, const void* feat, const float* rnorm, const float* coef, const float* scal,
+                          bool use_sigma, const double* grad_out, float grad_scale, const float* dfhat, void* dv,
+                          int64_t dv_stride, void* dt, int64_t dt_stride, int out_dtype, cudaStream_t st) {
+  bool done = false;
+  switch (out_dtype) {
+    case CROSSCLR_F32: done = grad_finish_vec<TF, float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+    case CROSSCLR_F16: done = grad_finish_vec<TF, __half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+    case CROSSCLR_BF16: done = grad_finish_vec<TF, __nv_bfloat16>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+    default: break;
+  }
+  if (done) return check_launch("grad_finish_vec_kernel");
+  return grad_finish_out<TF, true>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt,
+                                   dt_stride, out_dtype, st);
+}
+
 int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm,
                        const float* coef, const float* scal, bool use_sigma, const double* grad_out,
                        float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,
                        int64_t dt_stride, int out_dtype, cudaStream_t st) {
   TimedLaunch timed(CROSSCLR_K_GRADFIN, st);
   if (feat_dtype == CROSSCLR_F32)
-    return grad_finish_out<float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
-                                  dv_stride, dt, dt_stride, out_dtype, st);
-  if (feat_dtype == CROSSCLR_F16) {
-    bool done = false;
-    switch (out_dtype) {
-      case CROSSCLR_F32: done = grad_finish_vec<float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
-      case CROSSCLR_F16: done = grad_finish_vec<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
-      case CROSSCLR_BF16: done = grad_finish_vec<__nv_bfloat16>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
-      default: break;
-    }
-    if (done) return check_launch("grad_finish_vec_kernel");
-  }
+    return grad_finish_out<float, false>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
+                                         dv_stride, dt, dt_stride, out_dtype, st);
   if (feat_dtype == CROSSCLR_F16)
-    return grad_finish_out<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat,
-                                          dv, dv_stride, dt, dt_stride, out_dtype, st);
+    return grad_finish_16<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt,
+                                  dt_stride, out_dtype, st);
   set_error("crossclr_bwd: unsupported stacked dtype %d", feat_dtype);
   return CROSSCLR_EINVAL;
 }

@@ -25,10 +25,6 @@ constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 128;
 
-constexpr uint32_t kIdescS256 = make_idesc_f16(128, 256, 0, 0, 0, 0);   // S = A(K-major) * B(K-major)^T, N = 256
-constexpr uint32_t kIdescS128 = make_idesc_f16(128, 128, 0, 0, 0, 0);   // ... N = 128
-constexpr uint32_t kIdescG128 = make_idesc_f16(128, 128, 0, 0, 0, 1);   // dF += P(K-major) * F_J(MN-major), N = 128
-constexpr uint32_t kIdescG64 = make_idesc_f16(128, 64, 0, 0, 0, 1);     // ... N = 64 (odd chunk counts)
 
 __device__ __forceinline__ uint64_t kmajor_desc(uint32_t addr) { return make_smem_desc_sw128(addr, 1024, 0); }
 
@@ -61,6 +57,16 @@ __device__ __forceinline__ BlockSeg block_seg(int r0, int bseg) {
   return BlockSeg{seg & 1, (seg >> 1) * bseg + (r0 - seg * bseg)};
 }
 
+// residual scale q_j of stacked row j (normalised row = q_j * stored row; include/crossclr_b200.h), first word of the row tail
+__device__ __forceinline__ float row_q(const uint8_t* __restrict__ feat, const Geometry& g, int64_t j) {
+  return __ldg(reinterpret_cast<const float*>(feat + (j * g.pitch + g.dim) * 2));
+}
+
+// stacked-matrix tensor map of a geometry: {64, box_rows} boxes of the [rows][dim] operand inside the pitched rows
+#define CC_FEAT_TMAP(m, feat, g, box_rows) \
+  make_tmap_f16(m, feat, (uint64_t)(g).rows, (uint64_t)(g).dim, box_rows, true, (uint64_t)(g).pitch, false)
+
+constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;   // mbarrier block of the forward / single-CTA backward kernels
 constexpr int PTILE_BYTES = TM * 128 * 2;   // a [128 rows][128 columns] fp16 probability tile: 32 KiB
 constexpr int GBOX_BYTES = 64 * KC * 2;     // a [64 rows][64 columns] box of the dF operand: 8 KiB
 constexpr size_t kMaxSmem = 232448;         // 227 KiB opt-in dynamic shared memory per CTA
@@ -83,8 +89,10 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 matrix [rows][cols] (row-major) tiled into {64 cols, box_rows} boxes, 128-byte swizzle (or none)
-inline int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, bool swizzle = true) {
+// 16-bit matrix [rows][cols] (row-major, row pitch `pitch` elements; 0 = cols) tiled into {64 cols, box_rows} boxes,
+// 128-byte swizzle (or none)
+inline int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, bool swizzle = true,
+                         uint64_t pitch = 0, bool bf16 = false) {
   // The driver-API encode needs a current context on THIS thread.  torch's autograd worker threads only get
   // one lazily (first runtime call), so bind the primary context here; cudaFree(nullptr) is the documented no-op
   // that does it.
@@ -97,10 +105,10 @@ inline int make_tmap_f16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return CROSSCLR_ECUDA; }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {(pitch ? pitch : cols) * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return CROSSCLR_ECUDA; }

@@ -16,6 +16,7 @@
 //   warps 4..7  epilogue       : tcgen05.ld 32x32b (thread = row), exp2 / row sums (fwd) or fp16 P tile (bwd)
 // Synchronisation is mbarrier-only: full/empty per ring stage, full/empty per TMEM accumulator buffer.
 #include "tc_common.cuh"
+#include "finalize.cuh"
 
 namespace crossclr {
 using namespace ptx;
@@ -30,23 +31,28 @@ namespace {
 //   warp 2  TMEM allocator
 //   warps 4-7 epilogue: tcgen05.ld (software pipelined) -> x = acc*k - shift -> ex2 -> thread-local row sums
 // ================================================================================================
-__device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float k, float nshift, float (&rs)[4]) {
+// 32 accumulator columns of one row -> exponentials summed into rs.  x = (f_g . f_j) * (k q_g) * q_j - shift with the column
+// scales q_j broadcast from the warp's shared-memory copy (16-byte loads, four columns each).
+__device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float kq, float nshift, const float4* __restrict__ qc,
+                                              float (&rs)[4]) {
 #pragma unroll
   for (int q = 0; q < 32; q += 4) {
-    rs[0] += fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift));
-    rs[1] += fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift));
-    rs[2] += fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift));
-    rs[3] += fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift));
+    const float4 c = qc[q >> 2];
+    rs[0] += fast_exp2(fmaf(__uint_as_float(v[q + 0]) * kq, c.x, nshift));
+    rs[1] += fast_exp2(fmaf(__uint_as_float(v[q + 1]) * kq, c.y, nshift));
+    rs[2] += fast_exp2(fmaf(__uint_as_float(v[q + 2]) * kq, c.z, nshift));
+    rs[3] += fast_exp2(fmaf(__uint_as_float(v[q + 3]) * kq, c.w, nshift));
   }
 }
 
 // The 32-column chunk that holds the same-sample column (column r & 31 of the chunk): the masked intra-modal diagonal
 // counts as logit 0 (trainer/loss.py:65,96-97); the positive is kept out of X and written to stats[.,1].
-__device__ __forceinline__ void fwd_diag_chunk(const uint32_t (&v)[32], float k, float nshift, bool same_mod,
-                                               float diag_term, int r, int gi, float* __restrict__ stats, float (&rs)[4]) {
+__device__ __forceinline__ void fwd_diag_chunk(const uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
+                                               bool same_mod, float diag_term, int r, int gi, float* __restrict__ stats,
+                                               float (&rs)[4]) {
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
-    const float x = fmaf(__uint_as_float(v[q]), k, nshift);
+    const float x = fmaf(__uint_as_float(v[q]) * kq, qc[q], nshift);
     float e = fast_exp2(x);
     if (q == (r & 31)) {
       if (same_mod) e = diag_term;
@@ -54,196 +60,6 @@ __device__ __forceinline__ void fwd_diag_chunk(const uint32_t (&v)[32], float k,
     }
     rs[q & 3] += e;
   }
-}
-
-// Epilogue of one 128-row x 256-column accumulator tile (thread = row r of the block): x = acc*k - shift, 2^x summed
-// into the thread-local row sums; the same-sample column is the masked intra-modal diagonal (logit 0,
-// trainer/loss.py:65,96-97) or the positive (kept out of X, written to stats[.,1]).
-template <int H0 = 0, int H1 = 2>       // 128-column halves [H0, H1) of the tile
-__device__ __forceinline__ void fwd_tile_epilogue(uint32_t tbase, int jb, const BlockSeg& bi, int r, int gi,
-                                                  const Geometry& g, float diag_term, float nshift, float (&rs)[4],
-                                                  float* __restrict__ stats) {
-  uint32_t va[32], vb[32];
-  tmem_ld32(tbase + H0 * TM, va);
-#pragma unroll
-  for (int h = H0; h < H1; ++h) {               // 128-column halves, each inside one segment
-    const BlockSeg bj = block_seg(jb * FWD_TN + h * TM, g.bseg);
-    const bool same_mod = (bj.mod == bi.mod);
-    const bool diag_tile = (bj.samp0 == bi.samp0);
-    const float k = same_mod ? g.k_intra : g.k_inter;
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {            // chunk pairs (software pipelined tcgen05.ld)
-      const int c = h * 4 + c2 * 2;             // 32-column chunk index in the tile (0..7), even
-      tmem_ld_wait();
-      tmem_ld32(tbase + (c + 1) * 32, vb);
-      if (!diag_tile || (r >> 5) != (c & 3)) {
-        fwd_sum_chunk(va, k, nshift, rs);
-      } else {
-        // this chunk holds the same-sample column (local column index == r)
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const float x = fmaf(__uint_as_float(va[q]), k, nshift);
-          float e = fast_exp2(x);
-          if (q == (r & 31)) {
-            if (same_mod) e = diag_term;                       // masked intra-modal diagonal: logit 0
-            else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }  // positive logit, kept out of X
-          }
-          rs[q & 3] += e;
-        }
-      }
-      tmem_ld_wait();
-      if (c + 2 < H1 * 4) tmem_ld32(tbase + (c + 2) * 32, va);
-      if (!diag_tile || (r >> 5) != ((c + 1) & 3)) {
-        fwd_sum_chunk(vb, k, nshift, rs);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const float x = fmaf(__uint_as_float(vb[q]), k, nshift);
-          float e = fast_exp2(x);
-          if (q == (r & 31)) {
-            if (same_mod) e = diag_term;
-            else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }
-          }
-          rs[q & 3] += e;
-        }
-      }
-    }
-  }
-}
-
-template <bool kResident>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __restrict__ stats, int tiles_total,
-              int ncb, int nk, int num_stages) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_region = base;
-  const uint32_t ring_base = a_region + (kResident ? nk * CHUNK_BYTES : 0);
-  const uint32_t stage_bytes = (kResident ? 0 : CHUNK_BYTES) + 2 * CHUNK_BYTES;   // [A chunk] + B chunk of 256 rows
-  const uint32_t bar_base = ring_base + num_stages * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
-  const uint32_t a_full = bar_base + 8u * (2 * MAX_SLOTS);
-  const uint32_t a_empty = a_full + 8;
-  auto tfull_bar = [&](int b) { return a_full + 16u + 8u * b; };
-  auto tempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
-  const uint32_t tmem_slot = a_full + 48u;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_begin = (int)((long long)blockIdx.x * tiles_total / gridDim.x);
-  const int t_end = (int)((long long)(blockIdx.x + 1) * tiles_total / gridDim.x);
-
-  if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), EPI_THREADS); }
-    fence_barrier_init();
-  }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    Ring ring(num_stages);
-    int cur_ib = -1;
-    uint32_t a_cnt = 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int ib = t / ncb, jb = t - ib * ncb;
-      const int row0 = g.row_begin + ib * TM, col0 = jb * FWD_TN;
-      if (kResident && ib != cur_ib) {
-        mbar_wait(a_empty, (a_cnt & 1) ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(a_full, nk * CHUNK_BYTES);
-          for (int kc = 0; kc < nk; ++kc) tma_load_2d(a_region + kc * CHUNK_BYTES, &tmap, a_full, kc * KC, row0);
-        }
-        __syncwarp();
-        cur_ib = ib; ++a_cnt;
-      }
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-        if (elect_one()) {
-          uint32_t st = ring_base + ring.stage * stage_bytes;
-          mbar_arrive_expect_tx(full_bar(ring.stage), stage_bytes);
-          if (!kResident) { tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, row0); st += CHUNK_BYTES; }
-          tma_load_2d(st, &tmap, full_bar(ring.stage), kc * KC, col0);
-          tma_load_2d(st + CHUNK_BYTES, &tmap, full_bar(ring.stage), kc * KC, col0 + TM);
-        }
-        __syncwarp();
-        ring.advance();
-      }
-    }
-  } else if (warp == 1) {
-    Ring ring(num_stages);
-    int cur_ib = -1;
-    uint32_t a_cnt = 0, iter = 0;
-    for (int t = t_begin; t < t_end; ++t, ++iter) {
-      const int ib = t / ncb;
-      const uint32_t buf = iter & 1;
-      mbar_wait(tempty_bar(buf), ((iter >> 1) & 1) ^ 1);
-      if (kResident && ib != cur_ib) {
-        mbar_wait(a_full, a_cnt & 1);
-        cur_ib = ib; ++a_cnt;
-      }
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + buf * FWD_TN;
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(full_bar(ring.stage), ring.phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t st = ring_base + ring.stage * stage_bytes;
-          const uint32_t a_addr = kResident ? a_region + kc * CHUNK_BYTES : st;
-          const uint32_t b_addr = kResident ? st : st + CHUNK_BYTES;
-          issue_s_chunk(tmem_d, a_addr, b_addr, kIdescS256, kc == 0);
-          umma_commit(empty_bar(ring.stage));
-        }
-        __syncwarp();
-        ring.advance();
-      }
-      const bool last_of_block = (t + 1 == t_end) || ((t + 1) / ncb != ib);
-      if (elect_one()) {
-        umma_commit(tfull_bar(buf));
-        if (kResident && last_of_block) umma_commit(a_empty);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= EPI_WARP0) {
-    const int ew = warp - EPI_WARP0;
-    const int r = ew * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
-    int cur_ib = -1, gi = 0;
-    BlockSeg bi{0, 0};
-    float rs[4] = {0.f, 0.f, 0.f, 0.f};
-    uint32_t iter = 0;
-    const float k_diag_term = fast_exp2(-g.shift);
-    const float nshift = -g.shift;
-    for (int t = t_begin; t < t_end; ++t, ++iter) {
-      const int ib = t / ncb, jb = t - ib * ncb;
-      if (ib != cur_ib) {
-        if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
-        rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
-        cur_ib = ib;
-        const int row0 = g.row_begin + ib * TM;
-        gi = row0 + r;
-        bi = block_seg(row0, g.bseg);
-      }
-      const uint32_t buf = iter & 1;
-      const uint32_t tbase = lane_base + buf * FWD_TN;
-      mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
-      tc_fence_after();
-      fwd_tile_epilogue(tbase, jb, bi, r, gi, g, k_diag_term, nshift, rs, stats);
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));
-    }
-    if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ================================================================================================
@@ -256,7 +72,6 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __res
 // bytes on the leader's barriers; each CTA's epilogue drains its own 128 accumulator rows from its own TMEM and
 // its warps arrive (one lane each) on the leader's tempty barrier.
 // ================================================================================================
-constexpr uint32_t kIdescS256x2 = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
 constexpr int FWD2_THREADS = 640;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-19: epilogue
 
@@ -283,19 +98,21 @@ struct FwdTileWalk {
 };
 
 // as fwd_sum_chunk, but leaves the exponentials in v (bit patterns) for the column sums
-__device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float k, float nshift, float (&rs)[4]) {
+__device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
+                                                   float (&rs)[4]) {
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
-    const float e = fast_exp2(fmaf(__uint_as_float(v[q]), k, nshift));
+    const float e = fast_exp2(fmaf(__uint_as_float(v[q]) * kq, qc[q], nshift));
     rs[q & 3] += e;
     v[q] = __float_as_uint(e);
   }
 }
-__device__ __forceinline__ void fwd_diag_chunk_keep(uint32_t (&v)[32], float k, float nshift, bool same_mod, float diag_term,
-                                                    int r, int gi, int partner, float* __restrict__ stats, float (&rs)[4]) {
+__device__ __forceinline__ void fwd_diag_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
+                                                    bool same_mod, float diag_term, int r, int gi, int partner,
+                                                    float* __restrict__ stats, float (&rs)[4]) {
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
-    const float x = fmaf(__uint_as_float(v[q]), k, nshift);
+    const float x = fmaf(__uint_as_float(v[q]) * kq, qc[q], nshift);
     float e = fast_exp2(x);
     if (q == (r & 31)) {
       if (same_mod) e = diag_term;
@@ -343,8 +160,8 @@ __device__ __forceinline__ void warp_column_sums(const uint32_t (&a)[32], const 
 
 template <bool kResident, bool kSym>
 __global__ void __launch_bounds__(FWD2_THREADS, 1)
-fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __restrict__ stats, int tiles_total,
-               int ncb, int nk, int num_stages, int exp_flags) {
+fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ feat, Geometry g,
+               float* __restrict__ stats, int tiles_total, int ncb, int nk, int num_stages, int exp_flags, FwdFinalize fin) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
@@ -359,6 +176,9 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
   auto tempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
   const uint32_t tmem_slot = a_full + 48u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // column scales q_j: [16 epilogue warps][2 tile parities][64 columns], each warp's copy private to it
+  float* qv_all = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes - smem_u32(smem_raw)));
+  const uint32_t idesc_s = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -438,7 +258,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k)
             if (!(exp_flags & 2))
-              umma_ss_2sm(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdescS256x2, (kc == 0 && k == 0) ? 0u : 1u);
+              umma_ss_2sm(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s, (kc == 0 && k == 0) ? 0u : 1u);
           umma_commit_2sm(empty_bar(ring.stage), (uint16_t)3);
         }
         __syncwarp();
@@ -463,6 +283,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
     int cur_ib = -1, gi = 0;
     BlockSeg bi{0, 0};
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    float q_i = 1.f;
+    float* const qv_warp = qv_all + (warp - EPI_WARP0) * 128;
     const float k_diag_term = fast_exp2(-g.shift);
     const float nshift = -g.shift;
     const uint32_t tempty_ldr0 = mapa_cluster(tempty_bar(0), 0), tempty_ldr1 = mapa_cluster(tempty_bar(1), 0);
@@ -480,12 +302,16 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
         const int row0 = g.row_begin + (2 * ib + (int)rank) * TM;
         gi = row0 + r;
         bi = block_seg(row0, g.bseg);
+        q_i = row_q(feat, g, gi);
       }
       const bool same_mod = ((jseg & 1) == bi.mod);
       const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
-      const float k = same_mod ? g.k_intra : g.k_inter;
+      const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;      // row part of the logit scale
       const bool col_sums = kSym && jb != ib;                        // off-diagonal tile of the symmetric walk
       const int col_row0 = jb * FWD_TN + sl * 64;                    // stacked row of the slice's first column
+      float* const qv = qv_warp + (iter & 1) * 64;                   // this tile's column scales, fetched before the wait
+      qv[lane] = row_q(feat, g, col_row0 + lane);
+      qv[32 + lane] = row_q(feat, g, col_row0 + 32 + lane);
       w.next();
       if (w.ib != ib) { ib = w.ib; jb = w.jb; jseg = (jb * FWD_TN + half * TM) / g.bseg; joff = (jb * FWD_TN + half * TM) - jseg * g.bseg; }
       else { jb = w.jb; joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
@@ -498,22 +324,22 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
       tmem_ld32(tb + 32, vb);
       tmem_ld_wait();
       tc_fence_before();                                             // this warp's part of the tile is in registers
-      __syncwarp();
+      __syncwarp();                                                  // (also: every lane's column scales are in qv)
       if (lane == 0) mbar_arrive_cluster(buf ? tempty_ldr1 : tempty_ldr0);
       if (!(exp_flags & 1)) {
         // 32-column chunk c of the slice is chunk (2 (sl & 1) + c) of its half; the same-sample column r of a diagonal
         // half sits in chunk r >> 5 = quad
         if (!col_sums) {
-          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk(va, k, nshift, rs);
-          else fwd_diag_chunk(va, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
-          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk(vb, k, nshift, rs);
-          else fwd_diag_chunk(vb, k, nshift, same_mod, k_diag_term, r, gi, stats, rs);
+          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk(va, k, nshift, reinterpret_cast<const float4*>(qv), rs);
+          else fwd_diag_chunk(va, k, nshift, qv, same_mod, k_diag_term, r, gi, stats, rs);
+          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk(vb, k, nshift, reinterpret_cast<const float4*>(qv + 32), rs);
+          else fwd_diag_chunk(vb, k, nshift, qv + 32, same_mod, k_diag_term, r, gi, stats, rs);
         } else {
           const int partner = row_partner(gi, g.bseg);
-          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk_keep(va, k, nshift, rs);
-          else fwd_diag_chunk_keep(va, k, nshift, same_mod, k_diag_term, r, gi, partner, stats, rs);
-          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk_keep(vb, k, nshift, rs);
-          else fwd_diag_chunk_keep(vb, k, nshift, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk_keep(va, k, nshift, qv, rs);
+          else fwd_diag_chunk_keep(va, k, nshift, qv, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk_keep(vb, k, nshift, qv + 32, rs);
+          else fwd_diag_chunk_keep(vb, k, nshift, qv + 32, same_mod, k_diag_term, r, gi, partner, stats, rs);
           // the mirrored tile (jb, ib) is never computed: its row sums are this tile's column sums
           float c0, c1;
           warp_column_sums(va, vb, lane, c0, c1);
@@ -527,6 +353,24 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, float* __re
 
   tc_fence_before();
   __syncthreads();
+  if (fin.ticket != nullptr) {
+    // Fused finalize (single rank): the last CTA of the grid to get here turns the complete row statistics into the loss
+    // and the backward coefficients (finalize.cuh).  Scratch: the start of the operand area -- every MMA of the pair has
+    // completed (the epilogue warps have consumed the last tile), and no peer writes there.
+    double* s_sum = reinterpret_cast<double*>(smem_raw + (a_region - smem_u32(smem_raw)));
+    float* s_rho = reinterpret_cast<float*>(s_sum + 32);
+    int* s_last = reinterpret_cast<int*>(s_rho + 32);
+    if (threadIdx.x == 0) {
+      __threadfence();                                              // this CTA's atomics on `stats` before its ticket
+      *s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      finalize_block<true>(g, stats, fin.coef, fin.loss, fin.scal, s_sum, s_rho);
+      if (threadIdx.x == 0) *fin.ticket = 0u;
+    }
+  }
   cluster_sync_all();                    // neither CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
   if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
 }
@@ -571,15 +415,15 @@ struct BwdWalk {
 
 template <bool kResident>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float* __restrict__ coef,
-              const float* __restrict__ scal, float* __restrict__ dfhat, int n_units, int n_slabs, int ncb, int nk,
-              int num_slots) {
+bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ feat, Geometry g,
+              const float* __restrict__ coef, const float* __restrict__ scal, float* __restrict__ dfhat, int n_units,
+              int n_slabs, int ncb, int nk, int num_slots) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
   const uint32_t ring_base = a_region + (kResident ? nk * CHUNK_BYTES : 0);
-  const uint32_t cvec_base = ring_base + num_slots * CHUNK_BYTES;                 // float [2][128]
-  const uint32_t bar_base = cvec_base + 2 * BWD_TN * 4;
+  const uint32_t cvec_base = ring_base + num_slots * CHUNK_BYTES;                 // float2 [2][128]: (q_j, q_j kappa sigma / Z_j)
+  const uint32_t bar_base = cvec_base + 2 * BWD_TN * 8;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_SLOTS + s); };
   const uint32_t a_full = bar_base + 8u * (2 * MAX_SLOTS);
@@ -590,7 +434,10 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
   const uint32_t tmem_slot = a_full + 64u;
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw_u32));
-  float* cvec = reinterpret_cast<float*>(smem_raw + (cvec_base - raw_u32));
+  float2* cvec = reinterpret_cast<float2*>(smem_raw + (cvec_base - raw_u32));
+  const uint32_t idesc_s128 = make_idesc_f16(128, 128, 0, 0, 0, 0);   // S = A(K-major) * B(K-major)^T
+  const uint32_t idesc_g128 = make_idesc_f16(128, 128, 0, 0, 0, 1);             // dF += P(f16) * F_J(MN-major)
+  const uint32_t idesc_g64 = make_idesc_f16(128, 64, 0, 0, 0, 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u_begin = (int)((long long)blockIdx.x * n_units / gridDim.x);
@@ -695,7 +542,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
           const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
           const uint32_t a_addr = kResident ? a_region + kc * CHUNK_BYTES : st;
           const uint32_t b_addr = kResident ? st : st + CHUNK_BYTES;
-          issue_s_chunk(tmem_base + buf * BWD_TN, a_addr, b_addr, kIdescS128, kc == 0);
+          issue_s_chunk(tmem_base + buf * BWD_TN, a_addr, b_addr, idesc_s128, kc == 0);
           umma_commit(empty_bar(ring.stage));
           if (!kResident) umma_commit(empty_bar(ring.stage + 1));
         }
@@ -739,7 +586,7 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
               // B = Fhat_j[16 k16 .. +16, 64 or 128 d]: MN-major view of the TMA boxes; 16 K rows = 2048 bytes,
               // the second 64-wide MN atom is the next slot (LBO = 16 KiB)
               const uint64_t bd = make_smem_desc_sw128(st + k16 * 2048, 1024, CHUNK_BYTES);
-              umma_ts(tmem_acc + c * KC, p_tmem + k16 * 8, bd, dpair ? kIdescG128 : kIdescG64,
+              umma_ts(tmem_acc + c * KC, p_tmem + k16 * 8, bd, dpair ? idesc_g128 : idesc_g64,
                       (j > sg.j0 || k16 > 0) ? 1u : 0u);
             }
             umma_commit(empty_bar(ring.stage));
@@ -775,17 +622,22 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
       const int gi = row0 + r;
       const BlockSeg bi = block_seg(row0, g.bseg);
       const float iz_i = coef[2 * (int64_t)gi];
+      const float q_i = row_q(feat, g, gi);
+      const float nshift_i = nshift + log2f(q_i);      // the tile is P q_g q_j (symmetric): q_g rides in the exponent
       for (int j = sg.j0; j < sg.j1; ++j, ++p_cnt) {
         const int col0 = j * BWD_TN;
         const BlockSeg bj = block_seg(col0, g.bseg);
         const bool same_mod = (bj.mod == bi.mod);
         const bool diag_tile = (bj.samp0 == bi.samp0);
-        const float k = same_mod ? g.k_intra : g.k_inter;
+        const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
         const uint32_t buf = p_cnt & 1;
         const uint32_t tbuf = lane_base + buf * BWD_TN;
-        float* cv = cvec + buf * BWD_TN;
-        cv[r] = coef[2 * (int64_t)(col0 + r)] * ks;     // column r of this tile: kappa*sigma / Z_j
+        float2* cv = cvec + buf * BWD_TN;
+        {
+          const float qj = row_q(feat, g, col0 + r);
+          cv[r] = make_float2(qj, coef[2 * (int64_t)(col0 + r)] * ks * qj);   // column r: q_j, q_j kappa sigma / Z_j
+        }
         const float a_i = iz_i * ks;
         named_bar_sync(1, EPI_THREADS);
         mbar_wait(sfull_bar(buf), (p_cnt >> 1) & 1);
@@ -800,21 +652,17 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, Geometry g, const float*
           uint32_t packed[16];
           const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 cc = cv4[q >> 2];
-            float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
-            float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
-            float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
-            float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
+          for (int q = 0; q < 32; q += 2) {
+            const float4 cc = cv4[q >> 1];                       // (q_j, w_j) of columns q, q + 1
+            // P~ = 2^x (1/Z_g + 1/Z_j) kappa sigma q_g q_j,  x = (f_g . f_j) (k q_g) q_j - shift
+            float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]) * k, cc.x, nshift_i)) * fmaf(a_i, cc.x, cc.y);
+            float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]) * k, cc.z, nshift_i)) * fmaf(a_i, cc.z, cc.w);
             if (diag_tile) {                                     // same-sample pair handled in grad_finish
               if (c * 32 + q + 0 == r) e0 = 0.f;
               if (c * 32 + q + 1 == r) e1 = 0.f;
-              if (c * 32 + q + 2 == r) e2 = 0.f;
-              if (c * 32 + q + 3 == r) e3 = 0.f;
             }
-            __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
-            packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
-            packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+            __half2 h0 = __floats2half2_rn(e0, e1);
+            packed[q >> 1] = *reinterpret_cast<uint32_t*>(&h0);
           }
           // P(j) columns [32c, 32c+32) -> packed fp16 pairs in TMEM columns [16c, 16c+16) of the same buffer
           // (S columns < 32(c+1) are already in registers, so nothing unread is overwritten)
@@ -882,7 +730,7 @@ constexpr int PAIR_TN = 256;             // S tile columns in the S-CTA
 constexpr int PAIR_PBUF = 3;             // 128-column P tiles in flight in the G-CTA's shared memory
 constexpr int PAIR_NSLOT = 8;            // scratch P tiles per pair in global memory (ring)
 constexpr int PAIR_GGROUPS = 4;          // G-CTA ring: groups of four [64 j][64 d] boxes
-constexpr int PAIR_HDR = 3072;
+constexpr int PAIR_HDR = 5120;           // barriers (1 KiB) | column coefficient pairs [2][256] float2 (4 KiB)
 
 struct PairSeg { int ib, j0, j1; bool last_of_ib; };
 struct PairWalk {
@@ -901,8 +749,8 @@ struct PairWalk {
 
 template <bool kResident>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
-bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64, Geometry g,
-                const float* __restrict__ coef,
+bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
+                const uint8_t* __restrict__ feat, Geometry g, const float* __restrict__ coef,
                 const float* __restrict__ scal, float* __restrict__ dfhat, uint8_t* __restrict__ scratch, int n_units,
                 int ncb, int nk, int s_stages, int exp_flags, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -925,8 +773,9 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const uint32_t acc_full = base + 480u, acc_empty = base + 488u;
   const uint32_t tmem_slot = base + 496u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 496);
-  float* cvec = reinterpret_cast<float*>(smem_raw + 1024);          // [2][256]
-  const uint32_t data = base + PAIR_HDR;
+  float2* cvec = reinterpret_cast<float2*>(smem_raw + 1024);        // [2][256]: (q_j, q_j kappa sigma / Z_j)
+  const uint32_t data = base + (cluster_ctarank() == 0 ? PAIR_HDR : 1024);   // G-CTAs need all of the rest for P tiles + boxes
+  const uint32_t idesc_s256 = make_idesc_f16(128, 256, 0, 0, 0, 0);
 
   const uint32_t rank = cluster_ctarank();
   const uint32_t csize = cluster_nctarank();          // 1 S-CTA + (csize - 1) G-CTAs, one per 512-wide slab of D
@@ -1018,7 +867,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             if (elect_one()) {
               const uint32_t st = ring_base + ring.stage * stage_bytes;
               issue_s_chunk(tmem_base + buf * PAIR_TN, kResident ? a_region + kc * CHUNK_BYTES : st,
-                            kResident ? st : st + CHUNK_BYTES, kIdescS256, kc == 0);
+                            kResident ? st : st + CHUNK_BYTES, idesc_s256, kc == 0);
               umma_commit(empty_bar(ring.stage));
             }
             __syncwarp();
@@ -1060,14 +909,16 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const int n_tiles = u_end - u_begin;
       int cur_ib = -1, gi = 0;
       BlockSeg bi{0, 0};
-      float iz_i = 0.f;
-      float* cv = cvec + wg * PAIR_TN;
+      float iz_i = 0.f, q_i = 1.f, nshift_i = nshift;
+      float2* cv = cvec + wg * PAIR_TN;
       // column coefficients of this thread's two columns for the group's next tile, fetched one tile ahead
-      float izj0 = 0.f, izj1 = 0.f;
+      float izj0 = 0.f, izj1 = 0.f, qj0 = 1.f, qj1 = 1.f;
       if (wg < n_tiles) {
         const int jn = (u_begin + wg) % ncb;
         izj0 = coef[2 * (int64_t)(jn * PAIR_TN + r)];
         izj1 = coef[2 * (int64_t)(jn * PAIR_TN + TM + r)];
+        qj0 = row_q(feat, g, jn * PAIR_TN + r);
+        qj1 = row_q(feat, g, jn * PAIR_TN + TM + r);
       }
       for (int t = wg; t < n_tiles; t += 2) {
         const int u = u_begin + t;
@@ -1078,15 +929,19 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           gi = row0 + r;
           bi = block_seg(row0, g.bseg);
           iz_i = coef[2 * (int64_t)gi];
+          q_i = row_q(feat, g, gi);
+          nshift_i = nshift + log2f(q_i);                // the tile is P q_g q_j (symmetric): q_g rides in the exponent
         }
         const BlockSeg bj0 = block_seg(j * PAIR_TN, g.bseg), bj1 = block_seg(j * PAIR_TN + TM, g.bseg);
         const float ks0 = ((bj0.mod == bi.mod) ? g.w : 1.0f) * sigma, ks1 = ((bj1.mod == bi.mod) ? g.w : 1.0f) * sigma;
-        cv[r] = izj0 * ks0;                                        // kappa*sigma / Z_j of the tile's 256 columns
-        cv[TM + r] = izj1 * ks1;
+        cv[r] = make_float2(qj0, izj0 * ks0 * qj0);                // q_j, q_j kappa sigma / Z_j of the tile's 256 columns
+        cv[TM + r] = make_float2(qj1, izj1 * ks1 * qj1);
         if (t + 2 < n_tiles) {
           const int jn = (u + 2) % ncb;
           izj0 = coef[2 * (int64_t)(jn * PAIR_TN + r)];
           izj1 = coef[2 * (int64_t)(jn * PAIR_TN + TM + r)];
+          qj0 = row_q(feat, g, jn * PAIR_TN + r);
+          qj1 = row_q(feat, g, jn * PAIR_TN + TM + r);
         }
         named_bar_sync(1 + wg, EPI_THREADS);
         if (r == 0) TR(1 + wg, t >> 1, 0);
@@ -1100,7 +955,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           const BlockSeg bj = h ? bj1 : bj0;
           const bool same_mod = (bj.mod == bi.mod);
           const bool diag_tile = (bj.samp0 == bi.samp0);
-          const float k = same_mod ? g.k_intra : g.k_inter;
+          const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;
           const float a_i = iz_i * (h ? ks1 : ks0);
           const uint32_t th = 2u * (uint32_t)t + h;                // P tile index of this pair
           const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
@@ -1116,22 +971,17 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             uint32_t packed[16];
             const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              const float4 cc = cv4[q >> 2];
-              float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
-              float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
-              float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
-              float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
+            for (int q = 0; q < 32; q += 2) {
+              const float4 cc = cv4[q >> 1];                         // (q_j, w_j) of columns q, q + 1
+              float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]) * k, cc.x, nshift_i)) * fmaf(a_i, cc.x, cc.y);
+              float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]) * k, cc.z, nshift_i)) * fmaf(a_i, cc.z, cc.w);
               if (diag_tile) {                                     // same-sample pair handled in grad_finish
                 const int cbase = c4 * 32 + q;
                 if (cbase + 0 == r) e0 = 0.f;
                 if (cbase + 1 == r) e1 = 0.f;
-                if (cbase + 2 == r) e2 = 0.f;
-                if (cbase + 3 == r) e3 = 0.f;
               }
-              __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
-              packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
-              packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
+              __half2 h0 = __floats2half2_rn(e0, e1);
+              packed[q >> 1] = *reinterpret_cast<uint32_t*>(&h0);
             }
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch)
@@ -1297,469 +1147,6 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 }
 
 // ================================================================================================
-// Backward for D <= 512, D % 128 == 0: a CLUSTER OF FOUR CTAs = an S-pair (ranks 0, 1) and a G-pair (ranks 2, 3), each
-// pair driving ONE cta_group::2 MMA stream (M = 256) issued by its even-ranked leader.  The unit of work is a
-// (256-row block pair, 256-column block) of the stacked Gram matrix; CTA r of a pair owns rows [128 r, +128).
-//   S-pair: S[256 x 256] = A F_J^T.  CTA r keeps its 128 rows of A resident and stages rows [128 r, +128) of the 256-row
-//           column block, so each B chunk is fetched from L2 once per PAIR and read from shared memory once per SM.  Its
-//           two epilogue warpgroups turn its own 128 accumulator rows into fp16 P tiles (scratch ring in global memory,
-//           one channel per S-CTA -> G-CTA (2 + r)), exactly as in bwd_pair_kernel.
-//   G-pair: dF[256 x D] += P F_J.  A = P(j) (each CTA its own 128 rows, same buffer index in both), B = F_J[16 j x 256 d]
-//           MN-major with the 256 d of every MMA split half / half over the two CTAs, accumulators in all D TMEM columns
-//           of each CTA for its own 128 rows.
-// Why: both single-CTA-per-role kernels above are bound by L2 -> SM operand traffic (2 R^2 D / 128 bytes for each of S
-// and dF, ~1.1 GB at B=4096 D=512 against ~10 TB/s) and by shared-memory bandwidth; pairing halves both.
-// Barriers live at the same offsets in all four CTAs; "leader" barriers collect TMA bytes / arrivals of the pair,
-// tcgen05.commit multicasts hand buffers back to both CTAs of a pair (mask 0b0011 = S-pair, 0b1100 = G-pair).
-// ================================================================================================
-constexpr int QUAD_THREADS = 384;        // warps 0-3: producer / MMA / signallers-loaders (2, 3; 2 also owns TMEM); warps 4-11: epilogue
-constexpr uint16_t kMaskS = 0x3, kMaskG = 0xC;
-constexpr int QUAD_HDR = 1024 + 8 * 2 * 128 * 4 + 1024;   // barriers | per-warp column coefficients | pad: 10 KiB, 1 KiB aligned
-
-struct QuadSeg { int ib, j0, j1; bool last_of_ib; };     // ib = index of the 256-row block pair
-using QuadWalk = PairWalk;
-
-__global__ void __launch_bounds__(QUAD_THREADS, 1)
-bwd_quad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
-                const __grid_constant__ CUtensorMap tmap_p, Geometry g, const float* __restrict__ coef,
-                const float* __restrict__ scal, float* __restrict__ dfhat, uint8_t* __restrict__ scratch, int n_units,
-                int ncb, int nk, int s_stages, int exp_flags, unsigned long long* __restrict__ trace) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  const uint32_t base = smem_u32(smem_raw);
-  if (base & 1023u) __trap();
-  // debug timeline (CROSSCLR_PAIR_TRACE): quad 0 stamps clock64 per role / tile / event
-  auto TR = [&](int role, int tile, int ev) {
-    if (trace != nullptr && blockIdx.x < 4 && tile < 64) trace[(role * 64 + tile) * 4 + ev] = clock64();
-  };
-  auto full_bar = [&](int s) { return base + 8u * s; };
-  auto empty_bar = [&](int s) { return base + 96u + 8u * s; };
-  const uint32_t a_full = base + 192u, a_empty = base + 200u;
-  auto sfull_bar = [&](int b) { return base + 208u + 8u * b; };
-  auto sempty_bar = [&](int b) { return base + 224u + 8u * b; };
-  auto staged_bar = [&](int b) { return base + 240u + 8u * b; };     // S-CTA: a P tile's 128 rows are in global memory
-  auto pready_bar = [&](int b) { return base + 304u + 8u * b; };     // G-CTA: that tile is published (remote arrival)
-  auto pempty_bar = [&](int b) { return base + 368u + 8u * b; };     // S-CTA: scratch slot consumed (multicast commit)
-  auto pbfull_bar = [&](int b) { return base + 432u + 8u * b; };     // G leader: both CTAs' P tiles landed (TMA bytes)
-  auto pbempty_bar = [&](int b) { return base + 456u + 8u * b; };    // G-CTA: smem P buffer consumed (multicast commit)
-  const uint32_t acc_full = base + 480u, acc_empty = base + 488u;
-  const uint32_t tmem_slot = base + 496u;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 496);
-  float* cvw = reinterpret_cast<float*>(smem_raw + 1024);           // S-CTA: [8 epilogue warps][2 tile parities][128]
-
-  const uint32_t rank = cluster_ctarank();
-  const bool is_s = rank < 2;
-  const uint32_t data = base + (is_s ? QUAD_HDR : 1024);            // G-CTAs need all of the rest for P tiles + boxes
-  const uint32_t sub = rank & 1;                       // position in the pair = which 128 rows of the block pair
-  const uint32_t leader = rank & ~1u;                  // cluster rank of this pair's MMA-issuing CTA
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quad = blockIdx.x >> 2, nquads = gridDim.x >> 2;
-  const int u_begin = (int)((long long)quad * n_units / nquads);
-  const int u_end = (int)((long long)(quad + 1) * n_units / nquads);
-  const int channel = quad * 2 + (int)sub;             // scratch ring S-CTA `sub` -> G-CTA `2 + sub`
-
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap); prefetch_tmap(&tmap64); prefetch_tmap(&tmap_p); }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 16); }    // 8 warps x 2 CTAs
-    for (int b = 0; b < PAIR_NSLOT; ++b) {
-      mbar_init(staged_bar(b), 4); mbar_init(pready_bar(b), 1); mbar_init(pempty_bar(b), 1);   // staged: 4 warps per P tile
-    }
-    for (int b = 0; b < PAIR_PBUF; ++b) { mbar_init(pbfull_bar(b), 1); mbar_init(pbempty_bar(b), 1); }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 16);                                             // 8 warps x 2 CTAs
-    fence_barrier_init();
-  }
-  if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                    // every CTA's barriers are initialised before any remote arrival
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if ((is_s && (exp_flags & 8)) || (!is_s && (exp_flags & 4))) {
-    // perf experiment: this pair idles
-  } else if (is_s) {
-    // =========================================================================== S-pair
-    const uint32_t a_region = data;
-    const uint32_t ring_base = data + nk * CHUNK_BYTES;
-    if (warp == 0) {
-      // TMA producer: own 128 rows of A (resident), own half of each 256-row B chunk; bytes counted on the leader
-      Ring ring(s_stages);
-      int cur_ib = -1;
-      uint32_t a_cnt = 0;
-      const uint32_t a_full_ldr = mapa_cluster(a_full, leader);
-      QuadWalk walk(u_begin, u_end, ncb);
-      PairSeg sg;
-      while (walk.next(sg)) {
-        const int row0 = g.row_begin + (2 * sg.ib + (int)sub) * TM;
-        if (sg.ib != cur_ib) {
-          mbar_wait(a_empty, (a_cnt & 1) ^ 1);
-          if (elect_one()) {
-            if (sub == 0) mbar_arrive_expect_tx(a_full, 2 * nk * CHUNK_BYTES);
-            for (int kc = 0; kc < nk; ++kc) tma_load_2d_2sm(a_region + kc * CHUNK_BYTES, &tmap, a_full_ldr, kc * KC, row0);
-          }
-          __syncwarp();
-          cur_ib = sg.ib; ++a_cnt;
-        }
-        for (int j = sg.j0; j < sg.j1; ++j) {
-          for (int kc = 0; kc < nk; ++kc) {
-            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-            if (elect_one()) {
-              if (exp_flags & 512) {                                 // perf experiment: no B-chunk loads
-                if (sub == 0) mbar_arrive(full_bar(ring.stage));
-              } else {
-                if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
-                tma_load_2d_2sm(ring_base + ring.stage * CHUNK_BYTES, &tmap, mapa_cluster(full_bar(ring.stage), leader),
-                                kc * KC, j * PAIR_TN + (int)sub * TM);
-              }
-            }
-            __syncwarp();
-            ring.advance();
-          }
-        }
-      }
-    } else if (warp == 1 && sub == 0) {
-      // MMA issuer (leader): S tile t -> TMEM buffer t & 1 of both CTAs
-      Ring ring(s_stages);
-      int cur_ib = -1;
-      uint32_t a_cnt = 0, t = 0;
-      QuadWalk walk(u_begin, u_end, ncb);
-      PairSeg sg;
-      while (walk.next(sg)) {
-        if (sg.ib != cur_ib) {
-          mbar_wait(a_full, a_cnt & 1);
-          cur_ib = sg.ib; ++a_cnt;
-        }
-        for (int j = sg.j0; j < sg.j1; ++j, ++t) {
-          const uint32_t buf = t & 1;
-          if (lane == 0) TR(0, t, 0);
-          mbar_wait_cluster(sempty_bar(buf), ((t >> 1) & 1) ^ 1);
-          if (lane == 0) TR(0, t, 1);
-          tc_fence_after();
-          for (int kc = 0; kc < nk; ++kc) {
-            mbar_wait(full_bar(ring.stage), ring.phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t ad = kmajor_desc(a_region + kc * CHUNK_BYTES);
-              const uint64_t bd = kmajor_desc(ring_base + ring.stage * CHUNK_BYTES);
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                if (!(exp_flags & 256))                              // perf experiment: no S MMAs
-                  umma_ss_2sm(tmem_base + buf * PAIR_TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), kIdescS256x2,
-                              (kc == 0 && k == 0) ? 0u : 1u);
-              umma_commit_2sm(empty_bar(ring.stage), kMaskS);
-            }
-            __syncwarp();
-            ring.advance();
-          }
-          if (elect_one()) {
-            umma_commit_2sm(sfull_bar(buf), kMaskS);
-            if (sg.last_of_ib && j + 1 == sg.j1) umma_commit_2sm(a_empty, kMaskS);
-          }
-          if (lane == 0) TR(0, t, 2);
-          __syncwarp();
-        }
-      }
-    } else if (warp == 2 || warp == 3) {
-      // two signallers (P tiles of even / odd index): once the 128 rows of P tile th are in global memory (staged), make
-      // them visible GPU-wide and tell this channel's G-CTA
-      const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
-      for (uint32_t th = (uint32_t)(warp - 2); th < n_ptiles; th += 2) {
-        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
-        mbar_wait(staged_bar(slot), use & 1);
-        if (elect_one()) {
-          fence_acq_rel_gpu();
-          mbar_arrive_cluster_relaxed(mapa_cluster(pready_bar(slot), 2 + sub));
-        }
-        __syncwarp();
-      }
-    } else if (warp >= EPI_WARP0) {
-      // Eight epilogue warps, two per TMEM lane quadrant: warp (quadrant q, half wg) owns rows [32 q, +32) x columns
-      // [128 wg, +128) of EVERY S tile = rows of P tile 2t + wg of this channel, as four 32-column chunks.
-      // The chunks run through a two-register-buffer software pipeline that does not stop at tile boundaries: while chunk c
-      // is turned into fp16 P values, chunk c + 1 -- or chunk 0 of the next tile, if its MMAs are already done -- is on its
-      // way out of TMEM.  So the TMEM read-out (~1.7k cycles per tile, port-bound) hides under the ex2 / store work instead
-      // of adding to it, and a TMEM buffer is released as soon as its fourth chunk has been read (3/4 into the tile).
-      const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;
-      const int r = quadw * 32 + lane;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16) + wg * TM;
-      const float sigma = scal[0];
-      const float nshift = -g.shift;
-      const uint32_t sempty_ldr0 = mapa_cluster(sempty_bar(0), leader), sempty_ldr1 = mapa_cluster(sempty_bar(1), leader);
-      // scratch P tile layout = the no-swizzle K-major operand layout: [16 column chunks of 8][128 rows][16 bytes]
-      uint8_t* const p_scratch = scratch + (size_t)channel * PAIR_NSLOT * PTILE_BYTES + (size_t)r * 16;
-      const int n_tiles = u_end - u_begin;
-      const bool no_store = (exp_flags & 1) != 0;                   // perf experiment without the stores
-      int cur_ib = -1, gi = 0;
-      BlockSeg bi{0, 0};
-      float iz_i = 0.f;
-      // column coefficients kappa*sigma / Z_j of the warp's 128 columns: every warp keeps a private copy in shared memory
-      // (lane l publishes columns l, 32 + l, 64 + l, 96 + l, fetched one tile ahead): the epilogue warps never wait for
-      // each other
-      float* const cv_warp = cvw + (warp - EPI_WARP0) * 256;        // [tile parity][128]
-      // running tile coordinates (no divisions in the loop): block pair ib, column block j, and the segment / offset of
-      // this warp's 128-column half of the column block
-      int ib = u_begin / ncb, j = u_begin - ib * ncb;
-      int jseg = (j * PAIR_TN + wg * TM) / g.bseg, joff = (j * PAIR_TN + wg * TM) - jseg * g.bseg;
-      const float* const coef_col = coef + 2 * (int64_t)(wg * TM + lane);
-      float izj[4] = {0.f, 0.f, 0.f, 0.f};
-      if (n_tiles > 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) izj[q] = coef_col[2 * ((int64_t)j * PAIR_TN + 32 * q)];
-      }
-      uint32_t va[32], vb[32];
-      if (n_tiles > 0) {                                            // prologue of the pipeline: chunk 0 of tile 0
-        mbar_wait(sfull_bar(0), 0);
-        tc_fence_after();
-        tmem_ld32(lane_base, va);
-      }
-      for (int t = 0; t < n_tiles; ++t) {
-        if (ib != cur_ib) {
-          cur_ib = ib;
-          const int row0 = g.row_begin + (2 * ib + (int)sub) * TM;
-          gi = row0 + r;
-          bi = block_seg(row0, g.bseg);
-          iz_i = coef[2 * (int64_t)gi];
-        }
-        const bool same_mod = ((jseg & 1) == bi.mod);
-        const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
-        const float k = same_mod ? g.k_intra : g.k_inter;
-        const float ks = (same_mod ? g.w : 1.0f) * sigma;
-        float* cv = cv_warp + (t & 1) * TM;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) cv[32 * q + lane] = izj[q] * ks;
-        // advance to the next unit; fetch its column coefficients now, a whole tile ahead of their use
-        if (++j == ncb) { j = 0; ++ib; jseg = (wg * TM) / g.bseg; joff = wg * TM - jseg * g.bseg; }
-        else { joff += PAIR_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
-        if (t + 1 < n_tiles) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) izj[q] = coef_col[2 * ((int64_t)j * PAIR_TN + 32 * q)];
-        }
-        __syncwarp();
-        const float a_i = iz_i * ks;
-        const uint32_t buf = (uint32_t)t & 1;
-        const uint32_t tb = lane_base + buf * PAIR_TN;
-        const uint32_t tb_next = lane_base + (buf ^ 1) * PAIR_TN;
-        const uint32_t th = 2u * (uint32_t)t + wg;                 // P tile index of this channel
-        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
-        if (r == 0 && wg == 0) TR(1 + sub, t, 0);
-        if (!(exp_flags & 2)) mbar_wait(pempty_bar(slot), (use & 1) ^ 1);   // the dF MMAs that read this scratch slot are done
-        if (r == 0 && wg == 0) TR(1 + sub, t, 1);
-        uint8_t* const prow = p_scratch + (size_t)slot * PTILE_BYTES;
-        // 32 columns of this thread's row -> 16 packed fp16 pairs -> four 16-byte stores.  The same-sample column
-        // (handled in grad_finish) is cleared after packing, in the one chunk of a diagonal tile that holds it, so the
-        // hot loop carries no per-element predicate.
-        auto p_chunk = [&](const uint32_t (&v)[32], int c) {       // c: 32-column chunk of the warp's half (0..3)
-          uint32_t packed[16];
-          const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
-#pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            const float4 cc = cv4[q >> 2];
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]), k, nshift)) * (a_i + cc.x);
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]), k, nshift)) * (a_i + cc.y);
-            const float e2 = fast_exp2(fmaf(__uint_as_float(v[q + 2]), k, nshift)) * (a_i + cc.z);
-            const float e3 = fast_exp2(fmaf(__uint_as_float(v[q + 3]), k, nshift)) * (a_i + cc.w);
-            __half2 h0 = __floats2half2_rn(e0, e1), h1 = __floats2half2_rn(e2, e3);
-            packed[(q >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h0);
-            packed[(q >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
-          }
-          if (diag_tile && c == quadw) {                            // warp-uniform: this chunk holds column r of the P tile
-            const int pi = (r & 31) >> 1;
-            const uint32_t keep = (r & 1) ? 0x0000ffffu : 0xffff0000u;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i == pi) packed[i] &= keep;
-          }
-          if (!no_store) {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              st_global_v4(prow + (c * 4 + ch) * (TM * 16), packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2],
-                           packed[ch * 4 + 3]);
-          }
-        };
-        tmem_ld_wait();                          // chunk 0 (va)
-        tmem_ld32(tb + 32, vb);
-        p_chunk(va, 0);
-        tmem_ld_wait();                          // chunk 1 (vb)
-        tmem_ld32(tb + 64, va);
-        p_chunk(vb, 1);
-        tmem_ld_wait();                          // chunk 2 (va)
-        tmem_ld32(tb + 96, vb);
-        p_chunk(va, 2);
-        tmem_ld_wait();                          // chunk 3 (vb): this warp's part of the S tile is in registers
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(buf ? sempty_ldr1 : sempty_ldr0);
-        if (r == 0 && wg == 0) TR(1 + sub, t, 2);
-        // chunk 0 of the next tile, if its MMAs are already done (usually): its read-out runs under chunk 3's math
-        bool prefetched = false;
-        if (t + 1 < n_tiles && mbar_try_wait(sfull_bar(buf ^ 1), (((uint32_t)t + 1) >> 1) & 1)) {
-          tc_fence_after();
-          tmem_ld32(tb_next, va);
-          prefetched = true;
-        }
-        p_chunk(vb, 3);
-        // No proxy fence here: the arrive releases these generic-proxy stores (cta scope), the signaller's gpu-scope
-        // fence is cumulative over them, and the reading side fences generic -> async before its TMA load.
-        // (Measured alternatives, both slower: staging P in shared memory and writing it with bulk copies -- eight 512-byte
-        // copies per warp or one 32 KiB copy per tile -- queues the stores in front of the operand loads in the copy
-        // engine and starves the MMAs.)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(staged_bar(slot));
-        if (r == 0 && wg == 0) TR(1 + sub, t, 3);
-        if (t + 1 < n_tiles && !prefetched) {
-          mbar_wait(sfull_bar(buf ^ 1), (((uint32_t)t + 1) >> 1) & 1);
-          tc_fence_after();
-          tmem_ld32(tb_next, va);
-        }
-      }
-    }
-  } else {
-    // =========================================================================== G-pair
-    const uint32_t p_tiles = data;
-    const uint32_t ring_base = data + PAIR_PBUF * PTILE_BYTES;
-    const int nbox = g.dim / 128;                      // own [64 j][64 d] boxes per 64-row group: half of each MMA's N
-    const uint32_t group_bytes = (uint32_t)nbox * GBOX_BYTES;
-    const int nmma = (g.dim + 255) / 256;              // MMAs per K = 16 step: N = 256 each (last one 128 if D % 256)
-    if (warp == 0) {
-      Ring ring(PAIR_GGROUPS);
-      QuadWalk walk(u_begin, u_end, ncb);
-      PairSeg sg;
-      while (walk.next(sg)) {
-        for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh) {           // 128-column P tiles
-          for (int kh = 0; kh < 2; ++kh) {                          // 64-row halves of the K = 128 j rows
-            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-            if (elect_one()) {
-              const uint32_t st = ring_base + ring.stage * group_bytes;
-              const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), leader);
-              if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * group_bytes);
-              for (int q = 0; q < nbox; ++q) {
-                const int m = q >> 1;                               // MMA index; its N = nm, this CTA's half = nm / 2
-                const int nm = min(256, g.dim - m * 256);
-                const int d0 = m * 256 + (int)sub * (nm >> 1) + (q & 1) * 64;
-                tma_load_2d_2sm(st + q * GBOX_BYTES, &tmap64, full_ldr, d0, jh * TM + kh * 64);
-              }
-            }
-            __syncwarp();
-            ring.advance();
-          }
-        }
-      }
-    } else if (warp == 2 || warp == 3) {
-      // two P loaders (even / odd tiles): this channel's published scratch tile -> smem P buffer pb (same pb in both
-      // CTAs); bytes counted on the leader's pbfull barrier
-      const uint32_t n_ptiles = 2u * (uint32_t)(u_end - u_begin);
-      for (uint32_t th = (uint32_t)(warp - 2); th < n_ptiles; th += 2) {
-        const uint32_t slot = th % PAIR_NSLOT, use = th / PAIR_NSLOT;
-        const uint32_t pb = th % PAIR_PBUF, puse = th / PAIR_PBUF;
-        if (!(exp_flags & 2)) mbar_wait_cluster(pready_bar(slot), use & 1);
-        fence_proxy_async_global();
-        mbar_wait(pbempty_bar(pb), (puse & 1) ^ 1);
-        if (elect_one()) {
-          if (sub == 0) mbar_arrive_expect_tx(pbfull_bar(pb), 2 * PTILE_BYTES);
-          tma_load_2d_2sm(p_tiles + pb * PTILE_BYTES, &tmap_p, mapa_cluster(pbfull_bar(pb), leader), 0,
-                          (channel * PAIR_NSLOT + (int)slot) * 256);
-        }
-        __syncwarp();
-      }
-    } else if (warp == 1 && sub == 0) {
-      Ring ring(PAIR_GGROUPS);
-      uint32_t th = 0, seg_iter = 0;
-      QuadWalk walk(u_begin, u_end, ncb);
-      PairSeg sg;
-      while (walk.next(sg)) {
-        mbar_wait_cluster(acc_empty, (seg_iter & 1) ^ 1);   // both CTAs' drain warps have emptied the previous segment
-        tc_fence_after();
-        for (int jh = 2 * sg.j0; jh < 2 * sg.j1; ++jh, ++th) {
-          const uint32_t pb = th % PAIR_PBUF, puse = th / PAIR_PBUF;
-          const uint32_t slot = th % PAIR_NSLOT;
-          if (lane == 0) TR(5, th, 0);
-          mbar_wait(pbfull_bar(pb), puse & 1);              // both P tiles have landed in shared memory (TMA)
-          if (lane == 0) TR(5, th, 1);
-          tc_fence_after();
-          const uint32_t p_tile = p_tiles + pb * PTILE_BYTES;
-          for (int kh = 0; kh < 2; ++kh) {
-            mbar_wait(full_bar(ring.stage), ring.phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t st = ring_base + ring.stage * group_bytes;
-              for (int m = 0; m < nmma; ++m) {
-                const int nm = min(256, g.dim - m * 256);
-                const uint32_t idesc = make_idesc_f16(256, nm, 0, 0, 0, 1);
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  // A = P[:, 64 kh + 16 k16 .. +16): no-swizzle K-major, column chunks 8 kh + 2 k16 and the next one
-                  // (2048 bytes apart), 8-row groups 128 bytes apart; B = Fhat rows 64 kh + 16 k16 .. +16 of this CTA's
-                  // [64 j][64 d] boxes 2m, 2m + 1, MN-major: 16 K rows = 2048 bytes, next 64-wide MN atom = next box
-                  const uint64_t ad = make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * (TM * 16), TM * 16, 128);
-                  const uint64_t bd = make_smem_desc_sw128(st + 2 * m * GBOX_BYTES + k16 * 2048, 1024, GBOX_BYTES);
-                  umma_ss_2sm(tmem_base + m * 256, ad, bd, idesc, (jh > 2 * sg.j0 || kh > 0 || k16 > 0) ? 1u : 0u);
-                }
-              }
-              umma_commit_2sm(empty_bar(ring.stage), kMaskG);
-            }
-            __syncwarp();
-            ring.advance();
-          }
-          if (elect_one()) {
-            umma_commit_2sm(pbempty_bar(pb), kMaskG);
-            umma_commit_2sm(pempty_bar(slot), kMaskS);      // scratch slot `slot` of both channels is free again
-          }
-          if (lane == 0) TR(5, th, 2);
-          __syncwarp();
-        }
-        if (elect_one()) umma_commit_2sm(acc_full, kMaskG);
-        __syncwarp();
-        ++seg_iter;
-      }
-    } else if (warp >= EPI_WARP0) {
-      const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;     // wg: which 256-column half of D
-      const int r = quadw * 32 + lane;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16);
-      const uint32_t acc_empty_ldr = mapa_cluster(acc_empty, leader);
-      uint32_t seg_iter = 0;
-      QuadWalk walk(u_begin, u_end, ncb);
-      PairSeg sg;
-      while (walk.next(sg)) {
-        const int gi = g.row_begin + (2 * sg.ib + (int)sub) * TM + r;
-        mbar_wait(acc_full, seg_iter & 1);
-        tc_fence_after();
-        float* out = dfhat + (int64_t)(gi - g.row_begin) * g.dim;
-        const bool whole = (sg.j0 == 0 && sg.j1 == ncb);
-        const int c_end = min(g.dim, wg * 256 + 256) / 32;
-#pragma unroll 1
-        for (int c = wg * 8; c < c_end; ++c) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + c * 32, v);
-          tmem_ld_wait();
-          if (whole) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4)
-              *reinterpret_cast<float4*>(out + c * 32 + q) =
-                  make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
-                              __uint_as_float(v[q + 3]));
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4)
-              red_add_f32x4(out + c * 32 + q, __uint_as_float(v[q]), __uint_as_float(v[q + 1]),
-                            __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_ldr);
-        ++seg_iter;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                    // no CTA leaves while a peer may still touch its shared memory / TMEM pair
-  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
-}
-
-// ================================================================================================
 // Self-test kernel: one CTA, D[128][n] = A[128][k] * B^T with the operand forms the real kernels use.
 //   variant 0: A, B K-major from TMA tiles (the S product)
 //   variant 1: A K-major written by threads with the swizzle formula (the P tile), B MN-major TMA tiles
@@ -1833,7 +1220,7 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   if (threadIdx.x == 0) {
     uint32_t bytes = 0;
-    if (variant == 0) {
+    if (variant == 0 || variant == 6) {
       for (int kc = 0; kc < nk; ++kc) { tma_load_2d(a_s + kc * CHUNK_BYTES, &tmap_a, bar, kc * KC, 0); bytes += CHUNK_BYTES; }
     }
     if (variant == 1) {
@@ -1847,8 +1234,8 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     mbar_arrive_expect_tx(bar, bytes);
     mbar_wait(bar, 0);
     tc_fence_after();
-    if (variant == 0) {
-      const uint32_t idesc = make_idesc_f16(128, n, 0, 0, 0, 0);
+    if (variant == 0 || variant == 6) {
+      const uint32_t idesc = make_idesc_f16(128, n, 0, variant == 6 ? 1 : 0, 0, 0);      // variant 6: A fp16, B bf16
       for (int kc = 0; kc < nk; ++kc)
         for (int kk = 0; kk < 4; ++kk)
           umma_ss(tmem_base, kmajor_desc(a_s + kc * CHUNK_BYTES) + kk * 2, kmajor_desc(b_s + kc * bchunk) + kk * 2,
@@ -1950,10 +1337,9 @@ selftest_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 
-constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;
 
 // CROSSCLR_BWD_VARIANT (A/B measurements, tests): 1 forces the single-CTA slab kernel, 2 the 1 S-CTA + G-CTA(s)
-// cluster kernel, 3 the cta_group::2 quad kernel (D <= 512, D % 128 == 0); default 0 = chosen by shape.
+// cluster kernel, 4 the dataflow kernel (flow_kernels.cu) below its size threshold; default 0 = chosen by shape.
 int bwd_variant() {
   static int v = -1;
   if (v < 0) {
@@ -1965,16 +1351,6 @@ int bwd_variant() {
 
 }  // namespace
 
-// CROSSCLR_FWD_VARIANT=1 forces the single-CTA forward (A/B measurements, tests); default: cta_group::2 pairs.
-int fwd_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CROSSCLR_FWD_VARIANT");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
-}
-
 // CROSSCLR_FWD_SYM=0 disables the symmetric (upper-triangle) walk of the single-rank forward (A/B measurements).
 static bool fwd_sym_enabled() {
   static int v = -1;
@@ -1985,14 +1361,18 @@ static bool fwd_sym_enabled() {
   return v != 0;
 }
 
+constexpr int kFwdQvBytes = 16 * 2 * 64 * 4;      // per-warp column scales of the forward's 16 epilogue warps
+
 template <bool kResident, bool kSym>
-static int launch_fwd_tc2_t(const CUtensorMap& tmap, const Geometry& g, float* stats, cudaStream_t st) {
+static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, float* stats, cudaStream_t st,
+                            const FwdFinalize& fin) {
   const int nk = g.dim / KC, ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
   const int tiles = kSym ? ncb * (ncb + 1) / 2 : nrbp * ncb;
   const size_t a_bytes = kResident ? (size_t)nk * CHUNK_BYTES : 0;
   const size_t stage_bytes = (size_t)(kResident ? 1 : 2) * CHUNK_BYTES;
-  const int stages = (int)std::min<size_t>(MAX_SLOTS, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);
-  const size_t smem = 1024 + a_bytes + (size_t)stages * stage_bytes + kBarBytes;
+  const size_t fixed = 1024 + kBarBytes + kFwdQvBytes + a_bytes;
+  const int stages = (int)std::min<size_t>(MAX_SLOTS, (kMaxSmem - fixed) / stage_bytes);
+  const size_t smem = fixed + (size_t)stages * stage_bytes;
   CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident, kSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * std::min(tiles, sm_count() / 2));
@@ -2004,37 +1384,25 @@ static int launch_fwd_tc2_t(const CUtensorMap& tmap, const Geometry& g, float* s
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   static const int exp_flags = getenv("CROSSCLR_FWD_EXP") ? atoi(getenv("CROSSCLR_FWD_EXP")) : 0;   // perf experiments only
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym>, tmap, g, stats, tiles, ncb, nk, stages, exp_flags));
+  TimedLaunch timed(CROSSCLR_K_FWD, st);
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym>, tmap, (const uint8_t*)feat, g, stats, tiles, ncb, nk,
+                                   stages, exp_flags, fin));
   return check_launch("fwd_tc2_kernel");
 }
 
-int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_t st) {
+bool fwd_tc_can_finalize(const Geometry& g) { return g.row_count == g.rows && g.row_begin == 0; }
+
+int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_t st, const FwdFinalize* fin_req) {
+  const FwdFinalize fin = (fin_req != nullptr && fwd_tc_can_finalize(g)) ? *fin_req : FwdFinalize{nullptr, nullptr, nullptr, nullptr};
+  if (fin_req != nullptr && fin.ticket == nullptr) { set_error("fused finalize needs a single-rank problem"); return CROSSCLR_EINVAL; }
   CUtensorMap tmap;
-  int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
+  int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
-  const int nk = g.dim / KC, ncb = g.rows / FWD_TN, nrb = g.row_count / TM;
-  const int tiles = nrb * ncb;
-  TimedLaunch timed(CROSSCLR_K_FWD, st);
-  const bool resident = nk <= MAX_RES_CHUNKS;
-  if (fwd_variant() == 0) {
-    // single rank: all rows are owned, the Gram matrix is square and symmetric -> upper triangle of pair tiles only
-    const bool sym = g.row_count == g.rows && g.row_begin == 0 && fwd_sym_enabled();
-    if (sym) return resident ? launch_fwd_tc2_t<true, true>(tmap, g, stats, st) : launch_fwd_tc2_t<false, true>(tmap, g, stats, st);
-    return resident ? launch_fwd_tc2_t<true, false>(tmap, g, stats, st) : launch_fwd_tc2_t<false, false>(tmap, g, stats, st);
-  }
-  const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
-  const size_t stage_bytes = (size_t)(resident ? 2 : 3) * CHUNK_BYTES;
-  const int stages = (int)std::min<size_t>(6, (kMaxSmem - 1024 - kBarBytes - a_bytes) / stage_bytes);
-  const size_t smem = 1024 + a_bytes + (size_t)stages * stage_bytes + kBarBytes;
-  const int grid = std::min(tiles, sm_count());
-  if (resident) {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, g, stats, tiles, ncb, nk, stages);
-  } else {
-    CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, g, stats, tiles, ncb, nk, stages);
-  }
-  return check_launch("fwd_tc_kernel");
+  const bool resident = g.dim / KC <= MAX_RES_CHUNKS;
+  // single rank: all rows are owned, the Gram matrix is square and symmetric -> upper triangle of pair tiles only
+  const bool sym = g.row_count == g.rows && g.row_begin == 0 && fwd_sym_enabled();
+  if (sym) return resident ? launch_fwd_tc2_t<true, true>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, true>(tmap, feat, g, stats, st, fin);
+  return resident ? launch_fwd_tc2_t<true, false>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, false>(tmap, feat, g, stats, st, fin);
 }
 
 // How many clusters of bwd_pair_kernel (1 S-CTA + csize-1 G-CTAs) can be resident at once.  Queried once per
@@ -2104,7 +1472,7 @@ template <bool kResident>
 static int launch_bwd_pair_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
                              const float* scal, float* dfhat, void* scratch, int csize, cudaStream_t st) {
   CUtensorMap tmap64;                     // [64 rows][64 cols] boxes for the G-CTAs' MN-major operand groups
-  int rc = make_tmap_f16(&tmap64, feat, (uint64_t)g.rows, (uint64_t)g.dim, 64);
+  int rc = CC_FEAT_TMAP(&tmap64, feat, g, 64);
   if (rc) return rc;
   const int nk = g.dim / KC, ncb = g.rows / PAIR_TN, nrb = g.row_count / TM;
   const long long n_units_ll = (long long)nrb * ncb;
@@ -2114,6 +1482,7 @@ static int launch_bwd_pair_t(const CUtensorMap& tmap, const void* feat, const Ge
   const size_t a_bytes = kResident ? (size_t)nk * CHUNK_BYTES : 0;
   const int s_stages = std::min((int)((kMaxSmem - PAIR_HDR - a_bytes) / ((kResident ? 2 : 3) * CHUNK_BYTES)), MAX_SLOTS);
   const int nclusters = std::min(n_units, pair_clusters_resident<kResident>(csize));
+  TimedLaunch timed(CROSSCLR_K_BWD, st);               // after the host-side preparation: the bracket holds device work only
   CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   static const int exp_flags = getenv("CROSSCLR_PAIR_EXP") ? atoi(getenv("CROSSCLR_PAIR_EXP")) : 0;
   unsigned long long* trace = trace_buffer(st);
@@ -2126,80 +1495,14 @@ static int launch_bwd_pair_t(const CUtensorMap& tmap, const void* feat, const Ge
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_pair_kernel<kResident>, tmap, tmap64, g, coef, scal, dfhat,
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_pair_kernel<kResident>, tmap, tmap64, (const uint8_t*)feat, g, coef, scal, dfhat,
                                    (uint8_t*)scratch, n_units, ncb, nk, s_stages, exp_flags, trace));
   trace_dump(trace, st);
   return check_launch("bwd_pair_kernel");
 }
 
-// resident clusters of bwd_quad_kernel (4 CTAs, 227 KiB of shared memory each); queried once
-static int quad_clusters_resident() {
-  static int cached = -1;
-  if (cached < 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(4 * (sm_count() / 4));
-    cfg.blockDim = dim3(QUAD_THREADS);
-    cfg.dynamicSmemBytes = kMaxSmem;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr; cfg.numAttrs = 1;
-    int c = 0;
-    cudaFuncSetAttribute(bwd_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (cudaOccupancyMaxActiveClusters(&c, bwd_quad_kernel, &cfg) != cudaSuccess || c < 0) {
-      (void)cudaGetLastError();
-      c = 0;
-    }
-    cached = std::min(c, sm_count() / 4);
-  }
-  return cached;
-}
-
-// The quad kernel halves the L2 -> SM operand traffic of the 1 S-CTA + 1 G-CTA kernel, which is what bounds that one
-// (measured on B200, D = 512, quad vs pair: B = 4096 148-150 vs 150-154 us in three back-to-back A/B runs, B = 8192 0.449
-// vs 0.491 ms, B = 16384 1.87 vs 2.28 ms, B = 32768 8.98 vs 9.39 ms).  Used from 8192 stacked rows up (below that the
-// 4-CTA granularity leaves SMs idle); CROSSCLR_BWD_VARIANT=3 forces it, 2 forces the pair kernel.
-static bool use_quad(const Geometry& g) {
-  if (g.dim > 512 || g.dim % 128 != 0 || quad_clusters_resident() * 4 * 10 < sm_count() * 8) return false;
-  if (bwd_variant() == 3) return true;
-  return bwd_variant() == 0 && g.dim == 512 && g.rows >= 8192;
-}
-
-static int launch_bwd_quad(const CUtensorMap& tmap, const void* feat, const Geometry& g, const float* coef,
-                           const float* scal, float* dfhat, void* scratch, cudaStream_t st) {
-  CUtensorMap tmap64, tmap_p;             // [64 rows][64 cols] boxes of Fhat; whole 32 KiB P tiles of the scratch rings
-  int rc = make_tmap_f16(&tmap64, feat, (uint64_t)g.rows, (uint64_t)g.dim, 64);
-  if (rc) return rc;
-  const int nk = g.dim / KC, ncb = g.rows / PAIR_TN, nrbp = g.row_count / (2 * TM);
-  const long long n_units_ll = (long long)nrbp * ncb;
-  if (n_units_ll > 0x7fffffffLL) { set_error("crossclr_bwd: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
-  const int n_units = (int)n_units_ll;
-  const int nquads = std::min(n_units, quad_clusters_resident());
-  rc = make_tmap_f16(&tmap_p, scratch, (uint64_t)nquads * 2 * PAIR_NSLOT * 256, 64, 256, /*swizzle=*/false);
-  if (rc) return rc;
-  CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-  const int s_stages = std::min((int)((kMaxSmem - QUAD_HDR - (size_t)nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS);
-  CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(4 * nquads);
-  cfg.blockDim = dim3(QUAD_THREADS);
-  cfg.dynamicSmemBytes = kMaxSmem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr; cfg.numAttrs = 1;
-  static const int exp_flags = getenv("CROSSCLR_PAIR_EXP") ? atoi(getenv("CROSSCLR_PAIR_EXP")) : 0;   // perf experiments only
-  unsigned long long* trace = trace_buffer(st);
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, bwd_quad_kernel, tmap, tmap64, tmap_p, g, coef, scal, dfhat, (uint8_t*)scratch,
-                                   n_units, ncb, nk, s_stages, exp_flags, trace));
-  trace_dump(trace, st);
-  return check_launch("bwd_quad_kernel");
-}
-
 const char* bwd_tc_kernel_name(const Geometry& g) {
   if (bwd_flow_applies(g)) return "bwd_flow_kernel";
-  if (use_quad(g)) return "bwd_quad_kernel";
   if (pair_cluster_size(g.dim)) return "bwd_pair_kernel";
   return "bwd_tc_kernel";
 }
@@ -2207,18 +1510,11 @@ const char* bwd_tc_kernel_name(const Geometry& g) {
 int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const float* scal, float* dfhat,
                   void* scratch, cudaStream_t st) {
   CUtensorMap tmap;
-  int rc = make_tmap_f16(&tmap, feat, (uint64_t)g.rows, (uint64_t)g.dim, TM);
+  int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
-  if (bwd_flow_applies(g)) {                           // producer pairs -> P-tile pool -> consumer pairs (flow_kernels.cu)
-    TimedLaunch timed(CROSSCLR_K_BWD, st);
+  if (bwd_flow_applies(g))                             // producer pairs -> P-tile pool -> consumer pairs (flow_kernels.cu)
     return launch_bwd_flow(g, feat, coef, scal, dfhat, scratch, st);
-  }
-  if (use_quad(g)) {                                   // S-pair + G-pair, cta_group::2 MMAs
-    TimedLaunch timed(CROSSCLR_K_BWD, st);
-    return launch_bwd_quad(tmap, feat, g, coef, scal, dfhat, scratch, st);
-  }
   if (const int csize = pair_cluster_size(g.dim)) {    // > 1 slab would recompute S: role-specialised CTA clusters
-    TimedLaunch timed(CROSSCLR_K_BWD, st);
     return g.dim <= 512 ? launch_bwd_pair_t<true>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st)
                         : launch_bwd_pair_t<false>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st);
   }
@@ -2230,24 +1526,24 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   TimedLaunch timed(CROSSCLR_K_BWD, st);
   const bool resident = nk <= MAX_RES_CHUNKS;
   const size_t a_bytes = resident ? (size_t)nk * CHUNK_BYTES : 0;
-  const size_t avail = kMaxSmem - 1024 - 2 * BWD_TN * 4 - kBarBytes - a_bytes;
+  const size_t avail = kMaxSmem - 1024 - 2 * BWD_TN * 8 - kBarBytes - a_bytes;
   const int slots = std::min((int)(avail / CHUNK_BYTES) & ~1, MAX_SLOTS);
-  const size_t smem = 1024 + a_bytes + (size_t)slots * CHUNK_BYTES + 2 * BWD_TN * 4 + kBarBytes;
+  const size_t smem = 1024 + a_bytes + (size_t)slots * CHUNK_BYTES + 2 * BWD_TN * 8 + kBarBytes;
   const int grid = std::min(n_units, sm_count());
   // CTAs own balanced unit ranges; a range that cuts an item adds its partial slab into dfhat
   CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   if (resident) {
     CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_units, n_slabs, ncb, nk, slots);
+    bwd_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(tmap, (const uint8_t*)feat, g, coef, scal, dfhat, n_units, n_slabs, ncb, nk, slots);
   } else {
     CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, g, coef, scal, dfhat, n_units, n_slabs, ncb, nk, slots);
+    bwd_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(tmap, (const uint8_t*)feat, g, coef, scal, dfhat, n_units, n_slabs, ncb, nk, slots);
   }
   return check_launch("bwd_tc_kernel");
 }
 
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k) {
-  if (variant < 0 || variant > 5 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
+  if (variant < 0 || variant > 6 || k % KC != 0 || k < KC || k > 256 || n % 32 != 0 || n < 32 || n > 256 ||
       (variant == 1 && n % 64 != 0) || (variant == 4 && n % 64 != 0)) {
     set_error("crossclr_selftest: unsupported variant/shape (variant %d n %d k %d)", variant, n, k);
     return CROSSCLR_EINVAL;

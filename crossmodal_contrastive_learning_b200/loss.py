@@ -75,10 +75,11 @@ class _NativeOps:
         self.lib = N.load()
 
     def plan(self, prob, in_dtype, exact):
+        """(path code, stacked-row dtype, stacked-row pitch in elements) the library picks for this problem."""
         code = self.lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[in_dtype], 1 if exact else 0)
         if code < 0:
             N.check(code, "crossclr_choose_path")
-        return code, _FEAT_TORCH[self.lib.crossclr_feature_dtype(code)]
+        return code, _FEAT_TORCH[self.lib.crossclr_feature_dtype(code)], int(self.lib.crossclr_feature_pitch(code, prob.dim))
 
     def pack(self, x, feat_out, rnorm_out):
         B, D = x.shape
@@ -129,11 +130,11 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     dev = v.device
     world, rank = _group_info(group)
     prob = N.Problem(2 * world, B, D, 2 * rank * B, 2 * B, float(temperature), float(negative_weight))
-    code, feat_dtype = ops.plan(prob, v.dtype, path == "simt")
+    code, feat_dtype, pitch = ops.plan(prob, v.dtype, path == "simt")
     if path == "tc" and code != N.PATH_TC:
         raise RuntimeError(f"tensor-core path needs B % 128 == 0 and D % 64 == 0 (got B={B}, D={D})")
     rows = 2 * world * B
-    feat_all = torch.empty((2 * world, B, D), dtype=feat_dtype, device=dev)
+    feat_all = torch.empty((2 * world, B, pitch), dtype=feat_dtype, device=dev)
     rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
     stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
     coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)          # separate allocations: the custom op returns
@@ -209,10 +210,11 @@ class _CrossCLRFunction(torch.autograd.Function):
 _OUT_DTYPE = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}
 
 
-def _plan_py(B, D, path):
-    """The path libcrossclr_b200 picks (csrc/api.cu: crossclr_choose_path), for shape inference without the library."""
-    tc = (B % 128 == 0) and (D % 64 == 0) and path != "simt"
-    return (N.PATH_TC, torch.float16) if tc else (N.PATH_SIMT, torch.float32)
+def _plan_py(B, D, path, in_dtype):
+    """The path libcrossclr_b200 picks for a single-rank problem, asked of the library itself (crossclr_choose_path is a pure
+    function of the shape and dtype: no device needed), so that shape inference can never drift from the kernels' rule."""
+    prob = N.Problem(2, B, D, 0, 2 * B, 1.0, 1.0)
+    return _ops().plan(prob, torch.float32 if in_dtype == torch.float64 else in_dtype, path == "simt")
 
 
 @torch.library.custom_op("crossclr_b200::forward", mutates_args=())
@@ -228,9 +230,9 @@ def _op_forward(video: torch.Tensor, text: torch.Tensor, temperature: float, neg
 @_op_forward.register_fake
 def _(video, text, temperature, negative_weight, path):
     B, D = video.shape
-    _, fdt = _plan_py(B, D, path)
+    _, fdt, pitch = _plan_py(B, D, path, video.dtype)
     dev = video.device
-    return (torch.empty((), dtype=torch.float64, device=dev), torch.empty((2, B, D), dtype=fdt, device=dev),
+    return (torch.empty((), dtype=torch.float64, device=dev), torch.empty((2, B, pitch), dtype=fdt, device=dev),
             torch.empty(2 * B, dtype=torch.float32, device=dev), torch.empty((2 * B, 2), dtype=torch.float32, device=dev),
             torch.empty(4, dtype=torch.float32, device=dev))
 
@@ -240,7 +242,7 @@ def _op_backward(feat: torch.Tensor, rnorm: torch.Tensor, coef: torch.Tensor, sc
                  batch: int, dim: int, temperature: float, negative_weight: float, path: str, grad_scale: float,
                  out_dtype: int) -> tuple[torch.Tensor, torch.Tensor]:
     prob = N.Problem(2, batch, dim, 0, 2 * batch, float(temperature), float(negative_weight))
-    code, _ = _plan_py(batch, dim, path)
+    code = N.PATH_SIMT if feat.dtype == torch.float32 else N.PATH_TC
     with torch.cuda.device(feat.device):
         return _backward_impl(_ops(), prob, code, (feat, rnorm, coef, scal), grad_out, grad_scale,
                               _OUT_DTYPE[out_dtype])

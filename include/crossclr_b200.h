@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CROSSCLR_VERSION 110          /* 0.1.1 */
+#define CROSSCLR_VERSION 120          /* 0.1.2 */
 
 /* error codes */
 #define CROSSCLR_OK            0
@@ -51,8 +51,21 @@ extern "C" {
 /* kernel families ("path") */
 #define CROSSCLR_PATH_AUTO 0          /* tensor-core path when the shape allows it, else SIMT        */
 #define CROSSCLR_PATH_SIMT 1          /* fp32 CUDA-core kernels, any B / D, fp32 stacked features     */
-#define CROSSCLR_PATH_TC   2          /* tcgen05 + TMA + TMEM kernels, fp16 stacked features,
+#define CROSSCLR_PATH_TC   2          /* tcgen05 + TMA + TMEM kernels, fp16 stacked rows,
                                          requires bseg % 128 == 0 and dim % 64 == 0                   */
+
+/* Stacked rows of the tensor-core path.  Row g is stored as f_g with a row pitch of dim + CROSSCLR_ROW_TAIL elements;
+ * the first 4 bytes of the tail hold the fp32 residual scale q_g, and the L2-normalised row is q_g * f_g.
+ *   16-bit inputs: f_g = x_g * 2^-e (EXACT: a power-of-two rescale into ||f|| in [1, 2), stored as fp16 -- a bf16 value
+ *                  below 2 is exactly representable in fp16 down to 2^-17), q_g = 2^e / ||x_g|| in (1/2, 1]; rows inside the
+ *                  eps clamp (||x|| < 1e-12) are stored as in the fp32 case.
+ *                  The tensor cores then multiply the caller's own values and the cosine is formed in the fp32
+ *                  epilogue as q_i q_j (f_i . f_j): no operand rounding at all (gradients ~1e-5 of the reference).
+ *                  (kind::f16 MMAs need A and B of one format and the probability operand must be fp16 -- bf16 would
+ *                  cost 1.6e-3 on the gradients -- hence fp16 rows for bf16 inputs too.)
+ *   fp32 inputs:   f_g = fp16(x_g / max(||x_g||, 1e-12)), q_g = 1 (operand rounding 2^-12: gradients within ~2e-5 / tau).
+ * The SIMT path keeps plain fp32 normalised rows, pitch dim, no tail. */
+#define CROSSCLR_ROW_TAIL 64
 
 typedef struct crossclr_problem {
   int32_t nseg;             /* segments in the stacked matrix = 2 * world_size                        */
@@ -70,13 +83,15 @@ CROSSCLR_API const char* crossclr_last_error(void);
 /* 1 if `device` can run this library (compute capability 10.x), 0 otherwise, <0 on error. */
 CROSSCLR_API int crossclr_device_supported(int device);
 
-/* Resolve CROSSCLR_PATH_AUTO for a problem: CROSSCLR_PATH_TC when the shape allows it (the fp16
- * normalised operand keeps gradients within ~2e-4 of the fp32 reference), else CROSSCLR_PATH_SIMT.
- * `in_dtype` / `exact` are hints: exact != 0 forces the fp32 SIMT path. */
+/* Resolve CROSSCLR_PATH_AUTO for a problem and input dtype: CROSSCLR_PATH_TC when the shape allows it, else
+ * CROSSCLR_PATH_SIMT.  exact != 0 forces the fp32 SIMT path. */
 CROSSCLR_API int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact);
 
-/* Stacked-feature element type a path consumes: SIMT -> CROSSCLR_F32, TC -> CROSSCLR_F16. */
+/* Stacked-row element type a path consumes: SIMT -> CROSSCLR_F32, TC -> CROSSCLR_F16. */
 CROSSCLR_API int crossclr_feature_dtype(int path);
+
+/* Row pitch (in elements) of the stacked matrix of a path: dim for SIMT, dim + CROSSCLR_ROW_TAIL for TC. */
+CROSSCLR_API int64_t crossclr_feature_pitch(int path, int32_t dim);
 
 /* Bytes of scratch crossclr_bwd needs for this problem and path (crossclr_fwd needs none). */
 CROSSCLR_API size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path);
@@ -84,7 +99,8 @@ CROSSCLR_API size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int pa
 /*
  * L2-normalise one modality block `x` ([rows][dim], element stride 1, row stride `x_row_stride`
  * elements, dtype `in_dtype`) into its segment of the stacked matrix: `feat_out` points at the first
- * row of that segment (dtype `feat_dtype`, row stride dim) and receives x / max(||x||_2, 1e-12);
+ * row of that segment (dtype `feat_dtype`; CROSSCLR_F32: row stride dim, receives x / max(||x||_2, 1e-12);
+ * CROSSCLR_F16 / CROSSCLR_BF16: row stride dim + CROSSCLR_ROW_TAIL, receives (f, q) as described above);
  * `rnorm_out[rows]` receives 1 / max(||x||_2, 1e-12) (kept by the caller for the backward).
  * Replaces: trainer/loss.py:79-80 (F.normalize x2).
  */
@@ -93,7 +109,7 @@ CROSSCLR_API int crossclr_pack(const void* x, int in_dtype, int64_t x_row_stride
 
 /*
  * Both modality blocks of one rank in one launch: rows of `video` then rows of `text` are normalised into the
- * rank's two consecutive segments starting at `feat_out` ([2*rows][dim]); `rnorm_out[2*rows]`.
+ * rank's two consecutive segments starting at `feat_out` ([2*rows][pitch]); `rnorm_out[2*rows]`.
  * Replaces: trainer/loss.py:79-80.
  */
 CROSSCLR_API int crossclr_pack2(const void* video, const void* text, int in_dtype, int64_t video_row_stride,
@@ -102,8 +118,8 @@ CROSSCLR_API int crossclr_pack2(const void* video, const void* text, int in_dtyp
 
 /*
  * Single-rank forward in one call (nseg == 2): crossclr_pack2 -> crossclr_fwd -> crossclr_finalize on `stream`.
- * Buffers as in the individual calls: feat [2*bseg][dim] (dtype crossclr_feature_dtype(path)), rnorm [2*bseg],
- * stats / coef [2*bseg][2], scal [4], loss_out double[1].  Replaces: trainer/loss.py:79-114 (forward).
+ * Buffers as in the individual calls: feat [2*bseg][crossclr_feature_pitch(path, dim)] (dtype
+ * crossclr_feature_dtype(path)), rnorm [2*bseg], stats / coef [2*bseg][2], scal [4], loss_out double[1].  Replaces: trainer/loss.py:79-114 (forward).
  */
 CROSSCLR_API int crossclr_forward(const crossclr_problem_t* p, int path, const void* video, const void* text, int in_dtype,
                      int64_t video_row_stride, int64_t text_row_stride, void* feat, float* rnorm, float* stats,
@@ -114,8 +130,8 @@ CROSSCLR_API int crossclr_forward(const crossclr_problem_t* p, int path, const v
  *   stats[2g+0] = X_g    = sum over the 2B-1 non-positive logits of 2^(logit*log2e - shift)
  *                          (includes the intra-modal diagonal, which is logit 0: loss.py:65,96-97)
  *   stats[2g+1] = xpos_g = positive logit * log2e - shift
- * with shift = crossclr_shift(p).  `feat` is the full stacked matrix [nseg*bseg][dim] of normalised
- * rows; `stats` has room for [nseg*bseg][2] floats (only the owned rows are written).
+ * with shift = crossclr_shift(p).  `feat` is the full stacked matrix [nseg*bseg][pitch] in the layout of
+ * `path`; `stats` has room for [nseg*bseg][2] floats (only the owned rows are written).
  * Replaces: trainer/loss.py:83-100 (4 GEMMs, /tau, mask, weight, concat) and the row reductions of
  * :59-60; no B x B intermediate is written to memory.
  */
@@ -127,7 +143,7 @@ CROSSCLR_API int crossclr_fwd(const crossclr_problem_t* p, int path, const void*
  *   loss_out[0] (double) = (1/2B) sum_g log1p(X_g * 2^-xpos_g)          trainer/loss.py:60,:111-114
  *   coef[2g+0] = 1/Z_g, coef[2g+1] = X_g/Z_g   with Z_g = X_g + 2^xpos_g (shifted units)
  *   scal[0] = sigma (power-of-two scale applied to the fp16 probability tiles), scal[1] = 1/sigma,
- *   scal[2] = max_g X_g/Z_g, scal[3] reserved
+ *   scal[2] = max_g X_g/Z_g, scal[3] scratch (the single-rank forward's finalize ticket)
  */
 CROSSCLR_API int crossclr_finalize(const crossclr_problem_t* p, const float* stats, float* coef, double* loss_out,
                       float* scal, void* stream);

@@ -41,16 +41,16 @@ def run_ranks(v, t, world, tau=0.03, w=0.8, path="tc", reps=1):
     B = Bg // world
     dev = v.device
     probs = [N.Problem(2 * world, B, D, 2 * r * B, 2 * B, tau, w) for r in range(world)]
-    code, fdt = ops.plan(probs[0], v.dtype, path == "simt")
-    feat_all = torch.empty((2 * world, B, D), dtype=fdt, device=dev)
+    code, fdt, pitch = ops.plan(probs[0], v.dtype, path == "simt")
+    feat_all = torch.empty((2 * world, B, pitch), dtype=fdt, device=dev)
     rnorm = torch.empty((world, 2 * B), dtype=torch.float32, device=dev)
     stats = torch.empty((2 * world * B, 2), dtype=torch.float32, device=dev)
     coef = torch.empty_like(stats)
     scal = torch.empty(4, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float64, device=dev)
     go = torch.ones((), dtype=torch.float64, device=dev)
-    dv = torch.empty((Bg, D), dtype=v.dtype, device=dev)
-    dt = torch.empty((Bg, D), dtype=v.dtype, device=dev)
+    dv = torch.empty((Bg, D), dtype=torch.float32, device=dev)      # fp32 gradients whatever the input dtype
+    dt = torch.empty((Bg, D), dtype=torch.float32, device=dev)
     for rep in range(reps):
         if rep == reps - 1:
             torch.cuda.synchronize()
@@ -76,7 +76,7 @@ def check(B, D, world, aligned=2.0, sample=None, reps=3):
     t = (v + aligned * torch.randn(B, D, generator=g)).to(torch.bfloat16).float() if aligned else \
         torch.randn(B, D, generator=g).to(torch.bfloat16).float()
     t0 = time.time()
-    loss, dv, dt, kt, name = run_ranks(v.cuda(), t.cuda(), world, reps=reps)
+    loss, dv, dt, kt, name = run_ranks(v.to("cuda", IN_DTYPE), t.to("cuda", IN_DTYPE), world, reps=reps)
     rows = None if sample is None else np.arange(0, B, B // sample) + 1
     rl, rdv, rdt = O.loss_and_grads(v.numpy(), t.numpy(), 0.03, 0.8, rows=rows, row_block=2048)
     dvn, dtn = dv.double().cpu().numpy(), dt.double().cpu().numpy()
@@ -93,8 +93,14 @@ def check(B, D, world, aligned=2.0, sample=None, reps=3):
     return ok
 
 
+IN_DTYPE = torch.bfloat16
+
+
 def main():
+    global IN_DTYPE
     mode = sys.argv[1] if len(sys.argv) > 1 else "quick"
+    if len(sys.argv) > 2:
+        IN_DTYPE = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[sys.argv[2]]
     for variant, n, k in ((5, 128, 128), (5, 64, 64), (5, 256, 128), (3, 128, 128)):
         rc, err = selftest(variant, n, k)
         print(f"selftest variant {variant} n={n} k={k}: rc={rc} max err {err:.3e} {'OK' if rc == 0 and err < 1e-2 else 'FAIL'}", flush=True)

@@ -15,8 +15,8 @@ g = torch.Generator().manual_seed(0)
 v = torch.randn(B, D, generator=g).to(torch.bfloat16).cuda()
 t = torch.randn(B, D, generator=g).to(torch.bfloat16).cuda()
 probs = [N.Problem(2 * world, Bl, D, 2 * r * Bl, 2 * Bl, 0.03, 0.8) for r in range(world)]
-code, fdt = ops.plan(probs[0], v.dtype, False)
-feat = torch.empty((2 * world, Bl, D), dtype=fdt, device="cuda")
+code, fdt, pitch = ops.plan(probs[0], v.dtype, False)
+feat = torch.empty((2 * world, Bl, pitch), dtype=fdt, device="cuda")
 rn = torch.empty((world, 2 * Bl), dtype=torch.float32, device="cuda")
 stats = torch.empty((2 * B, 2), dtype=torch.float32, device="cuda"); coef = torch.empty_like(stats)
 scal = torch.empty(4, dtype=torch.float32, device="cuda"); loss = torch.empty((), dtype=torch.float64, device="cuda")

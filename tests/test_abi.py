@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(N.EXPORTS) == names           # the ctypes binding covers exactly the header
-    assert lib.crossclr_version() == 110
+    assert lib.crossclr_version() == 120
 
 
 def test_planning_and_validation_without_a_device():
@@ -34,10 +34,13 @@ def test_planning_and_validation_without_a_device():
     P = N.Problem
     ok = P(2, 4096, 512, 0, 8192, 0.03, 0.8)
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 0) == N.PATH_TC
+    assert lib.crossclr_choose_path(ctypes.byref(ok), N.F16, 0) == N.PATH_TC
+    assert lib.crossclr_choose_path(ctypes.byref(ok), N.F32, 0) == N.PATH_TC
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 1) == N.PATH_SIMT
     ragged = P(2, 100, 72, 0, 200, 0.03, 0.8)
     assert lib.crossclr_choose_path(ctypes.byref(ragged), N.F32, 0) == N.PATH_SIMT
     assert lib.crossclr_feature_dtype(N.PATH_TC) == N.F16 and lib.crossclr_feature_dtype(N.PATH_SIMT) == N.F32
+    assert lib.crossclr_feature_pitch(N.PATH_SIMT, 512) == 512 and lib.crossclr_feature_pitch(N.PATH_TC, 512) == 512 + N.ROW_TAIL
     assert lib.crossclr_workspace_bytes(ctypes.byref(ok), N.PATH_TC) >= 8192 * 512 * 4
     assert lib.crossclr_shift(ctypes.byref(ok)) == 0.0
     small_tau = P(2, 128, 64, 0, 256, 0.0075, 0.8)

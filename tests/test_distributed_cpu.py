@@ -23,7 +23,7 @@ class NumpyOps:
 
     def plan(self, prob, in_dtype, exact):
         from crossmodal_contrastive_learning_b200 import _native as N
-        return N.PATH_SIMT, torch.float32
+        return N.PATH_SIMT, torch.float32, prob.dim
 
     @staticmethod
     def _shift(prob):
