@@ -261,6 +261,54 @@ def kernel_times_eager(crit, v_dev, t_dev, steps, flush, NAT, torch):
     return NAT.timing_read()
 
 
+def isolated_kernel_ms(M, NAT, torch, crit, v_dev, t_dev, group, flush, reps):
+    """Median device time of the dominant kernel ALONE: the C ABI's `crossclr_bwd_accumulate` (control-word memset + the
+    backward similarity / gradient kernel, nothing else) and `crossclr_fwd` (statistics memset + forward kernel) of this
+    rank's real problem, each captured as its own CUDA graph and replayed between two CUDA events on the launching stream, L2
+    flushed before every replay.  No host work falls inside the bracket (eager brackets carry ~10 us of launch latency)."""
+    import ctypes
+    from crossmodal_contrastive_learning_b200 import loss as L
+    ops = L._ops()
+    lib = M.load_native()
+    with torch.no_grad():
+        _, prob, code, (feat, rnorm, coef, scal) = L._forward_impl(ops, v_dev, t_dev, TAU, W, "auto", group)
+    stats = torch.empty((prob.nseg * prob.bseg, 2), dtype=torch.float32, device=v_dev.device)
+    ws_bytes = int(lib.crossclr_workspace_bytes(ctypes.byref(prob), code))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v_dev.device)
+
+    def bwd():
+        NAT.check(lib.crossclr_bwd_accumulate(ctypes.byref(prob), code, L._ptr(feat), L._ptr(coef), L._ptr(scal), L._ptr(ws),
+                                              ws_bytes, L._stream()), "crossclr_bwd_accumulate")
+
+    def fwd():
+        NAT.check(lib.crossclr_fwd(ctypes.byref(prob), code, L._ptr(feat), L._ptr(stats), None, 0, L._stream()), "crossclr_fwd")
+
+    out = {}
+    for name, fn in (("bwd", bwd), ("fwd", fwd)):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            g.replay()
+            b_.record()
+            torch.cuda.synchronize()
+            ts.append(a_.elapsed_time(b_))
+        ts.sort()
+        out[name] = {"median_ms": ts[len(ts) // 2], "min_ms": ts[0], "mean_ms": sum(ts) / len(ts), "launches": len(ts)}
+    return out
+
+
 def run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush, steps=3, warmup=2):
     """One of the other BASELINE configs, eager module calls (host overhead is noise at these sizes): ms/step (device,
     max over ranks), pairs/s, per-kernel ms, step fraction of the measured sustained bf16 peak."""
@@ -301,6 +349,7 @@ def run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
     kt = kernel_times_eager(crit, v_dev, t_dev, 2, flush, NAT, torch)
+    iso = isolated_kernel_ms(M, NAT, torch, crit, v_dev, t_dev, group, flush, 3)
     _, sustained, _ = measured_peaks()
     alg = 14.0 * Bg * Bg * D / world
     name_bwd = bwd_kernel_from_library(M, NAT, world, rank, Bl, D)
@@ -310,10 +359,12 @@ def run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush
            "kernel_ms_per_step": {k: v[0] / 2 for k, v in kt.items()},
            "step_tflops_alg_per_gpu": alg / (ms * 1e-3) / 1e12, "step_frac_of_sustained": alg / (ms * 1e-3) / 1e12 / sustained,
            "bwd_frac_of_burst": None}
-    bms, bn = kt["bwd"]
-    if bn:
-        burst, _, _ = measured_peaks()
-        out["bwd_frac_of_burst"] = 8.0 * Bg * Bg * D / world / (bms / bn * 1e-3) / 1e12 / burst
+    burst, _, _ = measured_peaks()
+    bt = torch.tensor([iso["bwd"]["mean_ms"], iso["fwd"]["mean_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+    out["bwd_kernel_ms"], out["fwd_kernel_ms"] = float(bt[0]), float(bt[1])
+    out["bwd_frac_of_burst"] = 8.0 * Bg * Bg * D / world / (float(bt[0]) * 1e-3) / 1e12 / burst
     del v_dev, t_dev
     torch.cuda.empty_cache()
     return out
@@ -496,8 +547,12 @@ def run_b200_arm(args):
         clk.end()
     loss_val = float(pipe.loss_host[(pipe._k - 1) & 1]) if use_graph else float(loss_host_eager)
 
-    # per-kernel device times: eager steps behind a spin kernel (no host gaps inside the event brackets)
+    # per-kernel device times: the dominant kernel alone (graph replay), and every kernel family of eager steps
+    iso = isolated_kernel_ms(M, NAT, torch, crit, v_dev, t_dev, group, flush, args.steps)
     ktimes = kernel_times_eager(crit, v_dev, t_dev, args.steps, flush, NAT, torch)
+    iso_t = torch.tensor([iso["bwd"]["mean_ms"], iso["fwd"]["mean_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(iso_t, op=dist.ReduceOp.MAX)
     barrier()
 
     parity = None
@@ -527,9 +582,8 @@ def run_b200_arm(args):
         ms_step = total_ms / args.steps
         # dominant kernel = backward similarity/gradient kernel: 4 products = 8 B^2 D algorithmic FLOPs per step,
         # this rank computes 1/world of them (DESIGN.md "Roofline accounting")
-        fam = {k: (ms / max(n, 1), n) for k, (ms, n) in ktimes.items()}
-        bwd_ms, bwd_n = fam["bwd"]
-        fwd_ms, fwd_n = fam["fwd"]
+        bwd_ms, bwd_n = float(iso_t[0]), iso["bwd"]["launches"]
+        fwd_ms = float(iso_t[1])
         alg_bwd = 8.0 * Bg * Bg * D / world
         alg_fwd = 6.0 * Bg * Bg * D / world
         achieved = alg_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else None
@@ -558,14 +612,18 @@ def run_b200_arm(args):
                          "unit": "TFLOP/s", "frac": (achieved / burst if achieved else None), "traffic": traffic,
                          "peak_source": f"{src} bf16_tflops (burst; kernel timed alone with CUDA events)",
                          "algorithmic_flops_per_launch": alg_bwd, "avg_launch_ms": bwd_ms, "launches_timed": bwd_n,
-                         "timing": "library cudaEvents on the launching stream around the backward launch (control-word memset + "
-                                   "kernel), recorded after all host-side preparation; eager steps",
+                         "timing": "mean over launches_timed replays of a CUDA graph holding ONLY crossclr_bwd_accumulate (control-word "
+                                   "memset + the kernel), CUDA events on the launching stream around each replay, L2 flushed before "
+                                   "each, max over ranks",
+                         "median_launch_ms": iso["bwd"]["median_ms"], "min_launch_ms": iso["bwd"]["min_ms"],
                          "fwd_kernel": {"avg_launch_ms": fwd_ms, "algorithmic_flops_per_launch": alg_fwd,
                                         "achieved": (alg_fwd / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else None)},
                          "step": {"algorithmic_flops": 14.0 * Bg * Bg * D / world,
                                   "achieved": 14.0 * Bg * Bg * D / world / (ms_step * 1e-3) / 1e12,
                                   "frac_of_sustained": 14.0 * Bg * Bg * D / world / (ms_step * 1e-3) / 1e12 / sustained},
-                         "kernel_ms_per_step": {k: ms / args.steps for k, (ms, n) in ktimes.items()}},
+                         "kernel_ms_per_step": {k: ms / args.steps for k, (ms, n) in ktimes.items()},
+                         "kernel_ms_per_step_is": "library cudaEvents around each launch of EAGER steps (every bracket carries ~10 us "
+                                                  "of launch latency on a starved stream: shares, not absolutes)"},
             "clocks": clk.summary(),
         }
         if parity is not None:

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "simt_kernels.cu", "tc_kernels.cu", "flow_kernels.cu", "maxmargin.cu"]
-HEADERS = ["common.cuh", "tc_ptx.cuh", "tc_common.cuh", os.path.join(ROOT, "include", "crossclr_b200.h")]
+HEADERS = ["common.cuh", "tc_ptx.cuh", "tc_common.cuh", "finalize.cuh", os.path.join(ROOT, "include", "crossclr_b200.h")]
 LIB = os.path.join(HERE, "libcrossclr_b200.so")
 
 
@@ -37,8 +37,33 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library.  Safe under several ranks of one node: an exclusive file lock serialises the builders (the
+    staleness check is repeated under the lock, so only the first one compiles) and nvcc writes to a process-unique
+    temporary file that is renamed into place."""
+    import fcntl
+    import tempfile
     if not force and not is_stale():
         return LIB
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            fd, tmp = tempfile.mkstemp(prefix=".libcrossclr_b200.", suffix=".so.tmp", dir=HERE)
+            os.close(fd)
+            try:
+                _compile(tmp, verbose)
+                os.chmod(tmp, 0o755)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return LIB
+
+
+def _compile(out_path: str, verbose: bool) -> None:
     cmd = [
         nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
         "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -47,14 +72,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out_path]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stdout + proc.stderr)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
 
 
 if __name__ == "__main__":

@@ -209,38 +209,53 @@ int crossclr_finalize(const crossclr_problem_t* p, const float* stats, float* co
   return launch_finalize(make_geometry(p), stats, coef, loss_out, scal, (cudaStream_t)stream);
 }
 
-int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned, const float* coef,
-                 const float* scal, const double* grad_out, float grad_scale, void* dv, int64_t dv_row_stride,
-                 void* dt, int64_t dt_row_stride, int out_dtype, void* workspace, size_t workspace_bytes,
-                 void* stream) {
-  int rc = validate_problem(p);
-  if (rc) return rc;
-  CC_REQUIRE(feat && rnorm_owned && coef && scal && dv && dt, "crossclr_bwd: NULL pointer");
-  CC_REQUIRE(dv_row_stride >= p->dim && dt_row_stride >= p->dim, "crossclr_bwd: output row stride < dim");
+// stage 1 of the backward: dfhat (head of the workspace) = sum_j P~ f_j over the owned rows
+static int bwd_accumulate(const crossclr_problem_t* p, int path, const Geometry& g, const void* feat, const float* coef,
+                          const float* scal, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   if (workspace == nullptr || workspace_bytes < ::workspace_bytes(p, path)) {
     set_error("crossclr_bwd: workspace too small (%zu < %zu)", workspace_bytes, ::workspace_bytes(p, path));
     return CROSSCLR_EWORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  const Geometry g = make_geometry(p, path);
   float* dfhat = (float*)workspace;
-  int feat_dtype;
-  bool use_sigma;
   if (path_is_tc(path)) {
     CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
                p->bseg, p->dim);
-    rc = launch_bwd_tc(g, feat, coef, scal, dfhat, (char*)workspace + dfhat_bytes(p), st);
-    feat_dtype = CROSSCLR_F16;
-    use_sigma = true;
-  } else {
-    CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_bwd: path must be SIMT or TC (got %d)", path);
-    rc = launch_bwd_simt(g, (const float*)feat, coef, dfhat, st);
-    feat_dtype = CROSSCLR_F32;
-    use_sigma = false;
+    return launch_bwd_tc(g, feat, coef, scal, dfhat, (char*)workspace + dfhat_bytes(p), st);
   }
+  CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_bwd: path must be SIMT or TC (got %d)", path);
+  return launch_bwd_simt(g, (const float*)feat, coef, dfhat, st);
+}
+
+int crossclr_bwd_accumulate(const crossclr_problem_t* p, int path, const void* feat, const float* coef, const float* scal,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_problem(p);
   if (rc) return rc;
-  return launch_grad_finish(g, feat, feat_dtype, rnorm_owned, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
-                            dv_row_stride, dt, dt_row_stride, out_dtype, st);
+  CC_REQUIRE(feat && coef && scal, "crossclr_bwd_accumulate: NULL pointer");
+  return bwd_accumulate(p, path, make_geometry(p, path), feat, coef, scal, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int crossclr_bwd_finish(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned, const float* coef,
+                        const float* scal, const double* grad_out, float grad_scale, void* dv, int64_t dv_row_stride,
+                        void* dt, int64_t dt_row_stride, int out_dtype, const void* workspace, void* stream) {
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  CC_REQUIRE(feat && rnorm_owned && coef && scal && dv && dt && workspace, "crossclr_bwd_finish: NULL pointer");
+  CC_REQUIRE(dv_row_stride >= p->dim && dt_row_stride >= p->dim, "crossclr_bwd_finish: output row stride < dim");
+  CC_REQUIRE(path == CROSSCLR_PATH_SIMT || path_is_tc(path), "crossclr_bwd_finish: path must be SIMT or TC (got %d)", path);
+  const bool tc = path_is_tc(path);
+  return launch_grad_finish(make_geometry(p, path), feat, tc ? CROSSCLR_F16 : CROSSCLR_F32, rnorm_owned, coef, scal, tc, grad_out,
+                            grad_scale, (const float*)workspace, dv, dv_row_stride, dt, dt_row_stride, out_dtype,
+                            (cudaStream_t)stream);
+}
+
+int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned, const float* coef,
+                 const float* scal, const double* grad_out, float grad_scale, void* dv, int64_t dv_row_stride,
+                 void* dt, int64_t dt_row_stride, int out_dtype, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  int rc = crossclr_bwd_accumulate(p, path, feat, coef, scal, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return crossclr_bwd_finish(p, path, feat, rnorm_owned, coef, scal, grad_out, grad_scale, dv, dv_row_stride, dt, dt_row_stride,
+                             out_dtype, workspace, stream);
 }
 
 size_t crossclr_maxmargin_workspace_bytes(int32_t batch) {

@@ -357,7 +357,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const uint32_t sempty_ldr0 = mapa_cluster(sempty_bar(0), 0), sempty_ldr1 = mapa_cluster(sempty_bar(1), 0);
       // un-swizzled K-major operand layout of a sub-tile: [16 column chunks of 8][128 rows][16 bytes]
       uint8_t* const p_pool = P.pool + ((size_t)prod * FLOW_NSLOT * 4 + sub * 2 + wg) * PTILE_BYTES + (size_t)r * 16;
-      float2* const cv_warp = cvw + (warp - EPI_WARP0) * 256;       // [tile parity][128], private to the warp
+      float* const cv_warp = reinterpret_cast<float*>(cvw + (warp - EPI_WARP0) * 256);   // [tile parity][64 column pairs][4]
       const float* const coef_col = coef + 2 * (int64_t)(wg * TM + lane);
       FlowProdWalk walk(P, prod);
       FlowTile tl, nx;
@@ -395,9 +395,13 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         const bool diag_tile = (bj.samp0 == bi.samp0);
         const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;   // row part of the logit scale
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
-        float2* cv = cv_warp + (t & 1) * TM;
+        float* cv = cv_warp + (t & 1) * (2 * TM);                  // per column pair: (q_j, q_j+1, w_j, w_j+1)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cv[32 * q + lane] = make_float2(qj[q], izj[q] * ks * qj[q]);   // q_j, q_j kappa sigma / Z_j
+        for (int q = 0; q < 4; ++q) {
+          const int col = 32 * q + lane;
+          cv[(col >> 1) * 4 + (col & 1)] = qj[q];                    // q_j
+          cv[(col >> 1) * 4 + (col & 1) + 2] = izj[q] * ks * qj[q];  // w_j = q_j kappa sigma / Z_j
+        }
         if (have_next) {                                             // next tile's column coefficients, a whole tile ahead
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -425,13 +429,18 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         uint8_t* const prow = p_pool + (size_t)slot * (4 * PTILE_BYTES);
         auto p_chunk = [&](const uint32_t (&v)[32], int c) {         // c: 32-column chunk of the warp's half (0..3)
           uint32_t packed[16];
-          const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+          const float4* cv4 = reinterpret_cast<const float4*>(cv) + c * 16;
+          const uint64_t k2 = pack2(k, k), ns2 = pack2(nshift_i, nshift_i), a2 = pack2(a_i, a_i);
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
-            const float4 cc = cv4[q >> 1];                         // (q_j, w_j) of columns q, q + 1
+            const float4 cc = cv4[q >> 1];                         // (q_j, q_j+1, w_j, w_j+1) of columns q, q + 1
             // P~ = 2^x (1/Z_g + 1/Z_j) kappa sigma q_g q_j,  x = (f_g . f_j) (k q_g) q_j - shift     (q_g dF_g = sum_j P~ f_j)
-            const float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]) * k, cc.x, nshift_i)) * fmaf(a_i, cc.x, cc.y);
-            const float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]) * k, cc.z, nshift_i)) * fmaf(a_i, cc.z, cc.w);
+            // on packed fp32 pairs: FMUL2, FFMA2 -> 2 x ex2 -> FFMA2, FMUL2 -> one fp16 pair
+            const uint64_t q01 = pack2(cc.x, cc.y);
+            const uint64_t x01 = ffma2(fmul2(pack2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), k2), q01, ns2);
+            float x0, x1, e0, e1;
+            unpack2(x01, x0, x1);
+            unpack2(fmul2(pack2(fast_exp2(x0), fast_exp2(x1)), ffma2(a2, q01, pack2(cc.z, cc.w))), e0, e1);
             __half2 h0 = __floats2half2_rn(e0, e1);
             packed[q >> 1] = *reinterpret_cast<uint32_t*>(&h0);
           }

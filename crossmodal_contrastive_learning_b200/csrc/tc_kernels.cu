@@ -32,17 +32,30 @@ namespace {
 //   warps 4-7 epilogue: tcgen05.ld (software pipelined) -> x = acc*k - shift -> ex2 -> thread-local row sums
 // ================================================================================================
 // 32 accumulator columns of one row -> exponentials summed into rs.  x = (f_g . f_j) * (k q_g) * q_j - shift with the column
-// scales q_j broadcast from the warp's shared-memory copy (16-byte loads, four columns each).
+// scales q_j broadcast from the warp's shared-memory copy (16-byte loads, four columns each); the arithmetic runs on packed
+// fp32 pairs (FMUL2 / FFMA2 / FADD2).
+__device__ __forceinline__ float ex2_of(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float kq, float nshift, const float4* __restrict__ qc,
                                               float (&rs)[4]) {
+  const uint64_t kq2 = pack2(kq, kq), ns2 = pack2(nshift, nshift);
+  uint64_t rs01 = pack2(rs[0], rs[1]), rs23 = pack2(rs[2], rs[3]);
 #pragma unroll
   for (int q = 0; q < 32; q += 4) {
     const float4 c = qc[q >> 2];
-    rs[0] += fast_exp2(fmaf(__uint_as_float(v[q + 0]) * kq, c.x, nshift));
-    rs[1] += fast_exp2(fmaf(__uint_as_float(v[q + 1]) * kq, c.y, nshift));
-    rs[2] += fast_exp2(fmaf(__uint_as_float(v[q + 2]) * kq, c.z, nshift));
-    rs[3] += fast_exp2(fmaf(__uint_as_float(v[q + 3]) * kq, c.w, nshift));
+    const uint64_t x01 = ffma2(fmul2(pack2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), kq2), pack2(c.x, c.y), ns2);
+    const uint64_t x23 = ffma2(fmul2(pack2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), kq2), pack2(c.z, c.w), ns2);
+    float x0, x1, x2, x3;
+    unpack2(x01, x0, x1);
+    unpack2(x23, x2, x3);
+    rs01 = fadd2(rs01, pack2(ex2_of(x0), ex2_of(x1)));
+    rs23 = fadd2(rs23, pack2(ex2_of(x2), ex2_of(x3)));
   }
+  unpack2(rs01, rs[0], rs[1]);
+  unpack2(rs23, rs[2], rs[3]);
 }
 
 // The 32-column chunk that holds the same-sample column (column r & 31 of the chunk): the masked intra-modal diagonal
@@ -73,6 +86,7 @@ __device__ __forceinline__ void fwd_diag_chunk(const uint32_t (&v)[32], float kq
 // its warps arrive (one lane each) on the leader's tempty barrier.
 // ================================================================================================
 
+constexpr int FWD_QSTAGES = 4;        // tiles of column scales in flight (shared-memory ring of the producer warp)
 constexpr int FWD2_THREADS = 640;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-19: epilogue
 
 // Tiles (row-block pair ib, column block jb) of a linear range, row-major.  Symmetric mode (single rank: the owned rows
@@ -98,14 +112,26 @@ struct FwdTileWalk {
 };
 
 // as fwd_sum_chunk, but leaves the exponentials in v (bit patterns) for the column sums
-__device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
+__device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float4* __restrict__ qc,
                                                    float (&rs)[4]) {
+  const uint64_t kq2 = pack2(kq, kq), ns2 = pack2(nshift, nshift);
+  uint64_t rs01 = pack2(rs[0], rs[1]), rs23 = pack2(rs[2], rs[3]);
 #pragma unroll
-  for (int q = 0; q < 32; ++q) {
-    const float e = fast_exp2(fmaf(__uint_as_float(v[q]) * kq, qc[q], nshift));
-    rs[q & 3] += e;
-    v[q] = __float_as_uint(e);
+  for (int q = 0; q < 32; q += 4) {
+    const float4 c = qc[q >> 2];
+    const uint64_t x01 = ffma2(fmul2(pack2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), kq2), pack2(c.x, c.y), ns2);
+    const uint64_t x23 = ffma2(fmul2(pack2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), kq2), pack2(c.z, c.w), ns2);
+    float x0, x1, x2, x3;
+    unpack2(x01, x0, x1);
+    unpack2(x23, x2, x3);
+    const float e0 = ex2_of(x0), e1 = ex2_of(x1), e2 = ex2_of(x2), e3 = ex2_of(x3);
+    rs01 = fadd2(rs01, pack2(e0, e1));
+    rs23 = fadd2(rs23, pack2(e2, e3));
+    v[q + 0] = __float_as_uint(e0); v[q + 1] = __float_as_uint(e1);
+    v[q + 2] = __float_as_uint(e2); v[q + 3] = __float_as_uint(e3);
   }
+  unpack2(rs01, rs[0], rs[1]);
+  unpack2(rs23, rs[2], rs[3]);
 }
 __device__ __forceinline__ void fwd_diag_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
                                                     bool same_mod, float diag_term, int r, int gi, int partner,
@@ -176,8 +202,11 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
   auto tempty_bar = [&](int b) { return a_full + 32u + 8u * b; };
   const uint32_t tmem_slot = a_full + 48u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  // column scales q_j: [16 epilogue warps][2 tile parities][64 columns], each warp's copy private to it
-  float* qv_all = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes - smem_u32(smem_raw)));
+  // column scales q_j of the tiles in flight: ring of FWD_QSTAGES x [256 columns], filled by the TMA producer warp one tile
+  // ahead (a gather from the rows' tails), read by the epilogue warps with broadcast 16-byte loads
+  float* q_ring = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes - smem_u32(smem_raw)));
+  auto qfull_bar = [&](int s) { return a_full + 64u + 8u * s; };
+  auto qempty_bar = [&](int s) { return a_full + 96u + 8u * s; };
   const uint32_t idesc_s = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,6 +220,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     for (int s = 0; s < num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32); }   // 16 warps x 2 CTAs
+    for (int s = 0; s < FWD_QSTAGES; ++s) { mbar_init(qfull_bar(s), 1); mbar_init(qempty_bar(s), 16); }   // 16 epilogue warps
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
@@ -207,9 +237,32 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     uint32_t a_cnt = 0;
     const uint32_t a_full_ldr = mapa_cluster(a_full, 0);
     FwdTileWalk w(t_begin, ncb, kSym);
+    // column scales of tile t + 1 are gathered (8 per lane) while tile t's chunks are issued, and published afterwards
+    float qn[8];
+    if (t_begin < t_end) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qn[i] = row_q(feat, g, w.jb * FWD_TN + 32 * i + lane);
+    }
+    uint32_t qt = 0;
+    auto publish_q = [&]() {
+      const uint32_t qs = qt % FWD_QSTAGES;
+      mbar_wait(qempty_bar(qs), ((qt / FWD_QSTAGES) & 1) ^ 1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q_ring[qs * FWD_TN + 32 * i + lane] = qn[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qfull_bar(qs));
+      ++qt;
+    };
+    if (t_begin < t_end) publish_q();
     for (int t = t_begin; t < t_end; ++t, w.next()) {
       const int ib = w.ib, jb = w.jb;
       const int row0 = g.row_begin + (2 * ib + (int)rank) * TM, col0 = jb * FWD_TN + (int)rank * TM;
+      if (t + 1 < t_end) {
+        FwdTileWalk wn = w;
+        wn.next();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qn[i] = row_q(feat, g, wn.jb * FWD_TN + 32 * i + lane);
+      }
       if (kResident && ib != cur_ib) {
         mbar_wait(a_empty, (a_cnt & 1) ^ 1);
         if (elect_one()) {
@@ -231,6 +284,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         __syncwarp();
         ring.advance();
       }
+      if (t + 1 < t_end) publish_q();
     }
   } else if (warp == 1 && rank == 0) {
     // MMA issuer (leader only)
@@ -284,7 +338,6 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     BlockSeg bi{0, 0};
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     float q_i = 1.f;
-    float* const qv_warp = qv_all + (warp - EPI_WARP0) * 128;
     const float k_diag_term = fast_exp2(-g.shift);
     const float nshift = -g.shift;
     const uint32_t tempty_ldr0 = mapa_cluster(tempty_bar(0), 0), tempty_ldr1 = mapa_cluster(tempty_bar(1), 0);
@@ -309,12 +362,12 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
       const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;      // row part of the logit scale
       const bool col_sums = kSym && jb != ib;                        // off-diagonal tile of the symmetric walk
       const int col_row0 = jb * FWD_TN + sl * 64;                    // stacked row of the slice's first column
-      float* const qv = qv_warp + (iter & 1) * 64;                   // this tile's column scales, fetched before the wait
-      qv[lane] = row_q(feat, g, col_row0 + lane);
-      qv[32 + lane] = row_q(feat, g, col_row0 + 32 + lane);
+      const uint32_t qs = iter % FWD_QSTAGES;
+      const float* const qv = q_ring + qs * FWD_TN + sl * 64;        // this slice's column scales
       w.next();
       if (w.ib != ib) { ib = w.ib; jb = w.jb; jseg = (jb * FWD_TN + half * TM) / g.bseg; joff = (jb * FWD_TN + half * TM) - jseg * g.bseg; }
       else { jb = w.jb; joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
+      mbar_wait(qfull_bar(qs), (iter / FWD_QSTAGES) & 1);
       const uint32_t buf = iter & 1;
       const uint32_t tb = lane_base + buf * FWD_TN;
       mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
@@ -336,17 +389,21 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
           else fwd_diag_chunk(vb, k, nshift, qv + 32, same_mod, k_diag_term, r, gi, stats, rs);
         } else {
           const int partner = row_partner(gi, g.bseg);
-          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk_keep(va, k, nshift, qv, rs);
+          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk_keep(va, k, nshift, reinterpret_cast<const float4*>(qv), rs);
           else fwd_diag_chunk_keep(va, k, nshift, qv, same_mod, k_diag_term, r, gi, partner, stats, rs);
-          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk_keep(vb, k, nshift, qv + 32, rs);
+          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk_keep(vb, k, nshift, reinterpret_cast<const float4*>(qv + 32), rs);
           else fwd_diag_chunk_keep(vb, k, nshift, qv + 32, same_mod, k_diag_term, r, gi, partner, stats, rs);
           // the mirrored tile (jb, ib) is never computed: its row sums are this tile's column sums
           float c0, c1;
-          warp_column_sums(va, vb, lane, c0, c1);
-          atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane)], c0);
-          atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane + 1)], c1);
+          if (!(exp_flags & 16)) {
+            warp_column_sums(va, vb, lane, c0, c1);
+            atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane)], c0);
+            atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane + 1)], c1);
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qempty_bar(qs));                      // this warp is done with the tile's column scales
     }
     if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
   }
@@ -633,10 +690,11 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restric
         const float ks = (same_mod ? g.w : 1.0f) * sigma;
         const uint32_t buf = p_cnt & 1;
         const uint32_t tbuf = lane_base + buf * BWD_TN;
-        float2* cv = cvec + buf * BWD_TN;
+        float* cv = reinterpret_cast<float*>(cvec + buf * BWD_TN);   // per column pair: (q_j, q_j+1, w_j, w_j+1)
         {
           const float qj = row_q(feat, g, col0 + r);
-          cv[r] = make_float2(qj, coef[2 * (int64_t)(col0 + r)] * ks * qj);   // column r: q_j, q_j kappa sigma / Z_j
+          cv[(r >> 1) * 4 + (r & 1)] = qj;                                          // q_j
+          cv[(r >> 1) * 4 + (r & 1) + 2] = coef[2 * (int64_t)(col0 + r)] * ks * qj;  // w_j = q_j kappa sigma / Z_j
         }
         const float a_i = iz_i * ks;
         named_bar_sync(1, EPI_THREADS);
@@ -650,13 +708,17 @@ bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restric
           tmem_ld_wait();
           if (c + 1 < BWD_TN / 32) tmem_ld32(tbuf + (c + 1) * 32, (c & 1) ? va : vb);
           uint32_t packed[16];
-          const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+          const float4* cv4 = reinterpret_cast<const float4*>(cv) + c * 16;
+          const uint64_t k2 = pack2(k, k), ns2 = pack2(nshift_i, nshift_i), a2 = pack2(a_i, a_i);
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
-            const float4 cc = cv4[q >> 1];                       // (q_j, w_j) of columns q, q + 1
-            // P~ = 2^x (1/Z_g + 1/Z_j) kappa sigma q_g q_j,  x = (f_g . f_j) (k q_g) q_j - shift
-            float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]) * k, cc.x, nshift_i)) * fmaf(a_i, cc.x, cc.y);
-            float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]) * k, cc.z, nshift_i)) * fmaf(a_i, cc.z, cc.w);
+            const float4 cc = cv4[q >> 1];                       // (q_j, q_j+1, w_j, w_j+1) of columns q, q + 1
+            // P~ = 2^x (1/Z_g + 1/Z_j) kappa sigma q_g q_j,  x = (f_g . f_j) (k q_g) q_j - shift; packed fp32 pairs
+            const uint64_t q01 = pack2(cc.x, cc.y);
+            const uint64_t x01 = ffma2(fmul2(pack2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), k2), q01, ns2);
+            float x0, x1, e0, e1;
+            unpack2(x01, x0, x1);
+            unpack2(fmul2(pack2(ex2_of(x0), ex2_of(x1)), ffma2(a2, q01, pack2(cc.z, cc.w))), e0, e1);
             if (diag_tile) {                                     // same-sample pair handled in grad_finish
               if (c * 32 + q + 0 == r) e0 = 0.f;
               if (c * 32 + q + 1 == r) e1 = 0.f;
@@ -910,7 +972,7 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       int cur_ib = -1, gi = 0;
       BlockSeg bi{0, 0};
       float iz_i = 0.f, q_i = 1.f, nshift_i = nshift;
-      float2* cv = cvec + wg * PAIR_TN;
+      float* cv = reinterpret_cast<float*>(cvec + wg * PAIR_TN);     // per column pair: (q_j, q_j+1, w_j, w_j+1)
       // column coefficients of this thread's two columns for the group's next tile, fetched one tile ahead
       float izj0 = 0.f, izj1 = 0.f, qj0 = 1.f, qj1 = 1.f;
       if (wg < n_tiles) {
@@ -934,8 +996,10 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         const BlockSeg bj0 = block_seg(j * PAIR_TN, g.bseg), bj1 = block_seg(j * PAIR_TN + TM, g.bseg);
         const float ks0 = ((bj0.mod == bi.mod) ? g.w : 1.0f) * sigma, ks1 = ((bj1.mod == bi.mod) ? g.w : 1.0f) * sigma;
-        cv[r] = make_float2(qj0, izj0 * ks0 * qj0);                // q_j, q_j kappa sigma / Z_j of the tile's 256 columns
-        cv[TM + r] = make_float2(qj1, izj1 * ks1 * qj1);
+        cv[(r >> 1) * 4 + (r & 1)] = qj0;                          // q_j, w_j = q_j kappa sigma / Z_j of the tile's 256 columns
+        cv[(r >> 1) * 4 + (r & 1) + 2] = izj0 * ks0 * qj0;
+        cv[((TM + r) >> 1) * 4 + (r & 1)] = qj1;
+        cv[((TM + r) >> 1) * 4 + (r & 1) + 2] = izj1 * ks1 * qj1;
         if (t + 2 < n_tiles) {
           const int jn = (u + 2) % ncb;
           izj0 = coef[2 * (int64_t)(jn * PAIR_TN + r)];
@@ -969,12 +1033,16 @@ bwd_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             if (c + 1 < 8) tmem_ld32(lane_base + (c + 1) * 32, (c & 1) ? va : vb);
             else { tc_fence_before(); mbar_arrive(sempty_bar(wg)); }   // whole S tile is in registers: free the buffer
             uint32_t packed[16];
-            const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+            const float4* cv4 = reinterpret_cast<const float4*>(cv) + c * 16;
+            const uint64_t k2 = pack2(k, k), ns2 = pack2(nshift_i, nshift_i), a2 = pack2(a_i, a_i);
 #pragma unroll
             for (int q = 0; q < 32; q += 2) {
-              const float4 cc = cv4[q >> 1];                         // (q_j, w_j) of columns q, q + 1
-              float e0 = fast_exp2(fmaf(__uint_as_float(v[q + 0]) * k, cc.x, nshift_i)) * fmaf(a_i, cc.x, cc.y);
-              float e1 = fast_exp2(fmaf(__uint_as_float(v[q + 1]) * k, cc.z, nshift_i)) * fmaf(a_i, cc.z, cc.w);
+              const float4 cc = cv4[q >> 1];                         // (q_j, q_j+1, w_j, w_j+1) of columns q, q + 1
+              const uint64_t q01 = pack2(cc.x, cc.y);
+              const uint64_t x01 = ffma2(fmul2(pack2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), k2), q01, ns2);
+              float x0, x1, e0, e1;
+              unpack2(x01, x0, x1);
+              unpack2(fmul2(pack2(ex2_of(x0), ex2_of(x1)), ffma2(a2, q01, pack2(cc.z, cc.w))), e0, e1);
               if (diag_tile) {                                     // same-sample pair handled in grad_finish
                 const int cbase = c4 * 32 + q;
                 if (cbase + 0 == r) e0 = 0.f;
@@ -1361,7 +1429,7 @@ static bool fwd_sym_enabled() {
   return v != 0;
 }
 
-constexpr int kFwdQvBytes = 16 * 2 * 64 * 4;      // per-warp column scales of the forward's 16 epilogue warps
+constexpr int kFwdQvBytes = FWD_QSTAGES * FWD_TN * 4;   // ring of per-tile column scales
 
 template <bool kResident, bool kSym>
 static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, float* stats, cudaStream_t st,

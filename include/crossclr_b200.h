@@ -160,6 +160,21 @@ CROSSCLR_API int crossclr_bwd(const crossclr_problem_t* p, int path, const void*
                  int64_t dv_row_stride, void* dt, int64_t dt_row_stride, int out_dtype, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/*
+ * The two stages of crossclr_bwd, callable on their own (crossclr_bwd == accumulate, then finish, on one stream):
+ *   crossclr_bwd_accumulate  the similarity / gradient kernel: workspace[0 .. row_count*dim) (fp32) = for every owned row g
+ *                            q_g sigma sum_j P_gj Fhat_j without the positive-pair term -- the O(B^2 D) part, the kernel
+ *                            the roofline is quoted on (bench.py times this call alone);
+ *   crossclr_bwd_finish      positive-pair term, F.normalize backward, upstream gradient, cast -- O(B D).
+ * Replaces: the autograd backward of trainer/loss.py:83-112 (accumulate) and of :79-80, :114 (finish).
+ */
+CROSSCLR_API int crossclr_bwd_accumulate(const crossclr_problem_t* p, int path, const void* feat, const float* coef,
+                            const float* scal, void* workspace, size_t workspace_bytes, void* stream);
+CROSSCLR_API int crossclr_bwd_finish(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned,
+                        const float* coef, const float* scal, const double* grad_out, float grad_scale, void* dv,
+                        int64_t dv_row_stride, void* dt, int64_t dt_row_stride, int out_dtype, const void* workspace,
+                        void* stream);
+
 /* The constant log2-domain shift used by fwd/bwd for this problem: max(0, log2e*max(1,|w|)/tau - 96). */
 CROSSCLR_API float crossclr_shift(const crossclr_problem_t* p);
 
