@@ -416,6 +416,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: the bench prints ONE line
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 

@@ -116,10 +116,13 @@ int64_t crossclr_feature_pitch(int path, int32_t dim) {
   return CROSSCLR_EINVAL;
 }
 
+// workspace of the backward: [dfhat | dfhat of the late consumers | flag word block | kernel scratch]
+static size_t ws_flag_offset(const crossclr_problem_t* p) { return 2 * dfhat_bytes(p); }
+static size_t ws_scratch_offset(const crossclr_problem_t* p) { return 2 * dfhat_bytes(p) + 256; }
 static size_t workspace_bytes(const crossclr_problem_t* p, int path) {
   if (!path_is_tc(path)) return dfhat_bytes(p);
   // + P-tile scratch of the role-specialised backward kernels (cluster rings, or the dataflow kernel's pool + control words)
-  return dfhat_bytes(p) + std::max(bwd_pair_scratch_bytes(), bwd_flow_scratch_bytes(p->nseg * p->bseg, p->row_count));
+  return ws_scratch_offset(p) + std::max(bwd_pair_scratch_bytes(), bwd_flow_scratch_bytes(p->nseg * p->bseg, p->row_count));
 }
 
 size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {
@@ -220,7 +223,13 @@ static int bwd_accumulate(const crossclr_problem_t* p, int path, const Geometry&
   if (path_is_tc(path)) {
     CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
                p->bseg, p->dim);
-    return launch_bwd_tc(g, feat, coef, scal, dfhat, (char*)workspace + dfhat_bytes(p), st);
+    bool two = false;
+    int rc = launch_bwd_tc(g, feat, coef, scal, dfhat, (float*)((char*)workspace + dfhat_bytes(p)), &two,
+                           (char*)workspace + ws_scratch_offset(p), st);
+    if (rc) return rc;
+    // the finish stage may run from another call (crossclr_bwd_finish): leave word 0 of the flag block = partial count - 1
+    CC_CHECK_CUDA(cudaMemsetAsync((char*)workspace + ws_flag_offset(p), two ? 1 : 0, 4, st));
+    return CROSSCLR_OK;
   }
   CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_bwd: path must be SIMT or TC (got %d)", path);
   return launch_bwd_simt(g, (const float*)feat, coef, dfhat, st);
@@ -243,9 +252,11 @@ int crossclr_bwd_finish(const crossclr_problem_t* p, int path, const void* feat,
   CC_REQUIRE(dv_row_stride >= p->dim && dt_row_stride >= p->dim, "crossclr_bwd_finish: output row stride < dim");
   CC_REQUIRE(path == CROSSCLR_PATH_SIMT || path_is_tc(path), "crossclr_bwd_finish: path must be SIMT or TC (got %d)", path);
   const bool tc = path_is_tc(path);
+  // TC paths: the second partial (late consumers of the dataflow kernel) counts iff the flag word says so (read on device)
+  const float* dfhat2 = tc ? (const float*)((const char*)workspace + dfhat_bytes(p)) : nullptr;
   return launch_grad_finish(make_geometry(p, path), feat, tc ? CROSSCLR_F16 : CROSSCLR_F32, rnorm_owned, coef, scal, tc, grad_out,
                             grad_scale, (const float*)workspace, dv, dv_row_stride, dt, dt_row_stride, out_dtype,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, dfhat2);
 }
 
 int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned, const float* coef,

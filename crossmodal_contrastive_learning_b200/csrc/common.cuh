@@ -150,21 +150,23 @@ int launch_finalize(const Geometry& g, const float* stats, float* coef, double* 
 int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm_owned,
                        const float* coef, const float* scal, bool use_sigma, const double* grad_out,
                        float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,
-                       int64_t dt_stride, int out_dtype, cudaStream_t st);
+                       int64_t dt_stride, int out_dtype, cudaStream_t st, const float* dfhat2 = nullptr);
 // tc_kernels.cu
 // fused finalize (single rank, all rows owned): the last CTA of the forward writes coef / loss / scal; `ticket` must be 0
 struct FwdFinalize { float* coef; double* loss; float* scal; unsigned int* ticket; };
 bool fwd_tc_can_finalize(const Geometry& g);
 int launch_fwd_tc(const Geometry& g, const void* feat_f16, float* stats, cudaStream_t st, const FwdFinalize* fin = nullptr);
+// *two_partials: the result is dfhat + dfhat_late (grad_finish adds them)
 int launch_bwd_tc(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
-                  void* scratch, cudaStream_t st);
+                  float* dfhat_late, bool* two_partials, void* scratch, cudaStream_t st);
 size_t bwd_pair_scratch_bytes();   // global-memory P-tile rings of the paired backward (D <= 512)
 const char* bwd_tc_kernel_name(const Geometry& g);   // the backward kernel launch_bwd_tc picks for this problem
 // flow_kernels.cu: dataflow backward (producer pairs -> P-tile pool -> consumer pairs), D <= 512
 size_t bwd_flow_scratch_bytes(int rows, int row_count);
 bool bwd_flow_applies(const Geometry& g);
+// dfhat_late: a second [row_count][dim] partial that the kernel fills when its plan uses late consumers (*used_late)
 int launch_bwd_flow(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
-                    void* scratch, cudaStream_t st);
+                    float* dfhat_late, bool* used_late, void* scratch, cudaStream_t st);
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k);
 
 // maxmargin.cu (MaxMargin_coot, trainer/loss.py:17-41)

@@ -46,12 +46,16 @@ struct FlowParams {
   int parts;             // consumers per row block: consumer (I, part) takes the other-blocks x with x % parts == part
   int cnt;               // tile products per consumer ring = nb / parts
   int sym;               // symmetric schedule
+  int d0;                // symmetric schedule: tiles of cyclic distance >= d0 go to the LATE rings (consumed by producer pairs
+                         // once their own production is over); nb + 1 = no late rings
+  int cnt_main, cnt_late;   // tile products per main ring (= cnt without late rings) / per late ring
   int nk;                // dim / 64
   int s_stages;          // producer B ring depth
-  uint32_t* ring;        // [nrb * parts][cnt] descriptors, zero = not yet published
-  uint32_t* tail;        // [nrb * parts]
+  uint32_t* ring;        // [nrb * parts (+ nb late)][cnt] descriptors, zero = not yet published
+  uint32_t* tail;        // [nrb * parts (+ nb late)]
   uint32_t* release;     // [n_s][FLOW_NSLOT] consumer releases per pool slot (monotonic)
   uint8_t* pool;         // [n_s][FLOW_NSLOT][4][32 KiB]
+  float* dfhat_late;     // [row_count][dim]: partial dF of the late consumers (plain stores; grad_finish adds it)
   unsigned long long* trace;   // debug timeline (CROSSCLR_FLOW_TRACE), or nullptr
   int exp;               // perf experiments (CROSSCLR_FLOW_EXP; results are wrong): 1 consumers run on made-up descriptors,
                          // 2 producers neither wait for credits nor publish, 4 producers idle, 8 consumers idle
@@ -109,48 +113,69 @@ struct FlowTile {
   int ring_d, ring_t;    // consumer ring of the direct product, of the transposed product (-1: none)
 };
 
-// The ordered list of S tiles of producer `s` over all waves (every producer warp walks its own copy).
+// The ordered list of S tiles of producer `s` over all waves (every producer warp walks its own copy).  Symmetric schedule
+// with late rings: the producer's chunk of the (row block, cyclic distance) list is walked twice, first the tiles of the
+// main rings (d < d0), then its late tiles (d >= d0) -- fewer than FLOW_NSLOT, so the slots they hold until the late
+// consumers start are never needed again by this producer.
 struct FlowProdWalk {
-  int n_g, n_s, nb, parts, cnt, sym, s, nrings, nwaves;
-  int wave, k, k_end, c0;
+  int n_g, n_s, nb, parts, cnt, sym, s, nrings, nwaves, d0;
+  int wave, k, k0, k_end, c0, pass;
   int I, d;                                   // symmetric schedule: row block, cyclic distance
   __device__ FlowProdWalk(const FlowParams& P, int s_)
       : n_g(P.n_g), n_s(P.n_s), nb(P.nb), parts(P.parts), cnt(P.cnt), sym(P.sym), s(s_), nrings(P.nrb * P.parts),
-        wave(-1), k(0), k_end(0), c0(0), I(0), d(0) {
+        wave(-1), k(0), k0(0), k_end(0), c0(0), pass(1), I(0), d(0) {
     nwaves = (nrings + n_g - 1) / n_g;
+    d0 = P.d0;
   }
   __device__ __forceinline__ int nd(int i) const { return (nb & 1) ? (nb + 1) / 2 : (i < nb / 2 ? nb / 2 + 1 : nb / 2); }
+  __device__ __forceinline__ void seek(int kk) {      // symmetric schedule: (I, d) of linear tile index kk
+    I = 0;
+    int rem = kk;
+    while (I < nb && rem >= nd(I)) { rem -= nd(I); ++I; }
+    d = rem;
+  }
   __device__ bool next(FlowTile& t) {
-    while (k >= k_end) {
-      if (++wave >= nwaves) return false;
-      c0 = wave * n_g;
-      const int nr = min(n_g, nrings - c0);
-      const long long T = sym ? (long long)nb * (nb + 1) / 2 : (long long)nr * cnt;
-      k = (int)((long long)s * T / n_s);
-      k_end = (int)((long long)(s + 1) * T / n_s);
-      if (sym) {
-        I = 0;
-        int rem = k;
-        while (I < nb && rem >= nd(I)) { rem -= nd(I); ++I; }
-        d = rem;
+    for (;;) {
+      if (k >= k_end) {
+        if (sym && pass == 0 && d0 <= nb) {             // second pass over the chunk: the late tiles
+          pass = 1; k = k0; seek(k);
+          continue;
+        }
+        if (++wave >= nwaves) return false;
+        c0 = wave * n_g;
+        const int nr = min(n_g, nrings - c0);
+        const long long T = sym ? (long long)nb * (nb + 1) / 2 : (long long)nr * cnt;
+        k0 = k = (int)((long long)s * T / n_s);
+        k_end = (int)((long long)(s + 1) * T / n_s);
+        pass = 0;
+        if (sym) seek(k);
+        continue;
       }
-    }
-    if (!sym) {
-      const int c = c0 + k / cnt;
-      t.I = c / parts;
-      t.J = (c - t.I * parts) + parts * (k % cnt);
-      t.ring_d = c;
-      t.ring_t = -1;
-    } else {
-      int J = I + d;
-      if (J >= nb) J -= nb;
-      t.I = I; t.J = J;
-      t.ring_d = I * parts + (J % parts);
-      t.ring_t = d ? J * parts + (I % parts) : -1;
+      if (!sym) {
+        const int c = c0 + k / cnt;
+        t.I = c / parts;
+        t.J = (c - t.I * parts) + parts * (k % cnt);
+        t.ring_d = c;
+        t.ring_t = -1;
+        ++k;
+        return true;
+      }
+      const int Ic = I, dc = d;
       if (++d == nd(I)) { d = 0; ++I; }
+      ++k;
+      if ((dc >= d0) != (pass == 1)) continue;          // not this pass's kind
+      int J = Ic + dc;
+      if (J >= nb) J -= nb;
+      t.I = Ic; t.J = J;
+      if (dc >= d0) {                                   // late tile: both products go to the rows' late rings (parts == 1)
+        t.ring_d = nrings + Ic;
+        t.ring_t = nrings + J;
+      } else {
+        t.ring_d = Ic * parts + (J % parts);
+        t.ring_t = dc ? J * parts + (Ic % parts) : -1;
+      }
+      return true;
     }
-    ++k;
-    return true;
   }
 };
 
@@ -158,6 +183,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1)
 bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64,
                 const __grid_constant__ CUtensorMap tmap_p, const uint8_t* __restrict__ feat, Geometry g,
                 const float* __restrict__ coef, const float* __restrict__ scal, float* __restrict__ dfhat, FlowParams P) {
+  float* const dfhat_late = P.dfhat_late;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
@@ -169,13 +195,16 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   auto staged_bar = [&](int b) { return base + 240u + 8u * b; };     // producer: the CTA's two sub-tiles of a pool tile are stored
   auto pempty_bar = [&](int b) { return base + 304u + 8u * b; };     // producer: pool slot released by its consumer(s)
   auto pub_bar = [&](int b) { return base + 368u + 8u * b; };        // producer leader: the peer's half is fenced
-  auto pbfull_bar = [&](int b) { return base + 432u + 8u * b; };     // consumer leader: both CTAs' P sub-tiles landed (TMA)
-  auto pbempty_bar = [&](int b) { return base + 456u + 8u * b; };    // consumer: smem P buffer consumed (multicast commit)
-  auto dqfull_bar = [&](int b) { return base + 480u + 8u * b; };     // consumer: descriptor b of the local queue is valid
-  const uint32_t acc_full = base + 544u, acc_empty = base + 552u;
-  const uint32_t tmem_slot = base + 560u;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 560);
-  volatile uint32_t* dq = reinterpret_cast<volatile uint32_t*>(smem_raw + 576);   // consumer: [FLOW_DQ] descriptor words
+  const uint32_t tmem_slot = base + 432u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + 432);
+  // consumer roles: their own barrier region, untouched by the producer roles (a producer pair turns consumer at the end)
+  auto cfull_bar = [&](int s) { return base + 640u + 8u * s; };      // dF operand ring (FLOW_GGROUPS)
+  auto cempty_bar = [&](int s) { return base + 672u + 8u * s; };
+  auto pbfull_bar = [&](int b) { return base + 704u + 8u * b; };     // consumer leader: both CTAs' P sub-tiles landed (TMA)
+  auto pbempty_bar = [&](int b) { return base + 728u + 8u * b; };    // consumer: smem P buffer consumed (multicast commit)
+  auto dqfull_bar = [&](int b) { return base + 752u + 8u * b; };     // consumer: descriptor b of the local queue is valid
+  const uint32_t acc_full = base + 816u, acc_empty = base + 824u;
+  volatile uint32_t* dq = reinterpret_cast<volatile uint32_t*>(smem_raw + 832);   // consumer: [FLOW_DQ] descriptor words
   float2* cvw = reinterpret_cast<float2*>(smem_raw + 1024);         // producer: [8 epilogue warps][2 tile parities][128] (q_j, w_j)
   const uint32_t idesc_s = make_idesc_f16(256, 256, 0, 0, 0, 0);
 
@@ -198,6 +227,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(sempty_bar(b), 16); }    // 8 warps x 2 CTAs
     for (int b = 0; b < FLOW_NSLOT; ++b) { mbar_init(staged_bar(b), 8); mbar_init(pempty_bar(b), 1); mbar_init(pub_bar(b), 1); }
+    for (int s = 0; s < FLOW_GGROUPS; ++s) { mbar_init(cfull_bar(s), 1); mbar_init(cempty_bar(s), 1); }
     for (int b = 0; b < FLOW_PBUF; ++b) { mbar_init(pbfull_bar(b), 1); mbar_init(pbempty_bar(b), 1); }
     for (int b = 0; b < FLOW_DQ; ++b) mbar_init(dqfull_bar(b), 1);
     mbar_init(acc_full, 1); mbar_init(acc_empty, 16);                                             // 8 warps x 2 CTAs
@@ -210,9 +240,175 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if ((is_prod && (P.exp & 4)) || (!is_prod && (P.exp & 8))) {
-    // perf experiment: this role idles
-  } else if (is_prod) {
+  const int nrings_main = P.nrb * P.parts;
+  // The consumer roles of a pair for the rings c_first, c_first + c_stride, ... < c_end (late: rings of the late set).
+  auto consumer_roles = [&](int c_first, int c_stride, int c_end, bool late) {
+    const uint32_t p_tiles = base + 1024;
+    const uint32_t ring_base = p_tiles + FLOW_PBUF * PTILE_BYTES;
+    const int nbox = g.dim / 128;                      // own [64 j][64 d] boxes per 64-row group: half of each MMA's N
+    const uint32_t group_bytes = (uint32_t)nbox * GBOX_BYTES;
+    const int nmma = (g.dim + 255) / 256;              // MMAs per K = 16 step: N = 256 each (last one 128 if D % 256)
+    const int cnt_c = late ? P.cnt_late : P.cnt_main;
+    if (warp == 0) {
+      // TMA producer of the dF B operand: rows of the other block as [64 j][64 d] boxes, this CTA's half of every MMA's N
+      Ring ring(FLOW_GGROUPS);
+      uint32_t i = 0;
+      for (int c = c_first; c < c_end; c += c_stride) {
+        for (int p = 0; p < cnt_c; ++p, ++i) {
+          mbar_wait(dqfull_bar(i % FLOW_DQ), (i / FLOW_DQ) & 1);
+          const uint32_t e = dq[i % FLOW_DQ];
+          const int other = (int)(e & 0xFFFFFu);
+          for (int a = 0; a < 2; ++a) {
+            for (int kh = 0; kh < 2; ++kh) {                          // 64-row halves of the K = 128 rows of a sub-tile
+              mbar_wait(cempty_bar(ring.stage), ring.phase ^ 1);
+              if (elect_one()) {
+                const uint32_t st = ring_base + ring.stage * group_bytes;
+                const uint32_t full_ldr = mapa_cluster(cfull_bar(ring.stage), 0);
+                if (sub == 0) mbar_arrive_expect_tx(cfull_bar(ring.stage), 2 * group_bytes);
+                for (int q = 0; q < nbox; ++q) {
+                  const int m = q >> 1;                               // MMA index; its N = nm, this CTA's half = nm / 2
+                  const int nm = min(256, g.dim - m * 256);
+                  const int d0 = m * 256 + (int)sub * (nm >> 1) + (q & 1) * 64;
+                  tma_load_2d_2sm(st + q * GBOX_BYTES, &tmap64, full_ldr, d0, other * FLOW_TN + a * TM + kh * 64);
+                }
+              }
+              __syncwarp();
+              ring.advance();
+            }
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // dispatcher + P loader: next descriptor of the ring (arrival order) -> local queue -> this CTA's two sub-tiles
+      uint32_t i = 0, th = 0;
+      unsigned long long waited = 0;
+      for (int c = c_first; c < c_end; c += c_stride) {
+        for (int p = 0; p < cnt_c; ++p, ++i) {
+          if (lane == 0) {
+            const unsigned long long tw0 = (pair_stamp && !late) ? global_ns() : 0;
+            if ((pair == 0 && !late) && sub == 0) TR(1, i, 0);
+            const uint32_t e = (P.exp & 1) ? flow_desc((int)((i + pair) % (uint32_t)P.n_s), (int)(i & 7), (int)((i + pair) % (uint32_t)P.nb), (i & 1) != 0)
+                                           : poll_descriptor(P.ring + (size_t)c * P.cnt + p);
+            if ((pair == 0 && !late) && sub == 0) TR(1, i, 1);
+            if (pair_stamp && !late && sub == 0) {
+              const unsigned long long tw1 = global_ns();
+              if (i == 0) pair_stamp[0] = tw1; else waited += tw1 - tw0;
+              pair_stamp[2] = waited;
+            }
+            dq[i % FLOW_DQ] = e;
+            mbar_arrive(dqfull_bar(i % FLOW_DQ));
+            fence_proxy_async_global();                              // the tile's generic-proxy stores -> our TMA reads
+            const bool trans = (e & 0x40000000u) != 0;
+            const int tile = (int)((e >> 20) & 0x3FFu);              // producer * FLOW_NSLOT + slot
+            for (int a = 0; a < 2; ++a, ++th) {
+              const uint32_t pb = th % FLOW_PBUF, puse = th / FLOW_PBUF;
+              mbar_wait(pbempty_bar(pb), (puse & 1) ^ 1);
+              if (sub == 0) mbar_arrive_expect_tx(pbfull_bar(pb), 2 * PTILE_BYTES);
+              const int st_idx = trans ? (a * 2 + (int)sub) : ((int)sub * 2 + a);
+              tma_load_2d_2sm(p_tiles + pb * PTILE_BYTES, &tmap_p, mapa_cluster(pbfull_bar(pb), 0), 0,
+                              (tile * 4 + st_idx) * 256);
+            }
+            if ((pair == 0 && !late) && sub == 0) TR(1, i, 2);
+          }
+          __syncwarp();
+        }
+      }
+    } else if (warp == 1 && sub == 0) {
+      Ring ring(FLOW_GGROUPS);
+      uint32_t i = 0, th = 0, seg_iter = 0;
+      for (int c = c_first; c < c_end; c += c_stride) {
+        mbar_wait_cluster(acc_empty, (seg_iter & 1) ^ 1);   // both CTAs' drain warps have emptied the previous sweep
+        tc_fence_after();
+        for (int p = 0; p < cnt_c; ++p, ++i) {
+          mbar_wait(dqfull_bar(i % FLOW_DQ), (i / FLOW_DQ) & 1);
+          const uint32_t e = dq[i % FLOW_DQ];
+          const bool trans = (e & 0x40000000u) != 0;
+          for (int a = 0; a < 2; ++a, ++th) {
+            const uint32_t pb = th % FLOW_PBUF, puse = th / FLOW_PBUF;
+            if ((pair == 0 && !late) && lane == 0 && a == 0) TR(1, i, 3);
+            mbar_wait(pbfull_bar(pb), puse & 1);              // both CTAs' P sub-tiles have landed in shared memory (TMA)
+            if ((pair == 0 && !late) && lane == 0) TR(1, i, 4 + a);
+            tc_fence_after();
+            if (a == 1 && elect_one())                        // both sub-tiles of the pool tile are on chip: slot released
+              red_relaxed_gpu_add_u32(P.release + ((e >> 20) & 0x3FFu), 1u);
+            const uint32_t p_tile = p_tiles + pb * PTILE_BYTES;
+            for (int kh = 0; kh < 2; ++kh) {
+              mbar_wait(cfull_bar(ring.stage), ring.phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t st = ring_base + ring.stage * group_bytes;
+                for (int m = 0; m < nmma; ++m) {
+                  const int nm = min(256, g.dim - m * 256);
+                  const uint32_t idesc = make_idesc_f16(256, nm, 0, 0, trans ? 1 : 0, 1);
+#pragma unroll
+                  for (int k16 = 0; k16 < 4; ++k16) {
+                    // direct:     A = P[:, 64 kh + 16 k16 .. +16) K-major: column chunks 8 kh + 2 k16 and the next one (2048 B
+                    //             apart), 8-row groups 128 B apart
+                    // transposed: A = P^T: M = the sub-tile's 128 columns (16-byte chunks 2048 B apart), K = its rows
+                    //             64 kh + 16 k16 .. +16 (8-row groups 128 B apart): the same bytes read MN-major
+                    // B = Fhat rows 64 kh + 16 k16 .. +16 of this CTA's boxes 2m, 2m + 1, MN-major
+                    const uint64_t ad = trans ? make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * 128, 128, TM * 16)
+                                              : make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * (TM * 16), TM * 16, 128);
+                    const uint64_t bd = make_smem_desc_sw128(st + 2 * m * GBOX_BYTES + k16 * 2048, 1024, GBOX_BYTES);
+                    umma_ss_2sm(tmem_base + m * 256, ad, bd, idesc, (p > 0 || a > 0 || kh > 0 || k16 > 0) ? 1u : 0u);
+                  }
+                }
+                umma_commit_2sm(cempty_bar(ring.stage), kMaskPair);
+              }
+              __syncwarp();
+              ring.advance();
+            }
+            if (elect_one()) umma_commit_2sm(pbempty_bar(pb), kMaskPair);
+            if ((pair == 0 && !late) && lane == 0 && a == 1) TR(1, i, 6);
+            __syncwarp();
+          }
+        }
+        if (elect_one()) umma_commit_2sm(acc_full, kMaskPair);
+        __syncwarp();
+        ++seg_iter;
+        if (pair_stamp && lane == 0) pair_stamp[late ? 3 : 1] = global_ns();
+      }
+    } else if (warp >= EPI_WARP0) {
+      // drain: dF of the sweep -> dfhat (fp32, still scaled by sigma; grad_finish divides it out)
+      const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;     // wg: which 256-column half of D
+      const int r = quadw * 32 + lane;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16);
+      const uint32_t acc_empty_ldr = mapa_cluster(acc_empty, 0);
+      const bool whole = P.parts == 1;      // one main (and one late) consumer per row block: plain stores
+      uint32_t seg_iter = 0;
+      for (int c = c_first; c < c_end; c += c_stride, ++seg_iter) {
+        const int I = late ? c - nrings_main : c / P.parts;
+        mbar_wait(acc_full, seg_iter & 1);
+        tc_fence_after();
+        float* out = (late ? dfhat_late : dfhat) + ((int64_t)I * FLOW_TN + (int)sub * TM + r) * g.dim;
+        const int c_end = min(g.dim, wg * 256 + 256) / 32;
+#pragma unroll 1
+        for (int cc = wg * 8; cc < c_end; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + cc * 32, v);
+          tmem_ld_wait();
+          if (whole) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              *reinterpret_cast<float4*>(out + cc * 32 + q) =
+                  make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
+                              __uint_as_float(v[q + 3]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + cc * 32 + q), "f"(__uint_as_float(v[q])),
+                           "f"(__uint_as_float(v[q + 1])), "f"(__uint_as_float(v[q + 2])), "f"(__uint_as_float(v[q + 3]))
+                           : "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_ldr);
+      }
+    }
+  };
+
+  if (is_prod && !(P.exp & 4)) {
     // =========================================================================== producer pair
     const uint32_t a_region = data;
     const uint32_t ring_base = data + nk * CHUNK_BYTES;
@@ -424,7 +620,6 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           if (t == 0) pair_stamp[0] = tw1;
           pair_stamp[2] += tw1 - tw0;
           pair_stamp[1] = tw1;
-          pair_stamp[3] = t + 1;
         }
         uint8_t* const prow = p_pool + (size_t)slot * (4 * PTILE_BYTES);
         auto p_chunk = [&](const uint32_t (&v)[32], int c) {         // c: 32-column chunk of the warp's half (0..3)
@@ -491,171 +686,17 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         have = have_next;
       }
     }
-  } else {
-    // =========================================================================== consumer pair
-    const uint32_t p_tiles = data;
-    const uint32_t ring_base = data + FLOW_PBUF * PTILE_BYTES;
-    const int nbox = g.dim / 128;                      // own [64 j][64 d] boxes per 64-row group: half of each MMA's N
-    const uint32_t group_bytes = (uint32_t)nbox * GBOX_BYTES;
-    const int nmma = (g.dim + 255) / 256;              // MMAs per K = 16 step: N = 256 each (last one 128 if D % 256)
-    const int nrings = P.nrb * P.parts;
-    if (warp == 0) {
-      // TMA producer of the dF B operand: rows of the other block as [64 j][64 d] boxes, this CTA's half of every MMA's N
-      Ring ring(FLOW_GGROUPS);
-      uint32_t i = 0;
-      for (int c = pair; c < nrings; c += P.n_g) {
-        for (int p = 0; p < P.cnt; ++p, ++i) {
-          mbar_wait(dqfull_bar(i % FLOW_DQ), (i / FLOW_DQ) & 1);
-          const uint32_t e = dq[i % FLOW_DQ];
-          const int other = (int)(e & 0xFFFFFu);
-          for (int a = 0; a < 2; ++a) {
-            for (int kh = 0; kh < 2; ++kh) {                          // 64-row halves of the K = 128 rows of a sub-tile
-              mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-              if (elect_one()) {
-                const uint32_t st = ring_base + ring.stage * group_bytes;
-                const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), 0);
-                if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * group_bytes);
-                for (int q = 0; q < nbox; ++q) {
-                  const int m = q >> 1;                               // MMA index; its N = nm, this CTA's half = nm / 2
-                  const int nm = min(256, g.dim - m * 256);
-                  const int d0 = m * 256 + (int)sub * (nm >> 1) + (q & 1) * 64;
-                  tma_load_2d_2sm(st + q * GBOX_BYTES, &tmap64, full_ldr, d0, other * FLOW_TN + a * TM + kh * 64);
-                }
-              }
-              __syncwarp();
-              ring.advance();
-            }
-          }
-        }
-      }
-    } else if (warp == 2) {
-      // dispatcher + P loader: next descriptor of the ring (arrival order) -> local queue -> this CTA's two sub-tiles
-      uint32_t i = 0, th = 0;
-      unsigned long long waited = 0;
-      for (int c = pair; c < nrings; c += P.n_g) {
-        for (int p = 0; p < P.cnt; ++p, ++i) {
-          if (lane == 0) {
-            const unsigned long long tw0 = pair_stamp ? global_ns() : 0;
-            if (pair == 0 && sub == 0) TR(1, i, 0);
-            const uint32_t e = (P.exp & 1) ? flow_desc((int)((i + pair) % (uint32_t)P.n_s), (int)(i & 7), (int)((i + pair) % (uint32_t)P.nb), (i & 1) != 0)
-                                           : poll_descriptor(P.ring + (size_t)c * P.cnt + p);
-            if (pair == 0 && sub == 0) TR(1, i, 1);
-            if (pair_stamp && sub == 0) {
-              const unsigned long long tw1 = global_ns();
-              if (i == 0) pair_stamp[0] = tw1; else waited += tw1 - tw0;
-              pair_stamp[2] = waited;
-            }
-            dq[i % FLOW_DQ] = e;
-            mbar_arrive(dqfull_bar(i % FLOW_DQ));
-            fence_proxy_async_global();                              // the tile's generic-proxy stores -> our TMA reads
-            const bool trans = (e & 0x40000000u) != 0;
-            const int tile = (int)((e >> 20) & 0x3FFu);              // producer * FLOW_NSLOT + slot
-            for (int a = 0; a < 2; ++a, ++th) {
-              const uint32_t pb = th % FLOW_PBUF, puse = th / FLOW_PBUF;
-              mbar_wait(pbempty_bar(pb), (puse & 1) ^ 1);
-              if (sub == 0) mbar_arrive_expect_tx(pbfull_bar(pb), 2 * PTILE_BYTES);
-              const int st_idx = trans ? (a * 2 + (int)sub) : ((int)sub * 2 + a);
-              tma_load_2d_2sm(p_tiles + pb * PTILE_BYTES, &tmap_p, mapa_cluster(pbfull_bar(pb), 0), 0,
-                              (tile * 4 + st_idx) * 256);
-            }
-            if (pair == 0 && sub == 0) TR(1, i, 2);
-          }
-          __syncwarp();
-        }
-      }
-    } else if (warp == 1 && sub == 0) {
-      Ring ring(FLOW_GGROUPS);
-      uint32_t i = 0, th = 0, seg_iter = 0;
-      for (int c = pair; c < nrings; c += P.n_g) {
-        mbar_wait_cluster(acc_empty, (seg_iter & 1) ^ 1);   // both CTAs' drain warps have emptied the previous sweep
-        tc_fence_after();
-        for (int p = 0; p < P.cnt; ++p, ++i) {
-          mbar_wait(dqfull_bar(i % FLOW_DQ), (i / FLOW_DQ) & 1);
-          const uint32_t e = dq[i % FLOW_DQ];
-          const bool trans = (e & 0x40000000u) != 0;
-          for (int a = 0; a < 2; ++a, ++th) {
-            const uint32_t pb = th % FLOW_PBUF, puse = th / FLOW_PBUF;
-            if (pair == 0 && lane == 0 && a == 0) TR(1, i, 3);
-            mbar_wait(pbfull_bar(pb), puse & 1);              // both CTAs' P sub-tiles have landed in shared memory (TMA)
-            if (pair == 0 && lane == 0) TR(1, i, 4 + a);
-            tc_fence_after();
-            if (a == 1 && elect_one())                        // both sub-tiles of the pool tile are on chip: slot released
-              red_relaxed_gpu_add_u32(P.release + ((e >> 20) & 0x3FFu), 1u);
-            const uint32_t p_tile = p_tiles + pb * PTILE_BYTES;
-            for (int kh = 0; kh < 2; ++kh) {
-              mbar_wait(full_bar(ring.stage), ring.phase);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint32_t st = ring_base + ring.stage * group_bytes;
-                for (int m = 0; m < nmma; ++m) {
-                  const int nm = min(256, g.dim - m * 256);
-                  const uint32_t idesc = make_idesc_f16(256, nm, 0, 0, trans ? 1 : 0, 1);
-#pragma unroll
-                  for (int k16 = 0; k16 < 4; ++k16) {
-                    // direct:     A = P[:, 64 kh + 16 k16 .. +16) K-major: column chunks 8 kh + 2 k16 and the next one (2048 B
-                    //             apart), 8-row groups 128 B apart
-                    // transposed: A = P^T: M = the sub-tile's 128 columns (16-byte chunks 2048 B apart), K = its rows
-                    //             64 kh + 16 k16 .. +16 (8-row groups 128 B apart): the same bytes read MN-major
-                    // B = Fhat rows 64 kh + 16 k16 .. +16 of this CTA's boxes 2m, 2m + 1, MN-major
-                    const uint64_t ad = trans ? make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * 128, 128, TM * 16)
-                                              : make_smem_desc_nosw(p_tile + (kh * 8 + k16 * 2) * (TM * 16), TM * 16, 128);
-                    const uint64_t bd = make_smem_desc_sw128(st + 2 * m * GBOX_BYTES + k16 * 2048, 1024, GBOX_BYTES);
-                    umma_ss_2sm(tmem_base + m * 256, ad, bd, idesc, (p > 0 || a > 0 || kh > 0 || k16 > 0) ? 1u : 0u);
-                  }
-                }
-                umma_commit_2sm(empty_bar(ring.stage), kMaskPair);
-              }
-              __syncwarp();
-              ring.advance();
-            }
-            if (elect_one()) umma_commit_2sm(pbempty_bar(pb), kMaskPair);
-            if (pair == 0 && lane == 0 && a == 1) TR(1, i, 6);
-            __syncwarp();
-          }
-        }
-        if (elect_one()) umma_commit_2sm(acc_full, kMaskPair);
-        __syncwarp();
-        ++seg_iter;
-        if (pair_stamp && lane == 0) pair_stamp[1] = global_ns();
-      }
-    } else if (warp >= EPI_WARP0) {
-      // drain: dF of the sweep -> dfhat (fp32, still scaled by sigma; grad_finish divides it out)
-      const int quadw = warp & 3, wg = (warp - EPI_WARP0) >> 2;     // wg: which 256-column half of D
-      const int r = quadw * 32 + lane;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(quadw * 32) << 16);
-      const uint32_t acc_empty_ldr = mapa_cluster(acc_empty, 0);
-      const bool whole = P.parts == 1;
-      uint32_t seg_iter = 0;
-      for (int c = pair; c < nrings; c += P.n_g, ++seg_iter) {
-        const int I = c / P.parts;
-        mbar_wait(acc_full, seg_iter & 1);
-        tc_fence_after();
-        float* out = dfhat + ((int64_t)I * FLOW_TN + (int)sub * TM + r) * g.dim;
-        const int c_end = min(g.dim, wg * 256 + 256) / 32;
-#pragma unroll 1
-        for (int cc = wg * 8; cc < c_end; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + cc * 32, v);
-          tmem_ld_wait();
-          if (whole) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4)
-              *reinterpret_cast<float4*>(out + cc * 32 + q) =
-                  make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
-                              __uint_as_float(v[q + 3]));
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + cc * 32 + q), "f"(__uint_as_float(v[q])),
-                           "f"(__uint_as_float(v[q + 1])), "f"(__uint_as_float(v[q + 2])), "f"(__uint_as_float(v[q + 3]))
-                           : "memory");
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_ldr);
-      }
-    }
+  }
+
+  if (!is_prod && !(P.exp & 8)) consumer_roles(pair, P.n_g, nrings_main, false);
+  if (is_prod && P.d0 <= P.nb && !(P.exp & 4)) {
+    // production is over for this pair: every tile it made is stored and published, its TMEM and shared memory are free.
+    // It now consumes the late rings of rows prod, prod + n_s, ... (symmetric schedule only).
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    consumer_roles(nrings_main + prod, P.n_s, nrings_main + P.nb, true);
   }
 
   tc_fence_before();
@@ -698,6 +739,7 @@ int env_int(const char* name, int dflt) {
 struct FlowPlan {
   bool ok;
   int n_g, n_s, parts, cnt, sym, nb, nrb;
+  int d0, cnt_main, cnt_late;       // late rings of the symmetric schedule (d0 = nb + 1: none)
 };
 
 // Schedule for a problem, or ok = false when the dataflow kernel does not apply (the caller falls back).
@@ -733,6 +775,27 @@ FlowPlan flow_plan(const Geometry& g, int pairs) {
     f.n_s = (int)std::max<long long>(1, std::min<long long>(f.n_s, tiles));
   }
   if (force_ns > 0) f.n_s = std::max(1, std::min(force_ns, pairs - f.n_g));
+  // Late rings (symmetric schedule, one consumer per row block): the producers finish long before the consumers (an S tile
+  // costs ~1.3 dF tile products, and every S tile feeds two products), so the products of the tiles with the largest
+  // cyclic distance, d >= d0, are left to the producer pairs, which turn consumer when their production is over.  Balance:
+  // (nb - L) products on a main consumer  =  production (tiles / n_s S tiles) + L products on a late consumer.
+  f.d0 = f.nb + 1; f.cnt_main = f.cnt; f.cnt_late = 0;
+  static const int force_d0 = env_int("CROSSCLR_FLOW_D0", -1);
+  if (f.sym && f.parts == 1 && force_d0 != 0) {
+    const double tiles = 0.5 * f.nb * (f.nb + 1);
+    const double l_target = 0.5 * (f.nb - 1.3 * tiles / f.n_s);
+    int d0 = (f.nb & 1) ? (f.nb - 1) / 2 + 1 - (int)(l_target / 2.0) : (int)std::ceil(f.nb / 2.0 - (l_target - 1.0) / 2.0);
+    if (force_d0 > 0) d0 = force_d0;
+    const int nd_max = (f.nb & 1) ? (f.nb + 1) / 2 : f.nb / 2 + 1;      // distances 0 .. nd_max - 1
+    const int late_tiles_per_row = nd_max - d0;
+    // a producer's chunk crosses at most one row end (chunk < row), so it holds at most late_tiles_per_row late tiles in
+    // its FLOW_NSLOT slots while it goes on producing: keep two slots free
+    if (d0 >= 2 && late_tiles_per_row >= 1 && late_tiles_per_row <= FLOW_NSLOT - 3 && tiles / f.n_s < nd_max - 1 && f.n_s >= f.nb / 2) {
+      f.d0 = d0;
+      f.cnt_main = 2 * d0 - 1;
+      f.cnt_late = f.nb - f.cnt_main;
+    }
+  }
   f.ok = f.n_g >= 1 && f.n_s >= 1 && f.n_g + f.n_s <= pairs;
   return f;
 }
@@ -756,7 +819,7 @@ void flow_trace_dump(unsigned long long* trace, cudaStream_t st, const FlowPlan&
   if (!fp) return;
   unsigned long long t0 = ~0ull;
   for (int i = 0; i < 2 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
-  fprintf(fp, "# n_g %d n_s %d parts %d cnt %d sym %d nb %d nrb %d\n", f.n_g, f.n_s, f.parts, f.cnt, f.sym, f.nb, f.nrb);
+  fprintf(fp, "# n_g %d n_s %d parts %d cnt %d sym %d nb %d nrb %d d0 %d cnt_main %d cnt_late %d\n", f.n_g, f.n_s, f.parts, f.cnt, f.sym, f.nb, f.nrb, f.d0, f.cnt_main, f.cnt_late);
   fprintf(fp, "# role 0 = producer 0: mma_wait_sempty mma_start mma_issued epi_start staged_seen published epi_slot_ok epi_done\n");
   fprintf(fp, "# role 1 = consumer 0: poll_start desc_seen p_issued mma_wait_p p0_landed p1_landed mma_issued -   (ns since first stamp)\n");
   for (int role = 0; role < 2; ++role)
@@ -768,17 +831,18 @@ void flow_trace_dump(unsigned long long* trace, cudaStream_t st, const FlowPlan&
       }
       fprintf(fp, "\n");
     }
-  fprintf(fp, "# per pair (consumers first, then producers): first_ns last_ns waited_ns tiles\n");
+  fprintf(fp, "# per pair (consumers first, then producers): first_ns last_ns waited_ns late_consumer_done_ns\n");
   for (int p = 0; p < f.n_g + f.n_s && p < 128; ++p) {
     const unsigned long long* q = host + 2 * 64 * 8 + p * 4;
     fprintf(fp, "P %3d %s %8lld %8lld %8lld %4lld\n", p, p < f.n_g ? "cons" : "prod", q[0] ? (long long)(q[0] - t0) : -1ll,
-            q[1] ? (long long)(q[1] - t0) : -1ll, (long long)q[2], (long long)q[3]);
+            q[1] ? (long long)(q[1] - t0) : -1ll, (long long)q[2], q[3] ? (long long)(q[3] - t0) : -1ll);
   }
   fclose(fp);
 }
 
+// upper bound of the control words of any plan for this problem: rings (main + late), tails (parts <= 64), releases
 size_t flow_control_bytes(int nrb, int nb, int pairs) {
-  const size_t words = (size_t)nrb * nb + (size_t)nrb * 64 + (size_t)pairs * FLOW_NSLOT;   // rings, tails (parts <= 64), releases
+  const size_t words = 2 * (size_t)nrb * nb + (size_t)nrb * 64 + nb + (size_t)pairs * FLOW_NSLOT;
   return (words * 4 + 1023) & ~(size_t)1023;
 }
 
@@ -797,7 +861,7 @@ bool bwd_flow_applies(const Geometry& g) {
 }
 
 int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, const float* scal, float* dfhat,
-                    void* scratch, cudaStream_t st) {
+                    float* dfhat_late, bool* used_late, void* scratch, cudaStream_t st) {
   const int pairs = flow_pairs_resident();
   const FlowPlan f = flow_plan(g, pairs);
   if (!f.ok) { set_error("crossclr_bwd: the dataflow kernel does not apply to this problem"); return CROSSCLR_EINVAL; }
@@ -812,18 +876,24 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   if (rc) return rc;
   FlowParams P;
   P.n_g = f.n_g; P.n_s = f.n_s; P.nb = f.nb; P.nrb = f.nrb; P.parts = f.parts; P.cnt = f.cnt; P.sym = f.sym;
+  P.d0 = f.d0; P.cnt_main = f.cnt_main; P.cnt_late = f.cnt_late;
+  const bool late_on = f.d0 <= f.nb;
+  const size_t n_rings = (size_t)f.nrb * f.parts + (late_on ? f.nb : 0);
   P.nk = g.dim / KC;
   P.s_stages = std::min((int)((kMaxSmem - FLOW_HDR - (size_t)P.nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS);
   P.ring = (uint32_t*)scratch;
-  P.tail = P.ring + (size_t)f.nrb * f.nb;
-  P.release = P.tail + (size_t)f.nrb * 64;
+  P.tail = P.ring + n_rings * f.cnt;
+  P.release = P.tail + n_rings;
   P.pool = pool;
+  P.dfhat_late = dfhat_late;
+  *used_late = late_on;
+  const size_t ctl_used = ((n_rings * f.cnt + n_rings + (size_t)f.n_s * FLOW_NSLOT) * 4 + 255) & ~(size_t)255;
   P.trace = flow_trace_buffer(st);
   static const int exp_flags = env_int("CROSSCLR_FLOW_EXP", 0);
   P.exp = exp_flags;
   CC_CHECK_CUDA(cudaFuncSetAttribute(bwd_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
   TimedLaunch timed(CROSSCLR_K_BWD, st);               // after the host-side preparation: the bracket holds device work only
-  CC_CHECK_CUDA(cudaMemsetAsync(scratch, 0, ctl_bytes, st));
+  CC_CHECK_CUDA(cudaMemsetAsync(scratch, 0, ctl_used, st));
   if (f.parts > 1) CC_CHECK_CUDA(cudaMemsetAsync(dfhat, 0, (size_t)g.row_count * g.dim * sizeof(float), st));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * (f.n_g + f.n_s));

@@ -402,13 +402,15 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
                                                          const float* __restrict__ scal, bool use_sigma,
                                                          const double* __restrict__ grad_out, float grad_scale,
                                                          const float* __restrict__ dfhat, TO* __restrict__ dv,
-                                                         int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride) {
+                                                         int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride,
+                                                         const float* __restrict__ dfhat2, const unsigned int* __restrict__ two) {
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (l >= g.row_count) return;
   const int gr = g.row_begin + l;
   const int pg = row_partner(gr, g.bseg);
   const float rn_g = rn[l];                    // reciprocal norms of the OWNED rows only
+  const float* dh2 = (dfhat2 != nullptr && two != nullptr && *two != 0u) ? dfhat2 + (int64_t)l * g.dim : nullptr;
   const TF* fg = F + (int64_t)gr * g.pitch;
   const TF* fp = F + (int64_t)pg * g.pitch;
   const float qg = row_scale<TF, kTail>(fg, g.dim), qp = row_scale<TF, kTail>(fp, g.dim);
@@ -417,7 +419,8 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   const float* dh = dfhat + (int64_t)l * g.dim;
   float dot = 0.f;
   for (int d = lane; d < g.dim; d += 32) {
-    const float h = dh[d] * acc_scale + pos_coef * to_float<TF>(fp[d]);
+    const float acc = dh2 ? dh[d] + dh2[d] : dh[d];
+    const float h = acc * acc_scale + pos_coef * to_float<TF>(fp[d]);
     dot = fmaf(h, to_float<TF>(fg[d]), dot);
   }
   dot = warp_sum(dot) * qg * qg;        // (h . Fhat_g) Fhat_g with Fhat_g = q_g f_g
@@ -429,7 +432,8 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   const int r = gr % g.bseg;
   TO* out = mod == 0 ? dv + (int64_t)r * dv_stride : dt + (int64_t)r * dt_stride;
   for (int d = lane; d < g.dim; d += 32) {
-    const float h = dh[d] * acc_scale + pos_coef * to_float<TF>(fp[d]);
+    const float acc = dh2 ? dh[d] + dh2[d] : dh[d];
+    const float h = acc * acc_scale + pos_coef * to_float<TF>(fp[d]);
     out[d] = from_float<TO>(mult * (h - dot * to_float<TF>(fg[d])));
   }
 }
@@ -447,7 +451,8 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
                                                              const float* __restrict__ scal, bool use_sigma,
                                                              const double* __restrict__ grad_out, float grad_scale,
                                                              const float* __restrict__ dfhat, TO* __restrict__ dv,
-                                                             int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride) {
+                                                             int64_t dv_stride, TO* __restrict__ dt, int64_t dt_stride,
+                                                             const float* __restrict__ dfhat2, const unsigned int* __restrict__ two) {
   using H2 = typename Half2Of<TF>::type;
   const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -463,13 +468,20 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
   const uint4* fg = reinterpret_cast<const uint4*>(rowg);
   const uint4* fp = reinterpret_cast<const uint4*>(rowp);
   const float4* dh = reinterpret_cast<const float4*>(dfhat + (int64_t)l * g.dim);
+  const float4* dh2 = (dfhat2 != nullptr && two != nullptr && *two != 0u) ? reinterpret_cast<const float4*>(dfhat2 + (int64_t)l * g.dim)
+                                                                       : nullptr;   // partial of the late consumers
   float h[NV][8], f[NV][8];
   float dot = 0.f;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int idx = lane + 32 * v;
     const uint4 ug = __ldg(fg + idx), up = __ldg(fp + idx);
-    const float4 d0 = __ldg(dh + 2 * idx), d1 = __ldg(dh + 2 * idx + 1);
+    float4 d0 = __ldg(dh + 2 * idx), d1 = __ldg(dh + 2 * idx + 1);
+    if (dh2 != nullptr) {
+      const float4 e0 = __ldg(dh2 + 2 * idx), e1 = __ldg(dh2 + 2 * idx + 1);
+      d0.x += e0.x; d0.y += e0.y; d0.z += e0.z; d0.w += e0.w;
+      d1.x += e1.x; d1.y += e1.y; d1.z += e1.z; d1.w += e1.w;
+    }
     const H2* hg = reinterpret_cast<const H2*>(&ug);
     const H2* hp = reinterpret_cast<const H2*>(&up);
     const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -509,7 +521,8 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
 template <typename TF, typename TO>
 static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
                             const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
-                            const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, cudaStream_t st) {
+                            const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, cudaStream_t st,
+                            const float* dfhat2, const unsigned int* two) {
   const size_t osz = sizeof(TO);
   if (g.dim % 256 != 0 || g.dim > 1024 || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
       (dvs * osz) % 16 != 0 || (dts * osz) % 16 != 0 || (g.pitch * sizeof(TF)) % 16 != 0)
@@ -517,7 +530,7 @@ static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rn
   dim3 block(256), grid((g.row_count + 7) / 8);
 #define CC_GFV(NV)                                                                                                      \
   grad_finish_vec_kernel<TF, TO, NV><<<grid, block, 0, st>>>(g, (const TF*)feat, rnorm, coef, scal, use_sigma, grad_out, \
-                                                            grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
+                                                            grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts, dfhat2, two)
   switch (g.dim / 256) {
     case 1: CC_GFV(1); break;
     case 2: CC_GFV(2); break;
@@ -532,11 +545,11 @@ template <typename TF, bool kTail>
 static int grad_finish_out(const Geometry& g, const void* feat, const float* rnorm, const float* coef,
                            const float* scal, bool use_sigma, const double* grad_out, float grad_scale,
                            const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, int out_dtype,
-                           cudaStream_t st) {
+                           cudaStream_t st, const float* dfhat2 = nullptr, const unsigned int* two = nullptr) {
   dim3 block(256), grid((g.row_count + 7) / 8);
 #define CC_GF(TO)                                                                                                    \
   grad_finish_kernel<TF, TO, kTail><<<grid, block, 0, st>>>(g, (const TF*)feat, rnorm, coef, scal, use_sigma, grad_out, \
-                                                           grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts)
+                                                           grad_scale, dfhat, (TO*)dv, dvs, (TO*)dt, dts, dfhat2, two)
   switch (out_dtype) {
     case CROSSCLR_F32: CC_GF(float); break;
     case CROSSCLR_F16: CC_GF(__half); break;
@@ -550,30 +563,34 @@ static int grad_finish_out(const Geometry& g, const void* feat, const float* rno
 template <typename TF>
 static int grad_finish_16(const Geometry& g, const void* feat, const float* rnorm, const float* coef, const float* scal,
                           bool use_sigma, const double* grad_out, float grad_scale, const float* dfhat, void* dv,
-                          int64_t dv_stride, void* dt, int64_t dt_stride, int out_dtype, cudaStream_t st) {
+                          int64_t dv_stride, void* dt, int64_t dt_stride, int out_dtype, cudaStream_t st, const float* dfhat2,
+                          const unsigned int* two) {
   bool done = false;
   switch (out_dtype) {
-    case CROSSCLR_F32: done = grad_finish_vec<TF, float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
-    case CROSSCLR_F16: done = grad_finish_vec<TF, __half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
-    case CROSSCLR_BF16: done = grad_finish_vec<TF, __nv_bfloat16>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st); break;
+    case CROSSCLR_F32: done = grad_finish_vec<TF, float>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st, dfhat2, two); break;
+    case CROSSCLR_F16: done = grad_finish_vec<TF, __half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st, dfhat2, two); break;
+    case CROSSCLR_BF16: done = grad_finish_vec<TF, __nv_bfloat16>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt, dt_stride, st, dfhat2, two); break;
     default: break;
   }
   if (done) return check_launch("grad_finish_vec_kernel");
   return grad_finish_out<TF, true>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt,
-                                   dt_stride, out_dtype, st);
+                                   dt_stride, out_dtype, st, dfhat2, two);
 }
 
 int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm,
                        const float* coef, const float* scal, bool use_sigma, const double* grad_out,
                        float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,
-                       int64_t dt_stride, int out_dtype, cudaStream_t st) {
+                       int64_t dt_stride, int out_dtype, cudaStream_t st, const float* dfhat2) {
   TimedLaunch timed(CROSSCLR_K_GRADFIN, st);
+  // the flag word (second partial in use?) sits right behind the two partials, 256-byte aligned as in api.cu
+  const size_t part_bytes = ((size_t)g.row_count * (size_t)g.dim * sizeof(float) + 255) & ~(size_t)255;
+  const unsigned int* two = dfhat2 ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(dfhat) + 2 * part_bytes) : nullptr;
   if (feat_dtype == CROSSCLR_F32)
     return grad_finish_out<float, false>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
                                          dv_stride, dt, dt_stride, out_dtype, st);
   if (feat_dtype == CROSSCLR_F16)
     return grad_finish_16<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt,
-                                  dt_stride, out_dtype, st);
+                                  dt_stride, out_dtype, st, dfhat2, two);
   set_error("crossclr_bwd: unsupported stacked dtype %d", feat_dtype);
   return CROSSCLR_EINVAL;
 }

@@ -1576,12 +1576,13 @@ const char* bwd_tc_kernel_name(const Geometry& g) {
 }
 
 int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const float* scal, float* dfhat,
-                  void* scratch, cudaStream_t st) {
+                  float* dfhat_late, bool* two_partials, void* scratch, cudaStream_t st) {
+  *two_partials = false;
   CUtensorMap tmap;
   int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
   if (bwd_flow_applies(g))                             // producer pairs -> P-tile pool -> consumer pairs (flow_kernels.cu)
-    return launch_bwd_flow(g, feat, coef, scal, dfhat, scratch, st);
+    return launch_bwd_flow(g, feat, coef, scal, dfhat, dfhat_late, two_partials, scratch, st);
   if (const int csize = pair_cluster_size(g.dim)) {    // > 1 slab would recompute S: role-specialised CTA clusters
     return g.dim <= 512 ? launch_bwd_pair_t<true>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st)
                         : launch_bwd_pair_t<false>(tmap, feat, g, coef, scal, dfhat, scratch, csize, st);
