@@ -219,8 +219,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < num_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 32); }   // 16 warps x 2 CTAs
-    for (int s = 0; s < FWD_QSTAGES; ++s) { mbar_init(qfull_bar(s), 1); mbar_init(qempty_bar(s), 16); }   // 16 epilogue warps
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 16); }   // 8 warps of a group x 2 CTAs
+    for (int s = 0; s < FWD_QSTAGES; ++s) { mbar_init(qfull_bar(s), 1); mbar_init(qempty_bar(s), 8); }   // the 8 warps of the tile's group
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
@@ -326,29 +326,29 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
       __syncwarp();
     }
   } else if (warp >= EPI_WARP0) {
-    // Sixteen epilogue warps, four per TMEM lane quadrant: warp (quadrant q, slice s) owns rows [32 q, +32) x columns
-    // [64 s, +64) of EVERY tile.  Its 64 accumulators per row come out of TMEM with two back-to-back loads and the buffer
-    // is handed back as soon as they land, so a buffer is held for MMA time + read-out time (not + math time) and two
-    // buffers keep the tensor pipe busy; four warps per scheduler cover the ex2 latency.
-    const int quad = warp & 3, sl = (warp - EPI_WARP0) >> 2;
-    const int half = sl >> 1;                                        // the slice's 128-column half of the tile
+    // Sixteen epilogue warps in two ping-pong groups: group gsel takes the tiles of parity gsel, i.e. TMEM buffer gsel.  Inside
+    // a group, warp (quadrant q, half h) owns rows [32 q, +32) x columns [128 h, +128) of the tile, as two 64-column chunks:
+    // read-out of chunk 0 -> math -> read-out of chunk 1 -> buffer handed back -> math.  The TMEM read-out of a tile (128 KiB
+    // at 64 B/clk: ~2k cycles) therefore overlaps the other group's arithmetic instead of preceding every warp's own.
+    const int quad = warp & 3, half = ((warp - EPI_WARP0) >> 2) & 1, gsel = (warp - EPI_WARP0) >> 3;
     const int r = quad * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + sl * 64;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + gsel * FWD_TN + half * TM;
     int cur_ib = -1, gi = 0;
     BlockSeg bi{0, 0};
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     float q_i = 1.f;
     const float k_diag_term = fast_exp2(-g.shift);
     const float nshift = -g.shift;
-    const uint32_t tempty_ldr0 = mapa_cluster(tempty_bar(0), 0), tempty_ldr1 = mapa_cluster(tempty_bar(1), 0);
+    const uint32_t tempty_ldr = mapa_cluster(tempty_bar(gsel), 0);
     // running tile coordinates (no divisions in the loop): row-block pair ib, column block jb, and the segment / offset
-    // of this slice's half of the column block
+    // of this warp's half of the column block
     FwdTileWalk w(t_begin, ncb, kSym);
     int ib = w.ib, jb = w.jb;
     int jseg = (jb * FWD_TN + half * TM) / g.bseg, joff = (jb * FWD_TN + half * TM) - jseg * g.bseg;
     uint32_t iter = 0;
     for (int t = t_begin; t < t_end; ++t, ++iter) {
-      if (ib != cur_ib) {
+      const bool mine = (iter & 1) == (uint32_t)gsel;
+      if (mine && ib != cur_ib) {
         if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
         rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
         cur_ib = ib;
@@ -361,44 +361,47 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
       const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
       const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;      // row part of the logit scale
       const bool col_sums = kSym && jb != ib;                        // off-diagonal tile of the symmetric walk
-      const int col_row0 = jb * FWD_TN + sl * 64;                    // stacked row of the slice's first column
+      const int col_row0 = jb * FWD_TN + half * TM;                  // stacked row of the warp's first column
       const uint32_t qs = iter % FWD_QSTAGES;
-      const float* const qv = q_ring + qs * FWD_TN + sl * 64;        // this slice's column scales
+      const float* const qv = q_ring + qs * FWD_TN + half * TM;      // this half's column scales
       w.next();
       if (w.ib != ib) { ib = w.ib; jb = w.jb; jseg = (jb * FWD_TN + half * TM) / g.bseg; joff = (jb * FWD_TN + half * TM) - jseg * g.bseg; }
       else { jb = w.jb; joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
+      if (!mine) continue;
       mbar_wait(qfull_bar(qs), (iter / FWD_QSTAGES) & 1);
-      const uint32_t buf = iter & 1;
-      const uint32_t tb = lane_base + buf * FWD_TN;
-      mbar_wait(tfull_bar(buf), (iter >> 1) & 1);
+      mbar_wait(tfull_bar(gsel), (iter >> 1) & 1);
       tc_fence_after();
-      uint32_t va[32], vb[32];
-      tmem_ld32(tb, va);
-      tmem_ld32(tb + 32, vb);
-      tmem_ld_wait();
-      tc_fence_before();                                             // this warp's part of the tile is in registers
-      __syncwarp();                                                  // (also: every lane's column scales are in qv)
-      if (lane == 0) mbar_arrive_cluster(buf ? tempty_ldr1 : tempty_ldr0);
-      if (!(exp_flags & 1)) {
-        // 32-column chunk c of the slice is chunk (2 (sl & 1) + c) of its half; the same-sample column r of a diagonal
-        // half sits in chunk r >> 5 = quad
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {                                   // 64-column chunks of the half
+        uint32_t va[32], vb[32];
+        tmem_ld32(lane_base + c * 64, va);
+        tmem_ld32(lane_base + c * 64 + 32, vb);
+        tmem_ld_wait();
+        if (c == 1) {
+          tc_fence_before();                                         // this warp's part of the tile is in registers
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_ldr);
+        }
+        if (exp_flags & 1) continue;
+        // the same-sample column r of a diagonal half sits in its 32-column chunk r >> 5 = quad
+        const float* const qc = qv + c * 64;
         if (!col_sums) {
-          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk(va, k, nshift, reinterpret_cast<const float4*>(qv), rs);
-          else fwd_diag_chunk(va, k, nshift, qv, same_mod, k_diag_term, r, gi, stats, rs);
-          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk(vb, k, nshift, reinterpret_cast<const float4*>(qv + 32), rs);
-          else fwd_diag_chunk(vb, k, nshift, qv + 32, same_mod, k_diag_term, r, gi, stats, rs);
+          if (!diag_tile || quad != 2 * c) fwd_sum_chunk(va, k, nshift, reinterpret_cast<const float4*>(qc), rs);
+          else fwd_diag_chunk(va, k, nshift, qc, same_mod, k_diag_term, r, gi, stats, rs);
+          if (!diag_tile || quad != 2 * c + 1) fwd_sum_chunk(vb, k, nshift, reinterpret_cast<const float4*>(qc + 32), rs);
+          else fwd_diag_chunk(vb, k, nshift, qc + 32, same_mod, k_diag_term, r, gi, stats, rs);
         } else {
           const int partner = row_partner(gi, g.bseg);
-          if (!diag_tile || quad != 2 * (sl & 1)) fwd_sum_chunk_keep(va, k, nshift, reinterpret_cast<const float4*>(qv), rs);
-          else fwd_diag_chunk_keep(va, k, nshift, qv, same_mod, k_diag_term, r, gi, partner, stats, rs);
-          if (!diag_tile || quad != 2 * (sl & 1) + 1) fwd_sum_chunk_keep(vb, k, nshift, reinterpret_cast<const float4*>(qv + 32), rs);
-          else fwd_diag_chunk_keep(vb, k, nshift, qv + 32, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          if (!diag_tile || quad != 2 * c) fwd_sum_chunk_keep(va, k, nshift, reinterpret_cast<const float4*>(qc), rs);
+          else fwd_diag_chunk_keep(va, k, nshift, qc, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          if (!diag_tile || quad != 2 * c + 1) fwd_sum_chunk_keep(vb, k, nshift, reinterpret_cast<const float4*>(qc + 32), rs);
+          else fwd_diag_chunk_keep(vb, k, nshift, qc + 32, same_mod, k_diag_term, r, gi, partner, stats, rs);
           // the mirrored tile (jb, ib) is never computed: its row sums are this tile's column sums
-          float c0, c1;
           if (!(exp_flags & 16)) {
+            float c0, c1;
             warp_column_sums(va, vb, lane, c0, c1);
-            atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane)], c0);
-            atomicAdd(&stats[2 * (int64_t)(col_row0 + 2 * lane + 1)], c1);
+            atomicAdd(&stats[2 * (int64_t)(col_row0 + c * 64 + 2 * lane)], c0);
+            atomicAdd(&stats[2 * (int64_t)(col_row0 + c * 64 + 2 * lane + 1)], c1);
           }
         }
       }
