@@ -49,8 +49,11 @@ struct FlowParams {
   int d0;                // symmetric schedule: tiles of cyclic distance >= d0 go to the LATE rings (consumed by producer pairs
                          // once their own production is over); nb + 1 = no late rings
   int cnt_main, cnt_late;   // tile products per main ring (= cnt without late rings) / per late ring
+  int ds, dw;            // consumers split D into ds slabs of dw columns (D <= 512: 1 x D; else 2 x D/2): physical ring =
+                         // logical ring * ds + slab, every tile is consumed once per slab
+  int a_res;             // producer keeps its 128 rows of A resident (nk <= 8); else A streams beside B
   int nk;                // dim / 64
-  int s_stages;          // producer B ring depth
+  int s_stages;          // producer ring depth
   uint32_t* ring;        // [nrb * parts (+ nb late)][cnt] descriptors, zero = not yet published
   uint32_t* tail;        // [nrb * parts (+ nb late)]
   uint32_t* release;     // [n_s][FLOW_NSLOT] consumer releases per pool slot (monotonic)
@@ -124,6 +127,7 @@ struct FlowProdWalk {
   __device__ FlowProdWalk(const FlowParams& P, int s_)
       : n_g(P.n_g), n_s(P.n_s), nb(P.nb), parts(P.parts), cnt(P.cnt), sym(P.sym), s(s_), nrings(P.nrb * P.parts),
         wave(-1), k(0), k0(0), k_end(0), c0(0), pass(1), I(0), d(0) {
+    n_g = P.n_g / P.ds;                        // logical rings per wave (n_g is a multiple of ds)
     nwaves = (nrings + n_g - 1) / n_g;
     d0 = P.d0;
   }
@@ -245,9 +249,10 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   auto consumer_roles = [&](int c_first, int c_stride, int c_end, bool late) {
     const uint32_t p_tiles = base + 1024;
     const uint32_t ring_base = p_tiles + FLOW_PBUF * PTILE_BYTES;
-    const int nbox = g.dim / 128;                      // own [64 j][64 d] boxes per 64-row group: half of each MMA's N
+    const int dw = P.dw;                               // columns of D this consumer accumulates (its slab)
+    const int nbox = dw / 128;                         // own [64 j][64 d] boxes per 64-row group: half of each MMA's N
     const uint32_t group_bytes = (uint32_t)nbox * GBOX_BYTES;
-    const int nmma = (g.dim + 255) / 256;              // MMAs per K = 16 step: N = 256 each (last one 128 if D % 256)
+    const int nmma = (dw + 255) / 256;                 // MMAs per K = 16 step: N = 256 each (last one 128 if dw % 256)
     const int cnt_c = late ? P.cnt_late : P.cnt_main;
     if (warp == 0) {
       // TMA producer of the dF B operand: rows of the other block as [64 j][64 d] boxes, this CTA's half of every MMA's N
@@ -267,8 +272,8 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
                 if (sub == 0) mbar_arrive_expect_tx(cfull_bar(ring.stage), 2 * group_bytes);
                 for (int q = 0; q < nbox; ++q) {
                   const int m = q >> 1;                               // MMA index; its N = nm, this CTA's half = nm / 2
-                  const int nm = min(256, g.dim - m * 256);
-                  const int d0 = m * 256 + (int)sub * (nm >> 1) + (q & 1) * 64;
+                  const int nm = min(256, dw - m * 256);
+                  const int d0 = (c % P.ds) * dw + m * 256 + (int)sub * (nm >> 1) + (q & 1) * 64;
                   tma_load_2d_2sm(st + q * GBOX_BYTES, &tmap64, full_ldr, d0, other * FLOW_TN + a * TM + kh * 64);
                 }
               }
@@ -338,7 +343,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               if (elect_one()) {
                 const uint32_t st = ring_base + ring.stage * group_bytes;
                 for (int m = 0; m < nmma; ++m) {
-                  const int nm = min(256, g.dim - m * 256);
+                  const int nm = min(256, dw - m * 256);
                   const uint32_t idesc = make_idesc_f16(256, nm, 0, 0, trans ? 1 : 0, 1);
 #pragma unroll
                   for (int k16 = 0; k16 < 4; ++k16) {
@@ -377,13 +382,14 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       const bool whole = P.parts == 1;      // one main (and one late) consumer per row block: plain stores
       uint32_t seg_iter = 0;
       for (int c = c_first; c < c_end; c += c_stride, ++seg_iter) {
-        const int I = late ? c - nrings_main : c / P.parts;
+        const int cl = c / P.ds;                         // logical ring, slab c % ds
+        const int I = late ? cl - nrings_main : cl / P.parts;
         mbar_wait(acc_full, seg_iter & 1);
         tc_fence_after();
-        float* out = (late ? dfhat_late : dfhat) + ((int64_t)I * FLOW_TN + (int)sub * TM + r) * g.dim;
-        const int c_end = min(g.dim, wg * 256 + 256) / 32;
+        float* out = (late ? dfhat_late : dfhat) + ((int64_t)I * FLOW_TN + (int)sub * TM + r) * g.dim + (c % P.ds) * dw;
+        const int cc_end = min(dw, wg * 256 + 256) / 32;
 #pragma unroll 1
-        for (int cc = wg * 8; cc < c_end; ++cc) {
+        for (int cc = wg * 8; cc < cc_end; ++cc) {
           uint32_t v[32];
           tmem_ld32(lane_base + cc * 32, v);
           tmem_ld_wait();
@@ -410,10 +416,12 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 
   if (is_prod && !(P.exp & 4)) {
     // =========================================================================== producer pair
+    const bool a_res = P.a_res != 0;
     const uint32_t a_region = data;
-    const uint32_t ring_base = data + nk * CHUNK_BYTES;
+    const uint32_t ring_base = data + (a_res ? nk * CHUNK_BYTES : 0);
+    const uint32_t stage_bytes = a_res ? CHUNK_BYTES : 2 * CHUNK_BYTES;      // [own A chunk, streamed] + own half of the B chunk
     if (warp == 0) {
-      // TMA: own 128 rows of A (resident per row block), own half of each 256-row B chunk; bytes counted on the leader
+      // TMA: own 128 rows of A (resident per row block, or streamed), own half of each 256-row B chunk; bytes counted on the leader
       Ring ring(P.s_stages);
       int cur_I = -1;
       uint32_t a_cnt = 0;
@@ -422,7 +430,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       FlowTile tl;
       while (walk.next(tl)) {
         const int row0 = g.row_begin + tl.I * FLOW_TN + (int)sub * TM;
-        if (tl.I != cur_I) {
+        if (a_res && tl.I != cur_I) {
           mbar_wait(a_empty, (a_cnt & 1) ^ 1);
           if (elect_one()) {
             if (sub == 0) mbar_arrive_expect_tx(a_full, 2 * nk * CHUNK_BYTES);
@@ -434,9 +442,11 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
           if (elect_one()) {
-            if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
-            tma_load_2d_2sm(ring_base + ring.stage * CHUNK_BYTES, &tmap, mapa_cluster(full_bar(ring.stage), 0), kc * KC,
-                            tl.J * FLOW_TN + (int)sub * TM);
+            uint32_t st = ring_base + ring.stage * stage_bytes;
+            const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), 0);
+            if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * stage_bytes);
+            if (!a_res) { tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, row0); st += CHUNK_BYTES; }
+            tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, tl.J * FLOW_TN + (int)sub * TM);
           }
           __syncwarp();
           ring.advance();
@@ -452,7 +462,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
       bool have = walk.next(tl);
       while (have) {
         const bool have_next = walk.next(nx);
-        if (tl.I != cur_I) {
+        if (a_res && tl.I != cur_I) {
           mbar_wait(a_full, a_cnt & 1);
           cur_I = tl.I; ++a_cnt;
         }
@@ -465,8 +475,9 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           mbar_wait(full_bar(ring.stage), ring.phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t ad = kmajor_desc(a_region + kc * CHUNK_BYTES);
-            const uint64_t bd = kmajor_desc(ring_base + ring.stage * CHUNK_BYTES);
+            const uint32_t st = ring_base + ring.stage * stage_bytes;
+            const uint64_t ad = kmajor_desc(a_res ? a_region + kc * CHUNK_BYTES : st);
+            const uint64_t bd = kmajor_desc(a_res ? st : st + CHUNK_BYTES);
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k)
               umma_ss_2sm(tmem_base + buf * FLOW_TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s,
@@ -478,7 +489,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         if (elect_one()) {
           umma_commit_2sm(sfull_bar(buf), kMaskPair);
-          if (!have_next || nx.I != tl.I) umma_commit_2sm(a_empty, kMaskPair);   // last tile of this row block
+          if (a_res && (!have_next || nx.I != tl.I)) umma_commit_2sm(a_empty, kMaskPair);   // last tile of this row block
         }
         if (prod == 0 && lane == 0) TR(0, t, 2);
         __syncwarp();
@@ -504,7 +515,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           }
           __syncwarp();
         }
-        cum[slot] += (tl.ring_t >= 0) ? 2u : 1u;
+        cum[slot] += ((tl.ring_t >= 0) ? 2u : 1u) * (uint32_t)P.ds;
         ++t;
       }
     } else if (warp == 2 || warp == 3) {
@@ -526,13 +537,18 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             } else if (!(P.exp & 2)) {
               // ring positions first (two independent atomics in flight), then the peer's half, then ONE gpu-scope fence that
               // is cumulative over both halves (own: staged_bar, peer: cluster-scope acquire), then plain flag stores
-              const uint32_t pos_d = atomicAdd(P.tail + tl.ring_d, 1u);
-              const uint32_t pos_t = tl.ring_t >= 0 ? atomicAdd(P.tail + tl.ring_t, 1u) : 0u;
+              uint32_t pos_d[2], pos_t[2] = {0u, 0u};
+              for (int h = 0; h < P.ds; ++h) {
+                pos_d[h] = atomicAdd(P.tail + tl.ring_d * P.ds + h, 1u);
+                if (tl.ring_t >= 0) pos_t[h] = atomicAdd(P.tail + tl.ring_t * P.ds + h, 1u);
+              }
               mbar_wait_cluster(pub_bar(slot), use & 1);
               fence_acq_rel_gpu();
-              st_relaxed_gpu_u32(P.ring + (size_t)tl.ring_d * P.cnt + pos_d, flow_desc(prod, (int)slot, tl.J, false));
-              if (tl.ring_t >= 0)
-                st_relaxed_gpu_u32(P.ring + (size_t)tl.ring_t * P.cnt + pos_t, flow_desc(prod, (int)slot, tl.I, true));
+              for (int h = 0; h < P.ds; ++h) {
+                st_relaxed_gpu_u32(P.ring + (size_t)(tl.ring_d * P.ds + h) * P.cnt + pos_d[h], flow_desc(prod, (int)slot, tl.J, false));
+                if (tl.ring_t >= 0)
+                  st_relaxed_gpu_u32(P.ring + (size_t)(tl.ring_t * P.ds + h) * P.cnt + pos_t[h], flow_desc(prod, (int)slot, tl.I, true));
+              }
               if (prod == 0) TR(0, t, 5);
             }
           }
@@ -688,7 +704,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     }
   }
 
-  if (!is_prod && !(P.exp & 8)) consumer_roles(pair, P.n_g, nrings_main, false);
+  if (!is_prod && !(P.exp & 8)) consumer_roles(pair, P.n_g, nrings_main * P.ds, false);
   if (is_prod && P.d0 <= P.nb && !(P.exp & 4)) {
     // production is over for this pair: every tile it made is stored and published, its TMEM and shared memory are free.
     // It now consumes the late rings of rows prod, prod + n_s, ... (symmetric schedule only).
@@ -738,7 +754,7 @@ int env_int(const char* name, int dflt) {
 
 struct FlowPlan {
   bool ok;
-  int n_g, n_s, parts, cnt, sym, nb, nrb;
+  int n_g, n_s, parts, cnt, sym, nb, nrb, ds;
   int d0, cnt_main, cnt_late;       // late rings of the symmetric schedule (d0 = nb + 1: none)
 };
 
@@ -747,29 +763,32 @@ FlowPlan flow_plan(const Geometry& g, int pairs) {
   FlowPlan f = {};
   static const int variant = env_int("CROSSCLR_BWD_VARIANT", 0);
   if (variant != 0 && variant != 4) return f;
-  if (g.dim > 512 || g.dim % 128 != 0 || g.rows % FLOW_TN != 0 || g.row_count % FLOW_TN != 0 || pairs < 32) return f;
+  if (g.dim > 1024 || g.dim % 128 != 0 || (g.dim > 512 && g.dim % 256 != 0) || g.rows % FLOW_TN != 0 ||
+      g.row_count % FLOW_TN != 0 || pairs < 32)
+    return f;
   if (variant == 0 && g.rows < 2048) return f;                      // tiny problems: latency-bound either way
+  f.ds = g.dim > 512 ? 2 : 1;                                       // consumers take 512-column (or D/2) slabs of D
   f.nb = g.rows / FLOW_TN;
   f.nrb = g.row_count / FLOW_TN;
   if (f.nb >= (1 << 20) || pairs > 127) return f;
   static const int sym_max = env_int("CROSSCLR_FLOW_SYM_MAX", 48);
   static const int force_ns = env_int("CROSSCLR_FLOW_NS", 0);
   static const int force_ng = env_int("CROSSCLR_FLOW_NG", 0);
-  f.sym = (g.row_count == g.rows && g.row_begin == 0 && f.nb <= std::min(sym_max, pairs - 8)) ? 1 : 0;
+  f.sym = (g.row_count == g.rows && g.row_begin == 0 && f.nb * f.ds <= std::min(sym_max, pairs - 8)) ? 1 : 0;
   // consumers per row block: as many as fit in ~3/5 of the pairs (symmetric) or in the 32 consumer pairs of a wave
-  const int g_cap = force_ng > 0 ? force_ng : (f.sym ? std::max(f.nb, pairs * 3 / 5) : (pairs * 32) / 74);
+  const int g_cap = force_ng > 0 ? force_ng : (f.sym ? std::max(f.nb * f.ds, pairs * 3 / 5) : (pairs * 32) / 74);
   f.parts = 1;
-  while (f.nrb * f.parts * 2 <= g_cap && f.nb % (f.parts * 2) == 0) f.parts *= 2;
+  while (f.nrb * f.parts * 2 * f.ds <= g_cap && f.nb % (f.parts * 2) == 0) f.parts *= 2;
   f.cnt = f.nb / f.parts;
-  const int nrings = f.nrb * f.parts;
+  const int nrings = f.nrb * f.parts * f.ds;                         // physical rings: (row block, part, slab of D)
   if (f.sym) {
-    f.n_g = nrings;                                                  // single wave by construction
+    f.n_g = nrings;                                                  // single wave by construction (a multiple of ds)
     const long long tiles = (long long)f.nb * (f.nb + 1) / 2;
     // every remaining pair produces: measured at B = 4096, D = 512 (32 consumer pairs): 25 / 32 / 42 producer pairs ->
     // 129 / 127 / 121 us; the consumers are MMA-bound from their first tile on, more producers get them there sooner
     f.n_s = (int)std::max<long long>(1, std::min<long long>(tiles, pairs - f.n_g));
   } else {
-    f.n_g = std::min(nrings, std::max(1, std::min(g_cap, pairs - 1)));
+    f.n_g = std::min(nrings, std::max(f.ds, std::min(g_cap, pairs - 1) / f.ds * f.ds));   // a multiple of ds
     f.n_s = pairs - f.n_g;
     const long long tiles = (long long)f.nrb * f.nb;
     f.n_s = (int)std::max<long long>(1, std::min<long long>(f.n_s, tiles));
@@ -781,7 +800,7 @@ FlowPlan flow_plan(const Geometry& g, int pairs) {
   // (nb - L) products on a main consumer  =  production (tiles / n_s S tiles) + L products on a late consumer.
   f.d0 = f.nb + 1; f.cnt_main = f.cnt; f.cnt_late = 0;
   static const int force_d0 = env_int("CROSSCLR_FLOW_D0", -1);
-  if (f.sym && f.parts == 1 && force_d0 != 0) {
+  if (f.sym && f.parts == 1 && f.ds == 1 && force_d0 != 0) {
     const double tiles = 0.5 * f.nb * (f.nb + 1);
     const double l_target = 0.5 * (f.nb - 1.3 * tiles / f.n_s);
     int d0 = (f.nb & 1) ? (f.nb - 1) / 2 + 1 - (int)(l_target / 2.0) : (int)std::ceil(f.nb / 2.0 - (l_target - 1.0) / 2.0);
@@ -819,7 +838,7 @@ void flow_trace_dump(unsigned long long* trace, cudaStream_t st, const FlowPlan&
   if (!fp) return;
   unsigned long long t0 = ~0ull;
   for (int i = 0; i < 2 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
-  fprintf(fp, "# n_g %d n_s %d parts %d cnt %d sym %d nb %d nrb %d d0 %d cnt_main %d cnt_late %d\n", f.n_g, f.n_s, f.parts, f.cnt, f.sym, f.nb, f.nrb, f.d0, f.cnt_main, f.cnt_late);
+  fprintf(fp, "# n_g %d n_s %d parts %d cnt %d sym %d nb %d nrb %d ds %d d0 %d cnt_main %d cnt_late %d\n", f.n_g, f.n_s, f.parts, f.cnt, f.sym, f.nb, f.nrb, f.ds, f.d0, f.cnt_main, f.cnt_late);
   fprintf(fp, "# role 0 = producer 0: mma_wait_sempty mma_start mma_issued epi_start staged_seen published epi_slot_ok epi_done\n");
   fprintf(fp, "# role 1 = consumer 0: poll_start desc_seen p_issued mma_wait_p p0_landed p1_landed mma_issued -   (ns since first stamp)\n");
   for (int role = 0; role < 2; ++role)
@@ -840,9 +859,10 @@ void flow_trace_dump(unsigned long long* trace, cudaStream_t st, const FlowPlan&
   fclose(fp);
 }
 
-// upper bound of the control words of any plan for this problem: rings (main + late), tails (parts <= 64), releases
+// upper bound of the control words of any plan for this problem: rings (main + late, or two slabs), tails (parts <= 64),
+// releases
 size_t flow_control_bytes(int nrb, int nb, int pairs) {
-  const size_t words = 2 * (size_t)nrb * nb + (size_t)nrb * 64 + nb + (size_t)pairs * FLOW_NSLOT;
+  const size_t words = 2 * (size_t)nrb * nb + 2 * (size_t)nrb * 64 + nb + (size_t)pairs * FLOW_NSLOT;
   return (words * 4 + 1023) & ~(size_t)1023;
 }
 
@@ -878,9 +898,12 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   P.n_g = f.n_g; P.n_s = f.n_s; P.nb = f.nb; P.nrb = f.nrb; P.parts = f.parts; P.cnt = f.cnt; P.sym = f.sym;
   P.d0 = f.d0; P.cnt_main = f.cnt_main; P.cnt_late = f.cnt_late;
   const bool late_on = f.d0 <= f.nb;
-  const size_t n_rings = (size_t)f.nrb * f.parts + (late_on ? f.nb : 0);
+  const size_t n_rings = (size_t)f.nrb * f.parts * f.ds + (late_on ? f.nb : 0);
   P.nk = g.dim / KC;
-  P.s_stages = std::min((int)((kMaxSmem - FLOW_HDR - (size_t)P.nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS);
+  P.ds = f.ds; P.dw = g.dim / f.ds;
+  P.a_res = P.nk <= MAX_RES_CHUNKS ? 1 : 0;
+  P.s_stages = P.a_res ? std::min((int)((kMaxSmem - FLOW_HDR - (size_t)P.nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS)
+                       : std::min((int)((kMaxSmem - FLOW_HDR) / (2 * CHUNK_BYTES)), MAX_SLOTS);
   P.ring = (uint32_t*)scratch;
   P.tail = P.ring + n_rings * f.cnt;
   P.release = P.tail + n_rings;

@@ -106,7 +106,9 @@ def main():
         print(f"selftest variant {variant} n={n} k={k}: rc={rc} max err {err:.3e} {'OK' if rc == 0 and err < 1e-2 else 'FAIL'}", flush=True)
     ok = True
     cases = [(1024, 512, 1, 2.0, None), (2048, 256, 1, 0.0, None), (4096, 512, 1, 0.0, None), (4096, 512, 1, 2.0, None),
-             (1536, 384, 1, 2.0, None), (2048, 512, 4, 2.0, None), (4096, 512, 8, 0.0, None), (2560, 128, 1, 2.0, None)]
+             (1536, 384, 1, 2.0, None), (2048, 512, 4, 2.0, None), (4096, 512, 8, 0.0, None), (2560, 128, 1, 2.0, None),
+             (1024, 1024, 1, 2.0, None), (2048, 1024, 1, 0.0, None), (2048, 1024, 4, 2.0, None), (2048, 768, 1, 2.0, None),
+             (4096, 1024, 2, 2.0, None)]
     if mode == "full":
         cases += [(8192, 512, 1, 2.0, 16), (8192, 512, 2, 0.0, 16), (16384, 512, 1, 2.0, 16)]
     for B, D, world, al, sample in cases:
