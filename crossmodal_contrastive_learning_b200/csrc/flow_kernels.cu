@@ -409,7 +409,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_ldr);
+        if (lane == 0) mbar_arrive_cluster_relaxed(acc_empty_ldr);   // TMEM hand-back: no memory to order (see tc_ptx.cuh)
       }
     }
   };
@@ -511,7 +511,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           if (lane == 0) {
             if (!(P.exp & 2)) poll_counter_ge(P.release + prod * FLOW_NSLOT + slot, cum[slot]);
             mbar_arrive(pempty_bar(slot));
-            mbar_arrive_cluster(pempty_ldr + 8u * slot);
+            mbar_arrive_cluster_relaxed(pempty_ldr + 8u * slot);   // ordered behind the acquire load of the counter
           }
           __syncwarp();
         }
@@ -679,7 +679,8 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         tmem_ld_wait();                          // chunk 3 (vb): this warp's part of the S tile is in registers
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(buf ? sempty_ldr1 : sempty_ldr0);
+        if (lane == 0) mbar_arrive_cluster_relaxed(buf ? sempty_ldr1 : sempty_ldr0);   // TMEM hand-back: relaxed (a release
+                                                                              // arrive is a MEMBAR behind this warp's P stores)
         bool prefetched = false;
         if (have_next && mbar_try_wait(sfull_bar(buf ^ 1), ((t + 1) >> 1) & 1)) {
           tc_fence_after();

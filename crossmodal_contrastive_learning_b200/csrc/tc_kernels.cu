@@ -111,6 +111,11 @@ struct FwdTileWalk {
   __device__ __forceinline__ int next_ib() const { return (jb + 1 == ncb) ? ib + 1 : ib; }
 };
 
+// fire-and-forget fp32 add (REDG; atomicAdd with an unused result still compiles to ATOMG for .f32)
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // as fwd_sum_chunk, but leaves the exponentials in v (bit patterns) for the column sums
 __device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float4* __restrict__ qc,
                                                    float (&rs)[4]) {
@@ -349,7 +354,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     for (int t = t_begin; t < t_end; ++t, ++iter) {
       const bool mine = (iter & 1) == (uint32_t)gsel;
       if (mine && ib != cur_ib) {
-        if (cur_ib >= 0) atomicAdd(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
+        if (cur_ib >= 0) red_add_f32(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
         rs[0] = rs[1] = rs[2] = rs[3] = 0.f;
         cur_ib = ib;
         const int row0 = g.row_begin + (2 * ib + (int)rank) * TM;
@@ -380,7 +385,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         if (c == 1) {
           tc_fence_before();                                         // this warp's part of the tile is in registers
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_ldr);
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_ldr);   // TMEM hand-back: no memory to order
         }
         if (exp_flags & 1) continue;
         // the same-sample column r of a diagonal half sits in its 32-column chunk r >> 5 = quad
@@ -400,8 +405,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
           if (!(exp_flags & 16)) {
             float c0, c1;
             warp_column_sums(va, vb, lane, c0, c1);
-            atomicAdd(&stats[2 * (int64_t)(col_row0 + c * 64 + 2 * lane)], c0);
-            atomicAdd(&stats[2 * (int64_t)(col_row0 + c * 64 + 2 * lane + 1)], c1);
+            red_add_f32(&stats[2 * (int64_t)(col_row0 + c * 64 + 2 * lane)], c0);
+            red_add_f32(&stats[2 * (int64_t)(col_row0 + c * 64 + 2 * lane + 1)], c1);
           }
         }
       }

@@ -136,7 +136,9 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // generic-proxy global-memory accesses <-> async-proxy (TMA) accesses of the same locations
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-// arrival on another CTA's mbarrier without ordering of its own (pair it with an explicit fence)
+// arrival on another CTA's mbarrier without ordering of its own (pair it with an explicit fence).  Also the right form for
+// handing a TMEM buffer back to the MMA issuer: the reads are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync,
+// and a release arrive compiles to MEMBAR.ALL.CTA + ERRBAR, which waits for the warp's outstanding global stores
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
