@@ -24,7 +24,7 @@ EXPORTS = (
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
     "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
-    "crossclr_bwd_kernel_name", "crossclr_feature_pitch", "crossclr_bwd_accumulate", "crossclr_bwd_finish",
+    "crossclr_bwd_kernel_name", "crossclr_feature_pitch", "crossclr_segment_rows", "crossclr_bwd_accumulate", "crossclr_bwd_finish",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
 
@@ -62,6 +62,8 @@ def _declare(lib):
     lib.crossclr_feature_dtype.argtypes = [c.c_int]
     lib.crossclr_feature_pitch.restype = c.c_int64
     lib.crossclr_feature_pitch.argtypes = [c.c_int, c.c_int32]
+    lib.crossclr_segment_rows.restype = c.c_int64
+    lib.crossclr_segment_rows.argtypes = [c.c_int, c.c_int32]
     lib.crossclr_workspace_bytes.restype = c.c_size_t
     lib.crossclr_workspace_bytes.argtypes = [P, c.c_int]
     lib.crossclr_pack.restype = c.c_int
@@ -73,7 +75,7 @@ def _declare(lib):
     lib.crossclr_fwd.restype = c.c_int
     lib.crossclr_fwd.argtypes = [P, c.c_int, vp, vp, vp, c.c_size_t, vp]
     lib.crossclr_finalize.restype = c.c_int
-    lib.crossclr_finalize.argtypes = [P, vp, vp, vp, vp, vp]
+    lib.crossclr_finalize.argtypes = [P, c.c_int, vp, vp, vp, vp, vp]
     lib.crossclr_bwd.restype = c.c_int
     lib.crossclr_bwd.argtypes = [P, c.c_int, vp, vp, vp, vp, vp, c.c_float, vp, c.c_int64, vp, c.c_int64,
                                  c.c_int, vp, c.c_size_t, vp]

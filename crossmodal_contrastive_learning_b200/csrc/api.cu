@@ -67,10 +67,12 @@ int validate_problem(const crossclr_problem_t* p) {
   return CROSSCLR_OK;
 }
 
-static bool tc_shape_ok(const crossclr_problem_t* p) { return p->bseg % 128 == 0 && p->dim % 64 == 0; }
+// `auto` takes the tensor-core path unless the zero padding (segments to 128 rows, rows to 64 columns) would dominate the work
+static bool tc_worthwhile(const crossclr_problem_t* p) { return p->bseg >= 96 && p->dim >= 48; }
 
-static size_t dfhat_bytes(const crossclr_problem_t* p) {
-  return ((size_t)p->row_count * (size_t)p->dim * sizeof(float) + 255) & ~(size_t)255;
+// gradient accumulator of the owned rows, in the path's own (for TC: padded) geometry
+static size_t dfhat_bytes(const Geometry& g) {
+  return ((size_t)g.row_count * (size_t)g.dim * sizeof(float) + 255) & ~(size_t)255;
 }
 
 }  // namespace crossclr
@@ -98,7 +100,8 @@ int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact) {
   if (rc) return rc;
   CC_REQUIRE(in_dtype == CROSSCLR_F32 || in_dtype == CROSSCLR_F16 || in_dtype == CROSSCLR_BF16,
              "crossclr_choose_path: unsupported input dtype %d", in_dtype);
-  if (!tc_shape_ok(p) || exact) return CROSSCLR_PATH_SIMT;
+  if (!tc_worthwhile(p) || exact) return CROSSCLR_PATH_SIMT;
+  if (problem_needs_row_shift(p)) return CROSSCLR_PATH_SIMT;      // temperature below the constant shift's range (~0.0073)
   return CROSSCLR_PATH_TC;
 }
 
@@ -111,18 +114,26 @@ int crossclr_feature_dtype(int path) {
 
 int64_t crossclr_feature_pitch(int path, int32_t dim) {
   if (path == CROSSCLR_PATH_SIMT) return dim;
-  if (path_is_tc(path)) return (int64_t)dim + CROSSCLR_ROW_TAIL;
+  if (path_is_tc(path)) return (int64_t)tc_pad_dim(dim) + CROSSCLR_ROW_TAIL;
   set_error("crossclr_feature_pitch: path must be SIMT or TC");
   return CROSSCLR_EINVAL;
 }
 
+int64_t crossclr_segment_rows(int path, int32_t bseg) {
+  if (path == CROSSCLR_PATH_SIMT) return bseg;
+  if (path_is_tc(path)) return tc_pad_rows(bseg);
+  set_error("crossclr_segment_rows: path must be SIMT or TC");
+  return CROSSCLR_EINVAL;
+}
+
 // workspace of the backward: [dfhat | dfhat of the late consumers | flag word block | kernel scratch]
-static size_t ws_flag_offset(const crossclr_problem_t* p) { return 2 * dfhat_bytes(p); }
-static size_t ws_scratch_offset(const crossclr_problem_t* p) { return 2 * dfhat_bytes(p) + 256; }
+static size_t ws_flag_offset(const Geometry& g) { return 2 * dfhat_bytes(g); }
+static size_t ws_scratch_offset(const Geometry& g) { return 2 * dfhat_bytes(g) + 256; }
 static size_t workspace_bytes(const crossclr_problem_t* p, int path) {
-  if (!path_is_tc(path)) return dfhat_bytes(p);
+  const Geometry g = make_geometry(p, path);
+  if (!path_is_tc(path)) return dfhat_bytes(g);
   // + P-tile scratch of the role-specialised backward kernels (cluster rings, or the dataflow kernel's pool + control words)
-  return ws_scratch_offset(p) + std::max(bwd_pair_scratch_bytes(), bwd_flow_scratch_bytes(p->nseg * p->bseg, p->row_count));
+  return ws_scratch_offset(g) + std::max(bwd_pair_scratch_bytes(), bwd_flow_scratch_bytes(g.rows, g.row_count));
 }
 
 size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path) {
@@ -135,7 +146,7 @@ float crossclr_shift(const crossclr_problem_t* p) { return problem_shift(p); }
 const char* crossclr_bwd_kernel_name(const crossclr_problem_t* p, int path) {
   if (validate_problem(p)) return "";
   if (path == CROSSCLR_PATH_SIMT) return "bwd_simt_kernel";
-  if (!path_is_tc(path) || !tc_shape_ok(p)) return "";
+  if (!path_is_tc(path)) return "";
   return bwd_tc_kernel_name(make_geometry(p, path));
 }
 
@@ -167,7 +178,9 @@ int crossclr_forward(const crossclr_problem_t* p, int path, const void* video, c
   if (fdt < 0) return fdt;
   CC_REQUIRE(video && text && feat && rnorm && stats && coef && scal && loss_out, "crossclr_forward: NULL pointer");
   const Geometry g = make_geometry(p, path);
-  if (path_is_tc(path) && tc_shape_ok(p) && fwd_tc_can_finalize(g)) {
+  CC_REQUIRE(!(path_is_tc(path) && problem_needs_row_shift(p)), "temperature %g is below the tensor-core path's range: use "
+             "CROSSCLR_PATH_SIMT (crossclr_choose_path does)", (double)p->temperature);
+  if (path_is_tc(path) && fwd_tc_can_finalize(g)) {
     // three launches become two: pack also zeroes the statistics, the forward's last CTA finalizes
     CC_REQUIRE(p->bseg >= 0 && video_row_stride >= p->dim && text_row_stride >= p->dim, "crossclr_forward: bad shape/stride");
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scal + 3);
@@ -182,7 +195,7 @@ int crossclr_forward(const crossclr_problem_t* p, int path, const void* video, c
   if (rc) return rc;
   rc = crossclr_fwd(p, path, feat, stats, nullptr, 0, stream);
   if (rc) return rc;
-  return crossclr_finalize(p, stats, coef, loss_out, scal, stream);
+  return crossclr_finalize(p, path, stats, coef, loss_out, scal, stream);
 }
 
 int crossclr_fwd(const crossclr_problem_t* p, int path, const void* feat, float* stats, void* workspace,
@@ -193,23 +206,23 @@ int crossclr_fwd(const crossclr_problem_t* p, int path, const void* feat, float*
   CC_REQUIRE(feat && stats, "crossclr_fwd: NULL pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const Geometry g = make_geometry(p, path);
+  CC_REQUIRE(path == CROSSCLR_PATH_SIMT || path_is_tc(path), "crossclr_fwd: path must be SIMT or TC (got %d)", path);
+  CC_REQUIRE(!(path_is_tc(path) && problem_needs_row_shift(p)), "temperature %g is below the tensor-core path's range "
+             "(log2e max(1,|w|)/tau <= %g): use CROSSCLR_PATH_SIMT (crossclr_choose_path does)", (double)p->temperature,
+             (double)kConstShiftMaxLogit);
   // X accumulates with atomics across column ranges: zero the owned rows first
   CC_CHECK_CUDA(cudaMemsetAsync(stats + 2 * (size_t)g.row_begin, 0, 2 * (size_t)g.row_count * sizeof(float), st));
-  if (path_is_tc(path)) {
-    CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
-               p->bseg, p->dim);
-    return launch_fwd_tc(g, feat, stats, st);
-  }
-  CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_fwd: path must be SIMT or TC (got %d)", path);
+  if (path_is_tc(path)) return launch_fwd_tc(g, feat, stats, st);
   return launch_fwd_simt(g, (const float*)feat, stats, st);
 }
 
-int crossclr_finalize(const crossclr_problem_t* p, const float* stats, float* coef, double* loss_out, float* scal,
+int crossclr_finalize(const crossclr_problem_t* p, int path, const float* stats, float* coef, double* loss_out, float* scal,
                       void* stream) {
   int rc = validate_problem(p);
   if (rc) return rc;
   CC_REQUIRE(stats && coef && loss_out && scal, "crossclr_finalize: NULL pointer");
-  return launch_finalize(make_geometry(p), stats, coef, loss_out, scal, (cudaStream_t)stream);
+  CC_REQUIRE(path == CROSSCLR_PATH_SIMT || path_is_tc(path), "crossclr_finalize: path must be SIMT or TC (got %d)", path);
+  return launch_finalize(make_geometry(p, path), stats, coef, loss_out, scal, (cudaStream_t)stream);
 }
 
 // stage 1 of the backward: dfhat (head of the workspace) = sum_j P~ f_j over the owned rows
@@ -221,14 +234,12 @@ static int bwd_accumulate(const crossclr_problem_t* p, int path, const Geometry&
   }
   float* dfhat = (float*)workspace;
   if (path_is_tc(path)) {
-    CC_REQUIRE(tc_shape_ok(p), "tensor-core path needs bseg %% 128 == 0 and dim %% 64 == 0 (bseg %d dim %d)",
-               p->bseg, p->dim);
     bool two = false;
-    int rc = launch_bwd_tc(g, feat, coef, scal, dfhat, (float*)((char*)workspace + dfhat_bytes(p)), &two,
-                           (char*)workspace + ws_scratch_offset(p), st);
+    int rc = launch_bwd_tc(g, feat, coef, scal, dfhat, (float*)((char*)workspace + dfhat_bytes(g)), &two,
+                           (char*)workspace + ws_scratch_offset(g), st);
     if (rc) return rc;
     // the finish stage may run from another call (crossclr_bwd_finish): leave word 0 of the flag block = partial count - 1
-    CC_CHECK_CUDA(cudaMemsetAsync((char*)workspace + ws_flag_offset(p), two ? 1 : 0, 4, st));
+    CC_CHECK_CUDA(cudaMemsetAsync((char*)workspace + ws_flag_offset(g), two ? 1 : 0, 4, st));
     return CROSSCLR_OK;
   }
   CC_REQUIRE(path == CROSSCLR_PATH_SIMT, "crossclr_bwd: path must be SIMT or TC (got %d)", path);
@@ -252,9 +263,10 @@ int crossclr_bwd_finish(const crossclr_problem_t* p, int path, const void* feat,
   CC_REQUIRE(dv_row_stride >= p->dim && dt_row_stride >= p->dim, "crossclr_bwd_finish: output row stride < dim");
   CC_REQUIRE(path == CROSSCLR_PATH_SIMT || path_is_tc(path), "crossclr_bwd_finish: path must be SIMT or TC (got %d)", path);
   const bool tc = path_is_tc(path);
+  const Geometry g = make_geometry(p, path);
   // TC paths: the second partial (late consumers of the dataflow kernel) counts iff the flag word says so (read on device)
-  const float* dfhat2 = tc ? (const float*)((const char*)workspace + dfhat_bytes(p)) : nullptr;
-  return launch_grad_finish(make_geometry(p, path), feat, tc ? CROSSCLR_F16 : CROSSCLR_F32, rnorm_owned, coef, scal, tc, grad_out,
+  const float* dfhat2 = tc ? (const float*)((const char*)workspace + dfhat_bytes(g)) : nullptr;
+  return launch_grad_finish(g, feat, tc ? CROSSCLR_F16 : CROSSCLR_F32, rnorm_owned, coef, scal, tc, grad_out,
                             grad_scale, (const float*)workspace, dv, dv_row_stride, dt, dt_row_stride, out_dtype,
                             (cudaStream_t)stream, dfhat2);
 }

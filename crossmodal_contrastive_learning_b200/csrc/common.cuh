@@ -19,6 +19,10 @@ namespace crossclr {
 constexpr float kEps = 1e-12f;              // F.normalize default eps (trainer/loss.py:79-80)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kShiftHeadroom = 96.0f;     // largest shifted log2-logit we allow: 2^96 * 2^19 rows < 2^127
+// The constant shift keeps every term of a row representable only while the largest possible log2-logit, log2e max(1,|w|)/tau,
+// stays below this (tau >= ~0.0073 at |w| <= 1): beyond it a weakly aligned row flushes to zero as a whole.  Such problems run
+// on the exact path with per-row online maxima in the log2 domain, see Geometry::row_shift.
+constexpr float kConstShiftMaxLogit = 200.0f;
 
 // ---- error reporting -------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -62,10 +66,20 @@ inline int check_launch(const char* what) {
 }
 
 // ---- problem geometry (shared by every kernel) -------------------------------------------------
+// Tensor-core path: every segment is padded to a multiple of 128 rows and every row to a multiple of 64 columns with zeros
+// (crossclr_segment_rows / crossclr_feature_pitch), and nseg, bseg, dim, rows, row_begin, row_count below describe that PADDED
+// layout -- the tile kernels never see a ragged edge.  Zero rows drop out of every product on their own (sum_j P_gj f_j with
+// f_j = 0); what has to know the real extent is the forward's row sums (padded columns are masked in the segment's last
+// 128-column block), finalize (padded rows carry no loss and get coef = 0), pack and grad_finish.
 struct Geometry {
   int nseg, bseg, dim, rows;       // rows = nseg * bseg
   int row_begin, row_count;
+  int bvalid, dvalid, rows_valid;  // the caller's rows per segment, columns, and nseg * bvalid
   int pitch;                       // row pitch of the stacked matrix in elements (dim, or dim + CROSSCLR_ROW_TAIL on the TC path)
+  int row_shift;                   // SIMT path, small temperatures: no common shift; the forward keeps an online (max, sum) per row
+                                   // and stats = (log2 X_g, xpos_g), coef = (log2 Z_g, rho_g); the backward forms
+                                   // 2^(x - log2 Z_g) + 2^(x - log2 Z_j).  Like the reference's max-subtracted float64 softmax
+                                   // (trainer/loss.py:59-60) nothing over- or underflows, whatever the temperature.
   float k_inter;                   // log2e / tau
   float k_intra;                   // w * log2e / tau
   float shift;                     // log2-domain shift
@@ -73,19 +87,31 @@ struct Geometry {
   float w;
 };
 
-inline float problem_shift(const crossclr_problem_t* p) {
-  float wmax = fmaxf(1.0f, fabsf(p->negative_weight));
-  float lmax = kLog2e * wmax / p->temperature;
-  return fmaxf(0.0f, lmax - kShiftHeadroom);
+inline float problem_max_logit(const crossclr_problem_t* p) {
+  return kLog2e * fmaxf(1.0f, fabsf(p->negative_weight)) / p->temperature;
 }
+inline float problem_shift(const crossclr_problem_t* p) { return fmaxf(0.0f, problem_max_logit(p) - kShiftHeadroom); }
+inline bool problem_needs_row_shift(const crossclr_problem_t* p) { return problem_max_logit(p) > kConstShiftMaxLogit; }
 
 inline bool path_is_tc(int path) { return path == CROSSCLR_PATH_TC; }
+
+inline int tc_pad_rows(int bseg) { return (bseg + 127) / 128 * 128; }
+inline int tc_pad_dim(int dim) { return (dim + 63) / 64 * 64; }
 
 inline Geometry make_geometry(const crossclr_problem_t* p, int path = CROSSCLR_PATH_SIMT) {
   Geometry g;
   g.nseg = p->nseg; g.bseg = p->bseg; g.dim = p->dim; g.rows = p->nseg * p->bseg;
   g.row_begin = p->row_begin; g.row_count = p->row_count;
-  g.pitch = path_is_tc(path) ? p->dim + CROSSCLR_ROW_TAIL : p->dim;
+  g.bvalid = p->bseg; g.dvalid = p->dim; g.rows_valid = g.rows;
+  if (path_is_tc(path)) {
+    g.bseg = tc_pad_rows(p->bseg);
+    g.dim = tc_pad_dim(p->dim);
+    g.rows = p->nseg * g.bseg;
+    g.row_begin = p->row_begin / p->bseg * g.bseg;       // owned rows are whole segments (validate_problem)
+    g.row_count = p->row_count / p->bseg * g.bseg;
+  }
+  g.pitch = path_is_tc(path) ? g.dim + CROSSCLR_ROW_TAIL : g.dim;
+  g.row_shift = (path == CROSSCLR_PATH_SIMT && problem_needs_row_shift(p)) ? 1 : 0;
   g.inv_tau = 1.0f / p->temperature;
   g.k_inter = kLog2e / p->temperature;
   g.k_intra = p->negative_weight * kLog2e / p->temperature;

@@ -26,11 +26,25 @@ __device__ __forceinline__ void finalize_block(const Geometry& g, const float* _
   float rho_max = 0.f;
   for (int i = threadIdx.x; i < g.rows; i += blockDim.x) {
     const float2 sx = kThroughL2 ? __ldcg(reinterpret_cast<const float2*>(stats) + i) : reinterpret_cast<const float2*>(stats)[i];
+    if (g.bvalid != g.bseg && (i % g.bseg) >= g.bvalid) {       // zero-padding row: no loss, and a FINITE (zero) coefficient --
+      reinterpret_cast<float2*>(coef)[i] = make_float2(0.f, 0.f);   // the backward multiplies it into zero features
+      continue;
+    }
     const float X = sx.x, xp = sx.y;
-    const float Z = X + exp2f(xp);
-    const float rho = X / Z;
-    reinterpret_cast<float2*>(coef)[i] = make_float2(1.0f / Z, rho);
-    lsum += (double)row_loss_piece(X, xp);
+    float rho;
+    if (g.row_shift) {                                 // stats = (log2 X_g, xpos_g), both absolute
+      const float d = X - xp;                          // log2(X_g / e_pos)
+      const float e = exp2f(-fabsf(d));
+      rho = d > 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);       // X / Z
+      if (d != d) rho = d;
+      reinterpret_cast<float2*>(coef)[i] = make_float2(fmaxf(X, xp) + log2f(1.0f + e), rho);     // (log2 Z_g, rho_g)
+      lsum += (double)(log1pf(e) + (d > 0.f ? 0.6931471805599453f * d : 0.f));                    // log(1 + X / e_pos)
+    } else {
+      const float Z = X + exp2f(xp);
+      rho = X / Z;
+      reinterpret_cast<float2*>(coef)[i] = make_float2(1.0f / Z, rho);
+      lsum += (double)row_loss_piece(X, xp);
+    }
     rho_max = (rho != rho || rho_max != rho_max) ? __int_as_float(0x7fc00000) : fmaxf(rho_max, rho);   // NaN is sticky
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -49,7 +63,7 @@ __device__ __forceinline__ void finalize_block(const Geometry& g, const float* _
       tot += s_sum[w];
       rmax = (s_rho[w] != s_rho[w] || rmax != rmax) ? __int_as_float(0x7fc00000) : fmaxf(rmax, s_rho[w]);
     }
-    loss[0] = tot / (double)g.rows;
+    loss[0] = tot / (double)g.rows_valid;
     // fp16 probability tiles hold sigma * 2^x (1/Z_g + 1/Z_j) kappa <= sigma * 2 rho_max max(1,|w|)
     const float bound = 2.0f * rmax * fmaxf(1.0f, fabsf(g.w));
     int ex = 0;

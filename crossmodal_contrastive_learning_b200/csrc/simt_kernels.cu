@@ -27,18 +27,26 @@ __device__ __forceinline__ void split_rnorm(float norm, float rn, float& pow2, f
   q = rn * exp2f((float)(e - 1));
 }
 
+// Output rows: modality m, row r -> m * rows_pad + r, dimp columns (+ the tail when pitch > dimp).  Rows r >= rows and columns
+// d >= dim are zero padding (tensor-core layout); rnorm is compact: m * rows + r.
 template <typename Tin, typename Tout, bool kRaw>
 __global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ xv, const Tin* __restrict__ xt, int64_t sv,
-                                                  int64_t st_, int rows, int nmod, int dim, Tout* __restrict__ out,
-                                                  int64_t pitch, float* __restrict__ rnorm, float2* __restrict__ stats_zero,
-                                                  unsigned int* __restrict__ ticket_zero) {
+                                                  int64_t st_, int rows, int rows_pad, int nmod, int dim, int dimp,
+                                                  Tout* __restrict__ out, int64_t pitch, float* __restrict__ rnorm,
+                                                  float2* __restrict__ stats_zero, unsigned int* __restrict__ ticket_zero) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= nmod * rows) return;
+  if (row >= nmod * rows_pad) return;
   if (stats_zero != nullptr && lane == 0) stats_zero[row] = make_float2(0.f, 0.f);   // the forward accumulates into it
   if (ticket_zero != nullptr && row == 0 && lane == 0) *ticket_zero = 0u;
-  const Tin* src = row < rows ? xv + (int64_t)row * sv : xt + (int64_t)(row - rows) * st_;
+  const int mod = row >= rows_pad ? 1 : 0, r = row - mod * rows_pad;
   Tout* dst = out + (int64_t)row * pitch;
+  if (r >= rows) {                                             // padding row: zero features, q = 1
+    for (int d = lane; d < dimp; d += 32) dst[d] = from_float<Tout>(0.f);
+    if (lane == 0 && pitch > dimp) *reinterpret_cast<float*>(dst + dimp) = 1.0f;
+    return;
+  }
+  const Tin* src = mod == 0 ? xv + (int64_t)r * sv : xt + (int64_t)r * st_;
   float ss = 0.f;
   for (int d = lane; d < dim; d += 32) {
     const float f = to_float<Tin>(src[d]);
@@ -49,26 +57,33 @@ __global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ xv, c
   const float rn = 1.0f / fmaxf(norm, kEps);
   float mul = rn, q = 1.0f;
   if (kRaw) split_rnorm(norm, rn, mul, q);
-  for (int d = lane; d < dim; d += 32) dst[d] = from_float<Tout>(to_float<Tin>(src[d]) * mul);
+  for (int d = lane; d < dimp; d += 32) dst[d] = from_float<Tout>(d < dim ? to_float<Tin>(src[d]) * mul : 0.f);
   if (lane == 0) {
-    rnorm[row] = rn;
-    if (pitch > dim) *reinterpret_cast<float*>(dst + dim) = q;
+    rnorm[mod * rows + r] = rn;
+    if (pitch > dimp) *reinterpret_cast<float*>(dst + dimp) = q;
   }
 }
 
 // bf16 -> fp16 rows, both modalities of one rank in one launch, 16-byte vectors held in registers between the norm and the
 // scale pass (dim <= 1024, dim % 8 == 0).  The rescale is exact: a power of two.
 __global__ void __launch_bounds__(256) pack2_bf16_raw_kernel(const uint4* __restrict__ xv, const uint4* __restrict__ xt,
-                                                            int64_t sv_vec, int64_t st_vec, int rows, int dim_vec,
-                                                            uint4* __restrict__ out, int64_t pitch_vec, float* __restrict__ rnorm,
-                                                            float2* __restrict__ stats_zero, unsigned int* __restrict__ ticket_zero) {
+                                                            int64_t sv_vec, int64_t st_vec, int rows, int rows_pad, int dim_vec,
+                                                            int dimp_vec, uint4* __restrict__ out, int64_t pitch_vec,
+                                                            float* __restrict__ rnorm, float2* __restrict__ stats_zero,
+                                                            unsigned int* __restrict__ ticket_zero) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= 2 * rows) return;
+  if (row >= 2 * rows_pad) return;
   if (stats_zero != nullptr && lane == 0) stats_zero[row] = make_float2(0.f, 0.f);
   if (ticket_zero != nullptr && row == 0 && lane == 0) *ticket_zero = 0u;
-  const uint4* src = row < rows ? xv + (int64_t)row * sv_vec : xt + (int64_t)(row - rows) * st_vec;
+  const int mod = row >= rows_pad ? 1 : 0, r = row - mod * rows_pad;
   uint4* dst = out + (int64_t)row * pitch_vec;
+  if (r >= rows) {                                             // padding row: zero features, q = 1
+    for (int d = lane; d < dimp_vec; d += 32) dst[d] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0) *reinterpret_cast<float*>(dst + dimp_vec) = 1.0f;
+    return;
+  }
+  const uint4* src = mod == 0 ? xv + (int64_t)r * sv_vec : xt + (int64_t)r * st_vec;
   uint4 u[4];
   float ss = 0.f;
 #pragma unroll
@@ -103,25 +118,28 @@ __global__ void __launch_bounds__(256) pack2_bf16_raw_kernel(const uint4* __rest
         oh[k] = __floats2half2_rn(f.x * mul, f.y * mul);
       }
       dst[d] = o;
+    } else if (d < dimp_vec) {
+      dst[d] = make_uint4(0u, 0u, 0u, 0u);                   // padding columns
     }
   }
   if (lane == 0) {
-    rnorm[row] = rn;
-    *reinterpret_cast<float*>(dst + dim_vec) = q;
+    rnorm[mod * rows + r] = rn;
+    *reinterpret_cast<float*>(dst + dimp_vec) = q;
   }
 }
 
 template <typename Tin>
-static int pack_dispatch(const void* xv, const void* xt, int in_dtype, int64_t sv, int64_t st_, int rows, int nmod, int dim,
+static int pack_dispatch(const void* xv, const void* xt, int64_t sv, int64_t st_, int rows, int nmod, int dim,
                          void* out, int out_dtype, float* rnorm, cudaStream_t st, float* stats_zero, unsigned int* ticket_zero) {
-  dim3 block(256), grid((nmod * rows + 7) / 8);
-  const int64_t pitch = out_dtype == CROSSCLR_F32 ? dim : dim + CROSSCLR_ROW_TAIL;
-#define CC_PACK(Tout, kRaw)                                                                                                \
-  pack_kernel<Tin, Tout, kRaw><<<grid, block, 0, st>>>((const Tin*)xv, (const Tin*)xt, sv, st_, rows, nmod, dim, (Tout*)out, \
-                                                       pitch, rnorm, (float2*)stats_zero, ticket_zero)
+  const bool tc = out_dtype != CROSSCLR_F32;                       // the tensor-core layout is padded (Geometry)
+  const int rows_pad = tc ? tc_pad_rows(rows) : rows, dimp = tc ? tc_pad_dim(dim) : dim;
+  dim3 block(256), grid((nmod * rows_pad + 7) / 8);
+  const int64_t pitch = tc ? dimp + CROSSCLR_ROW_TAIL : dimp;
+#define CC_PACK(Tout, kRaw)                                                                                              \
+  pack_kernel<Tin, Tout, kRaw><<<grid, block, 0, st>>>((const Tin*)xv, (const Tin*)xt, sv, st_, rows, rows_pad, nmod, dim, \
+                                                       dimp, (Tout*)out, pitch, rnorm, (float2*)stats_zero, ticket_zero)
   if (out_dtype == CROSSCLR_F32) CC_PACK(float, false);
-  else if (out_dtype == CROSSCLR_F16 && in_dtype != CROSSCLR_F32) CC_PACK(__half, true);     // 16-bit inputs: exact rescale
-  else if (out_dtype == CROSSCLR_F16) CC_PACK(__half, false);
+  else if (out_dtype == CROSSCLR_F16) CC_PACK(__half, true);     // power-of-two rescale: exact for 16-bit-representable values
   else { set_error("crossclr_pack: unsupported stacked dtype %d", out_dtype); return CROSSCLR_EINVAL; }
 #undef CC_PACK
   return check_launch("pack_kernel");
@@ -133,16 +151,17 @@ static int pack_any(const void* xv, const void* xt, int in_dtype, int64_t sv, in
   TimedLaunch timed(CROSSCLR_K_PACK, st);
   if (nmod == 2 && in_dtype == CROSSCLR_BF16 && out_dtype == CROSSCLR_F16 && dim % 8 == 0 && dim <= 1024 && sv % 8 == 0 &&
       st_ % 8 == 0 && ((uintptr_t)xv % 16 == 0) && ((uintptr_t)xt % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
-    dim3 block(256), grid((2 * rows + 7) / 8);
-    pack2_bf16_raw_kernel<<<grid, block, 0, st>>>((const uint4*)xv, (const uint4*)xt, sv / 8, st_ / 8, rows, dim / 8,
-                                                  (uint4*)out, (dim + CROSSCLR_ROW_TAIL) / 8, rnorm, (float2*)stats_zero,
-                                                  ticket_zero);
+    const int rows_pad = tc_pad_rows(rows), dimp = tc_pad_dim(dim);
+    dim3 block(256), grid((2 * rows_pad + 7) / 8);
+    pack2_bf16_raw_kernel<<<grid, block, 0, st>>>((const uint4*)xv, (const uint4*)xt, sv / 8, st_ / 8, rows, rows_pad, dim / 8,
+                                                  dimp / 8, (uint4*)out, (dimp + CROSSCLR_ROW_TAIL) / 8, rnorm,
+                                                  (float2*)stats_zero, ticket_zero);
     return check_launch("pack2_bf16_raw_kernel");
   }
   switch (in_dtype) {
-    case CROSSCLR_F32: return pack_dispatch<float>(xv, xt, in_dtype, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
-    case CROSSCLR_F16: return pack_dispatch<__half>(xv, xt, in_dtype, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
-    case CROSSCLR_BF16: return pack_dispatch<__nv_bfloat16>(xv, xt, in_dtype, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
+    case CROSSCLR_F32: return pack_dispatch<float>(xv, xt, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
+    case CROSSCLR_F16: return pack_dispatch<__half>(xv, xt, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
+    case CROSSCLR_BF16: return pack_dispatch<__nv_bfloat16>(xv, xt, sv, st_, rows, nmod, dim, out, out_dtype, rnorm, st, stats_zero, ticket_zero);
     default: set_error("crossclr_pack: unsupported input dtype %d", in_dtype); return CROSSCLR_EINVAL;
   }
 }
@@ -163,6 +182,24 @@ int launch_pack(const void* x, int in_dtype, int64_t stride, int rows, int dim, 
 constexpr int FT = 64;   // tile rows == tile cols
 constexpr int FK = 16;   // k chunk
 
+// log2(2^a + 2^b); -inf is the empty sum
+__device__ __forceinline__ float logaddexp2(float a, float b) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  return lo == -INFINITY ? hi : hi + log2f(1.0f + exp2f(lo - hi));
+}
+// merge a partial log2-sum into *addr (CAS loop: a handful of partials per row)
+__device__ __forceinline__ void atomic_logaddexp2(float* addr, float l) {
+  int* ai = reinterpret_cast<int*>(addr);
+  int old = *ai, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(ai, assumed, __float_as_int(logaddexp2(__int_as_float(assumed), l)));
+  } while (old != assumed);
+}
+
+// kRowShift (Geometry::row_shift): every thread keeps a running (max, sum 2^(x - max)) per row -- an online softmax -- and the
+// row's partials merge in the log2 domain, so nothing over- or underflows whatever the temperature: stats[g] = (log2 X_g, xpos_g).
+template <bool kRowShift>
 __global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* __restrict__ F,
                                                       float* __restrict__ stats, int col_tiles_per_block) {
   __shared__ float As[FK][FT + 4];
@@ -175,7 +212,7 @@ __global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* 
   const int ct1 = min(n_col_tiles, ct0 + col_tiles_per_block);
 
   int gi[4], mod_i[4], samp_i[4];
-  float rsum[4];
+  float rsum[4], rmax[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     gi[r] = row0 + ty * 4 + r;
@@ -184,8 +221,13 @@ __global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* 
     mod_i[r] = row_modality(gg, g.bseg);
     samp_i[r] = row_sample(gg, g.bseg);
     rsum[r] = 0.f;
+    rmax[r] = -INFINITY;
     if (!ok) gi[r] = -1;
   }
+  auto online_add = [&](int r, float x) {        // rsum[r] 2^rmax[r] += 2^x
+    if (x > rmax[r]) { rsum[r] = fmaf(rsum[r], exp2f(rmax[r] - x), 1.0f); rmax[r] = x; }
+    else rsum[r] += exp2f(x - rmax[r]);
+  };
 
   for (int ct = ct0; ct < ct1; ++ct) {
     const int col0 = ct * FT;
@@ -231,10 +273,13 @@ __global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* 
         if (gi[r] < 0) continue;
         const bool same_mod = (mod_i[r] == mod_j);
         const float k = same_mod ? g.k_intra : g.k_inter;
-        const float x = fmaf(acc[r][c], k, -g.shift);
+        const float x = kRowShift ? acc[r][c] * k : fmaf(acc[r][c], k, -g.shift);
         if (samp_i[r] == samp_j) {
-          if (same_mod) rsum[r] += exp2f(-g.shift);   // masked intra-modal diagonal: logit 0 (loss.py:65,96-97)
-          else stats[2 * (int64_t)gi[r] + 1] = x;     // the positive logit a_ii (loss.py:102-109)
+          if (!same_mod) stats[2 * (int64_t)gi[r] + 1] = x;   // the positive logit a_ii (loss.py:102-109)
+          else if (kRowShift) online_add(r, 0.f);          // masked intra-modal diagonal: logit 0 (loss.py:65,96-97)
+          else rsum[r] += exp2f(-g.shift);
+        } else if (kRowShift) {
+          online_add(r, x);
         } else {
           rsum[r] += exp2f(x);
         }
@@ -243,6 +288,13 @@ __global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* 
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
+    if (kRowShift) {
+      float l = rsum[r] > 0.f ? rmax[r] + log2f(rsum[r]) : -INFINITY;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) l = logaddexp2(l, __shfl_xor_sync(0xffffffffu, l, o));
+      if (tx == 0 && gi[r] >= 0 && l != -INFINITY) atomic_logaddexp2(&stats[2 * (int64_t)gi[r]], l);
+      continue;
+    }
     float v = rsum[r];
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -252,15 +304,27 @@ __global__ void __launch_bounds__(256) fwd_simt_kernel(Geometry g, const float* 
   }
 }
 
+// Row-shift mode: the log2-domain accumulators start at the empty sum.
+__global__ void row_shift_init_kernel(Geometry g, float2* __restrict__ stats) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < g.row_count) stats[g.row_begin + l] = make_float2(-INFINITY, 0.f);
+}
+
 int launch_fwd_simt(const Geometry& g, const float* feat, float* stats, cudaStream_t st) {
   TimedLaunch timed(CROSSCLR_K_FWD, st);
+  if (g.row_shift) {
+    row_shift_init_kernel<<<(g.row_count + 255) / 256, 256, 0, st>>>(g, reinterpret_cast<float2*>(stats));
+    int rc = check_launch("row_shift_init_kernel");
+    if (rc) return rc;
+  }
   const int row_tiles = (g.row_count + FT - 1) / FT;
   const int n_col_tiles = (g.rows + FT - 1) / FT;
   int splits = max(1, min(n_col_tiles, (2 * 148 + row_tiles - 1) / row_tiles));
   int per = (n_col_tiles + splits - 1) / splits;
   splits = (n_col_tiles + per - 1) / per;
   dim3 grid(row_tiles, splits), block(256);
-  fwd_simt_kernel<<<grid, block, 0, st>>>(g, feat, stats, per);
+  if (g.row_shift) fwd_simt_kernel<true><<<grid, block, 0, st>>>(g, feat, stats, per);
+  else fwd_simt_kernel<false><<<grid, block, 0, st>>>(g, feat, stats, per);
   return check_launch("fwd_simt_kernel");
 }
 
@@ -332,8 +396,13 @@ __global__ void __launch_bounds__(256) bwd_simt_kernel(Geometry g, const float* 
         if (jok && gi[r] >= 0 && samp_i[r] != samp_j) {
           const bool same_mod = (mod_i[r] == mod_j);
           const float k = same_mod ? g.k_intra : g.k_inter;
-          const float x = fmaf(s[r], k, -g.shift);
-          p = exp2f(x) * (iz_i[r] + iz_j) * (same_mod ? g.w : 1.0f);
+          if (g.row_shift) {                          // coef[.,0] = log2 Z: two exponentials, each against its own row's Z
+            const float x = s[r] * k;
+            p = (exp2f(x - iz_i[r]) + exp2f(x - iz_j)) * (same_mod ? g.w : 1.0f);
+          } else {
+            const float x = fmaf(s[r], k, -g.shift);
+            p = exp2f(x) * (iz_i[r] + iz_j) * (same_mod ? g.w : 1.0f);
+          }
         }
         Ps[tys * 4 + r][txs] = p;
       }
@@ -408,8 +477,10 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   const int lane = threadIdx.x & 31;
   if (l >= g.row_count) return;
   const int gr = g.row_begin + l;
+  const int r = gr % g.bseg;
+  if (r >= g.bvalid) return;                   // zero-padding row of the tensor-core layout
   const int pg = row_partner(gr, g.bseg);
-  const float rn_g = rn[l];                    // reciprocal norms of the OWNED rows only
+  const float rn_g = rn[(l / g.bseg) * g.bvalid + r];   // reciprocal norms of the OWNED rows only, compact
   const float* dh2 = (dfhat2 != nullptr && two != nullptr && *two != 0u) ? dfhat2 + (int64_t)l * g.dim : nullptr;
   const TF* fg = F + (int64_t)gr * g.pitch;
   const TF* fp = F + (int64_t)pg * g.pitch;
@@ -425,13 +496,12 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   }
   dot = warp_sum(dot) * qg * qg;        // (h . Fhat_g) Fhat_g with Fhat_g = q_g f_g
   if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
-  double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows;
+  double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows_valid;
   if (grad_out != nullptr) m *= grad_out[0];
   const float mult = (float)m * rn_g;
   const int mod = row_modality(gr, g.bseg);
-  const int r = gr % g.bseg;
   TO* out = mod == 0 ? dv + (int64_t)r * dv_stride : dt + (int64_t)r * dt_stride;
-  for (int d = lane; d < g.dim; d += 32) {
+  for (int d = lane; d < g.dvalid; d += 32) {
     const float acc = dh2 ? dh[d] + dh2[d] : dh[d];
     const float h = acc * acc_scale + pos_coef * to_float<TF>(fp[d]);
     out[d] = from_float<TO>(mult * (h - dot * to_float<TF>(fg[d])));
@@ -458,8 +528,10 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
   const int lane = threadIdx.x & 31;
   if (l >= g.row_count) return;
   const int gr = g.row_begin + l;
+  const int r = gr % g.bseg;
+  if (r >= g.bvalid) return;                   // zero-padding row
   const int pg = row_partner(gr, g.bseg);
-  const float rn_g = rn[l];
+  const float rn_g = rn[(l / g.bseg) * g.bvalid + r];
   const TF* rowg = F + (int64_t)gr * g.pitch;
   const TF* rowp = F + (int64_t)pg * g.pitch;
   const float qg = *reinterpret_cast<const float*>(rowg + g.dim), qp = *reinterpret_cast<const float*>(rowp + g.dim);
@@ -497,11 +569,10 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(Geometry g, const 
   }
   dot = warp_sum(dot) * qg * qg;        // (h . Fhat_g) Fhat_g with Fhat_g = q_g f_g
   if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
-  double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows;
+  double m = (double)g.inv_tau * (double)grad_scale / (double)g.rows_valid;
   if (grad_out != nullptr) m *= grad_out[0];
   const float mult = (float)m * rn_g;
   const int mod = row_modality(gr, g.bseg);
-  const int r = gr % g.bseg;
   TO* out = mod == 0 ? dv + (int64_t)r * dv_stride : dt + (int64_t)r * dt_stride;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -524,7 +595,7 @@ static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rn
                             const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, cudaStream_t st,
                             const float* dfhat2, const unsigned int* two) {
   const size_t osz = sizeof(TO);
-  if (g.dim % 256 != 0 || g.dim > 1024 || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
+  if (g.dim % 256 != 0 || g.dim > 1024 || g.dvalid != g.dim || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
       (dvs * osz) % 16 != 0 || (dts * osz) % 16 != 0 || (g.pitch * sizeof(TF)) % 16 != 0)
     return false;
   dim3 block(256), grid((g.row_count + 7) / 8);

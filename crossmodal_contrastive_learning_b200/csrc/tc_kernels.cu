@@ -58,19 +58,22 @@ __device__ __forceinline__ void fwd_sum_chunk(const uint32_t (&v)[32], float kq,
   unpack2(rs23, rs[2], rs[3]);
 }
 
-// The 32-column chunk that holds the same-sample column (column r & 31 of the chunk): the masked intra-modal diagonal
-// counts as logit 0 (trainer/loss.py:65,96-97); the positive is kept out of X and written to stats[.,1].
-__device__ __forceinline__ void fwd_diag_chunk(const uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
-                                               bool same_mod, float diag_term, int r, int gi, float* __restrict__ stats,
-                                               float (&rs)[4]) {
+// A 32-column chunk that needs per-column care (scalar code; a few chunks per row block):
+//  * it holds the same-sample column dq (>= 0): the masked intra-modal diagonal counts as logit 0
+//    (trainer/loss.py:65,96-97); the positive is kept out of X and written to stats[.,1];
+//  * only its first nv columns are real rows -- the rest is the zero padding at the end of a segment (Geometry) and adds nothing.
+__device__ __forceinline__ void fwd_special_chunk(const uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
+                                                  bool same_mod, float diag_term, int dq, int nv, int gi,
+                                                  float* __restrict__ stats, float (&rs)[4]) {
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
     const float x = fmaf(__uint_as_float(v[q]) * kq, qc[q], nshift);
     float e = fast_exp2(x);
-    if (q == (r & 31)) {
+    if (q == dq) {
       if (same_mod) e = diag_term;
       else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; }
     }
+    if (q >= nv) e = 0.f;
     rs[q & 3] += e;
   }
 }
@@ -138,17 +141,18 @@ __device__ __forceinline__ void fwd_sum_chunk_keep(uint32_t (&v)[32], float kq, 
   unpack2(rs01, rs[0], rs[1]);
   unpack2(rs23, rs[2], rs[3]);
 }
-__device__ __forceinline__ void fwd_diag_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
-                                                    bool same_mod, float diag_term, int r, int gi, int partner,
-                                                    float* __restrict__ stats, float (&rs)[4]) {
+__device__ __forceinline__ void fwd_special_chunk_keep(uint32_t (&v)[32], float kq, float nshift, const float* __restrict__ qc,
+                                                       bool same_mod, float diag_term, int dq, int nv, int gi, int partner,
+                                                       float* __restrict__ stats, float (&rs)[4]) {
 #pragma unroll
   for (int q = 0; q < 32; ++q) {
     const float x = fmaf(__uint_as_float(v[q]) * kq, qc[q], nshift);
     float e = fast_exp2(x);
-    if (q == (r & 31)) {
+    if (q == dq) {
       if (same_mod) e = diag_term;
       else { e = 0.f; stats[2 * (int64_t)gi + 1] = x; stats[2 * (int64_t)partner + 1] = x; }   // the mirrored tile is skipped
     }
+    if (q >= nv) e = 0.f;
     rs[q & 3] += e;
     v[q] = __float_as_uint(e);
   }
@@ -343,7 +347,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     float rs[4] = {0.f, 0.f, 0.f, 0.f};
     float q_i = 1.f;
     const float k_diag_term = fast_exp2(-g.shift);
-    const float nshift = -g.shift;
+    float nshift = -g.shift;                       // -inf for a zero-padding row: all its exponentials are 0
     const uint32_t tempty_ldr = mapa_cluster(tempty_bar(gsel), 0);
     // running tile coordinates (no divisions in the loop): row-block pair ib, column block jb, and the segment / offset
     // of this warp's half of the column block
@@ -361,7 +365,9 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         gi = row0 + r;
         bi = block_seg(row0, g.bseg);
         q_i = row_q(feat, g, gi);
+        nshift = (gi % g.bseg) < g.bvalid ? -g.shift : -INFINITY;
       }
+      const int ncv = g.bvalid - joff;                               // real columns in this half (>= TM: all of them)
       const bool same_mod = ((jseg & 1) == bi.mod);
       const bool diag_tile = ((jseg >> 1) * g.bseg + joff == bi.samp0);
       const float k = (same_mod ? g.k_intra : g.k_inter) * q_i;      // row part of the logit scale
@@ -390,17 +396,19 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         if (exp_flags & 1) continue;
         // the same-sample column r of a diagonal half sits in its 32-column chunk r >> 5 = quad
         const float* const qc = qv + c * 64;
+        const int nva = ncv - c * 64, nvb = nva - 32;
+        const bool dga = diag_tile && quad == 2 * c, dgb = diag_tile && quad == 2 * c + 1;
         if (!col_sums) {
-          if (!diag_tile || quad != 2 * c) fwd_sum_chunk(va, k, nshift, reinterpret_cast<const float4*>(qc), rs);
-          else fwd_diag_chunk(va, k, nshift, qc, same_mod, k_diag_term, r, gi, stats, rs);
-          if (!diag_tile || quad != 2 * c + 1) fwd_sum_chunk(vb, k, nshift, reinterpret_cast<const float4*>(qc + 32), rs);
-          else fwd_diag_chunk(vb, k, nshift, qc + 32, same_mod, k_diag_term, r, gi, stats, rs);
+          if (!dga && nva >= 32) fwd_sum_chunk(va, k, nshift, reinterpret_cast<const float4*>(qc), rs);
+          else fwd_special_chunk(va, k, nshift, qc, same_mod, k_diag_term, dga ? (r & 31) : -1, nva, gi, stats, rs);
+          if (!dgb && nvb >= 32) fwd_sum_chunk(vb, k, nshift, reinterpret_cast<const float4*>(qc + 32), rs);
+          else fwd_special_chunk(vb, k, nshift, qc + 32, same_mod, k_diag_term, dgb ? (r & 31) : -1, nvb, gi, stats, rs);
         } else {
           const int partner = row_partner(gi, g.bseg);
-          if (!diag_tile || quad != 2 * c) fwd_sum_chunk_keep(va, k, nshift, reinterpret_cast<const float4*>(qc), rs);
-          else fwd_diag_chunk_keep(va, k, nshift, qc, same_mod, k_diag_term, r, gi, partner, stats, rs);
-          if (!diag_tile || quad != 2 * c + 1) fwd_sum_chunk_keep(vb, k, nshift, reinterpret_cast<const float4*>(qc + 32), rs);
-          else fwd_diag_chunk_keep(vb, k, nshift, qc + 32, same_mod, k_diag_term, r, gi, partner, stats, rs);
+          if (!dga && nva >= 32) fwd_sum_chunk_keep(va, k, nshift, reinterpret_cast<const float4*>(qc), rs);
+          else fwd_special_chunk_keep(va, k, nshift, qc, same_mod, k_diag_term, dga ? (r & 31) : -1, nva, gi, partner, stats, rs);
+          if (!dgb && nvb >= 32) fwd_sum_chunk_keep(vb, k, nshift, reinterpret_cast<const float4*>(qc + 32), rs);
+          else fwd_special_chunk_keep(vb, k, nshift, qc + 32, same_mod, k_diag_term, dgb ? (r & 31) : -1, nvb, gi, partner, stats, rs);
           // the mirrored tile (jb, ib) is never computed: its row sums are this tile's column sums
           if (!(exp_flags & 16)) {
             float c0, c1;

@@ -74,12 +74,19 @@ class _NativeOps:
     def __init__(self):
         self.lib = N.load()
 
-    def plan(self, prob, in_dtype, exact):
+    def plan(self, prob, in_dtype, exact, force_tc=False):
         """(path code, stacked-row dtype, stacked-row pitch in elements) the library picks for this problem."""
-        code = self.lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[in_dtype], 1 if exact else 0)
-        if code < 0:
-            N.check(code, "crossclr_choose_path")
+        if force_tc:
+            code = N.PATH_TC          # any shape (zero padding); a temperature outside its range is refused at launch
+        else:
+            code = self.lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[in_dtype], 1 if exact else 0)
+            if code < 0:
+                N.check(code, "crossclr_choose_path")
         return code, _FEAT_TORCH[self.lib.crossclr_feature_dtype(code)], int(self.lib.crossclr_feature_pitch(code, prob.dim))
+
+    def seg_rows(self, code, bseg):
+        """Rows per segment of the stacked matrix / stats / coef of a path (the tensor-core layout pads segments to 128 rows)."""
+        return int(self.lib.crossclr_segment_rows(code, bseg))
 
     def pack(self, x, feat_out, rnorm_out):
         B, D = x.shape
@@ -102,8 +109,8 @@ class _NativeOps:
         N.check(self.lib.crossclr_fwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(stats), None, 0, _stream()),
                 "crossclr_fwd")
 
-    def finalize(self, prob, stats, coef, loss, scal):
-        N.check(self.lib.crossclr_finalize(ctypes.byref(prob), _ptr(stats), _ptr(coef), _ptr(loss), _ptr(scal),
+    def finalize(self, prob, code, stats, coef, loss, scal):
+        N.check(self.lib.crossclr_finalize(ctypes.byref(prob), code, _ptr(stats), _ptr(coef), _ptr(loss), _ptr(scal),
                                            _stream()), "crossclr_finalize")
 
     def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt):
@@ -130,11 +137,10 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     dev = v.device
     world, rank = _group_info(group)
     prob = N.Problem(2 * world, B, D, 2 * rank * B, 2 * B, float(temperature), float(negative_weight))
-    code, feat_dtype, pitch = ops.plan(prob, v.dtype, path == "simt")
-    if path == "tc" and code != N.PATH_TC:
-        raise RuntimeError(f"tensor-core path needs B % 128 == 0 and D % 64 == 0 (got B={B}, D={D})")
-    rows = 2 * world * B
-    feat_all = torch.empty((2 * world, B, pitch), dtype=feat_dtype, device=dev)
+    code, feat_dtype, pitch = ops.plan(prob, v.dtype, path == "simt", path == "tc")
+    S = ops.seg_rows(code, B)                                   # rows per segment in the path's layout (>= B: zero padding)
+    rows = 2 * world * S
+    feat_all = torch.empty((2 * world, S, pitch), dtype=feat_dtype, device=dev)
     rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
     stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
     coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)          # separate allocations: the custom op returns
@@ -149,8 +155,8 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     # in-place all-gather: rank r's block already sits at its slot of the output
     dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1), group=group)
     ops.fwd(prob, code, feat_all, stats)
-    dist.all_gather_into_tensor(stats.view(-1), stats[2 * rank * B:2 * (rank + 1) * B].reshape(-1), group=group)
-    ops.finalize(prob, stats, coef, loss, scal)
+    dist.all_gather_into_tensor(stats.view(-1), stats[2 * rank * S:2 * (rank + 1) * S].reshape(-1), group=group)
+    ops.finalize(prob, code, stats, coef, loss, scal)
     return loss, prob, code, (feat_all, rnorm, coef, scal)
 
 
@@ -210,11 +216,14 @@ class _CrossCLRFunction(torch.autograd.Function):
 _OUT_DTYPE = {0: torch.float32, 1: torch.float16, 2: torch.bfloat16}
 
 
-def _plan_py(B, D, path, in_dtype):
-    """The path libcrossclr_b200 picks for a single-rank problem, asked of the library itself (crossclr_choose_path is a pure
-    function of the shape and dtype: no device needed), so that shape inference can never drift from the kernels' rule."""
-    prob = N.Problem(2, B, D, 0, 2 * B, 1.0, 1.0)
-    return _ops().plan(prob, torch.float32 if in_dtype == torch.float64 else in_dtype, path == "simt")
+def _plan_py(B, D, path, in_dtype, temperature, negative_weight):
+    """(dtype, pitch, segment rows) of the stacked matrix libcrossclr_b200 uses for a single-rank problem, asked of the library
+    itself (pure functions of the problem and dtype: no device needed), so that shape inference can never drift from the
+    kernels' rule."""
+    prob = N.Problem(2, B, D, 0, 2 * B, float(temperature), float(negative_weight))
+    ops = _ops()
+    code, fdt, pitch = ops.plan(prob, torch.float32 if in_dtype == torch.float64 else in_dtype, path == "simt", path == "tc")
+    return fdt, pitch, ops.seg_rows(code, B)
 
 
 @torch.library.custom_op("crossclr_b200::forward", mutates_args=())
@@ -230,10 +239,10 @@ def _op_forward(video: torch.Tensor, text: torch.Tensor, temperature: float, neg
 @_op_forward.register_fake
 def _(video, text, temperature, negative_weight, path):
     B, D = video.shape
-    _, fdt, pitch = _plan_py(B, D, path, video.dtype)
+    fdt, pitch, S = _plan_py(B, D, path, video.dtype, temperature, negative_weight)
     dev = video.device
-    return (torch.empty((), dtype=torch.float64, device=dev), torch.empty((2, B, pitch), dtype=fdt, device=dev),
-            torch.empty(2 * B, dtype=torch.float32, device=dev), torch.empty((2 * B, 2), dtype=torch.float32, device=dev),
+    return (torch.empty((), dtype=torch.float64, device=dev), torch.empty((2, S, pitch), dtype=fdt, device=dev),
+            torch.empty(2 * B, dtype=torch.float32, device=dev), torch.empty((2 * S, 2), dtype=torch.float32, device=dev),
             torch.empty(4, dtype=torch.float32, device=dev))
 
 

@@ -23,6 +23,7 @@ int main(void) {
   if (path < 0) { fprintf(stderr, "%s\n", crossclr_last_error()); return 1; }
   const size_t fsz = crossclr_feature_dtype(path) == CROSSCLR_F32 ? 4 : 2;
   const size_t pitch = (size_t)crossclr_feature_pitch(path, D);      /* stacked rows carry a tail on the tensor-core paths */
+  const size_t S = (size_t)crossclr_segment_rows(path, B);           /* and segments are padded to a multiple of 128 rows */
 
   float* h = (float*)malloc((size_t)2 * B * D * sizeof(float));
   unsigned s = 12345u;
@@ -33,8 +34,8 @@ int main(void) {
   double* loss;
   const size_t ws_bytes = crossclr_workspace_bytes(&p, path);
   CK(cudaMalloc((void**)&video, (size_t)B * D * 4)); CK(cudaMalloc((void**)&text, (size_t)B * D * 4));
-  CK(cudaMalloc(&feat, (size_t)2 * B * pitch * fsz));   CK(cudaMalloc((void**)&rnorm, (size_t)2 * B * 4));
-  CK(cudaMalloc((void**)&stats, (size_t)2 * B * 8));  CK(cudaMalloc((void**)&coef, (size_t)2 * B * 8));
+  CK(cudaMalloc(&feat, 2 * S * pitch * fsz));   CK(cudaMalloc((void**)&rnorm, (size_t)2 * B * 4));
+  CK(cudaMalloc((void**)&stats, 2 * S * 8));  CK(cudaMalloc((void**)&coef, 2 * S * 8));
   CK(cudaMalloc((void**)&scal, 16));                  CK(cudaMalloc((void**)&loss, 8));
   CK(cudaMalloc((void**)&dv, (size_t)B * D * 4));     CK(cudaMalloc((void**)&dt, (size_t)B * D * 4));
   CK(cudaMalloc(&ws, ws_bytes));

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CROSSCLR_VERSION 120          /* 0.1.2 */
+#define CROSSCLR_VERSION 130          /* 0.1.3 */
 
 /* error codes */
 #define CROSSCLR_OK            0
@@ -49,13 +49,20 @@ extern "C" {
 #define CROSSCLR_BF16 2
 
 /* kernel families ("path") */
-#define CROSSCLR_PATH_AUTO 0          /* tensor-core path when the shape allows it, else SIMT        */
+#define CROSSCLR_PATH_AUTO 0          /* crossclr_choose_path decides                                 */
 #define CROSSCLR_PATH_SIMT 1          /* fp32 CUDA-core kernels, any B / D, fp32 stacked features     */
-#define CROSSCLR_PATH_TC   2          /* tcgen05 + TMA + TMEM kernels, fp16 stacked rows,
-                                         requires bseg % 128 == 0 and dim % 64 == 0                   */
+#define CROSSCLR_PATH_TC   2          /* tcgen05 + TMA + TMEM kernels, fp16 stacked rows, any B / D:
+                                         segments are zero-padded to 128 rows, rows to 64 columns     */
 
-/* Stacked rows of the tensor-core path.  Row g is stored as f_g with a row pitch of dim + CROSSCLR_ROW_TAIL elements;
- * the first 4 bytes of the tail hold the fp32 residual scale q_g, and the L2-normalised row is q_g * f_g.
+/* Stacked rows of the tensor-core path.  The layout is PADDED: every segment holds crossclr_segment_rows(path, bseg) =
+ * roundup(bseg, 128) rows, of which the first bseg are the caller's and the rest are zero rows (q = 1), and every row holds
+ * roundup(dim, 64) feature columns (zeros beyond dim) followed by the tail: the row pitch is
+ * crossclr_feature_pitch(path, dim) = roundup(dim, 64) + CROSSCLR_ROW_TAIL elements.  stats and coef are indexed by PADDED
+ * stacked row (nseg * crossclr_segment_rows rows; padded rows hold no statistics and coef = 0), rnorm and the gradients by
+ * the caller's rows.  A shape with bseg % 128 == 0 and dim % 64 == 0 has no padding at all.  Zero rows drop out of every
+ * product; the forward masks them out of the row sums.  (Reference: trainer/loss.py:83-88 takes any [B, D].)
+ * Row g is stored as f_g; the first 4 bytes of the tail hold the fp32 residual scale q_g, and the L2-normalised row is
+ * q_g * f_g.
  *   16-bit inputs: f_g = x_g * 2^-e (EXACT: a power-of-two rescale into ||f|| in [1, 2), stored as fp16 -- a bf16 value
  *                  below 2 is exactly representable in fp16 down to 2^-17), q_g = 2^e / ||x_g|| in (1/2, 1]; rows inside the
  *                  eps clamp (||x|| < 1e-12) are stored as in the fp32 case.
@@ -63,8 +70,9 @@ extern "C" {
  *                  epilogue as q_i q_j (f_i . f_j): no operand rounding at all (gradients ~1e-5 of the reference).
  *                  (kind::f16 MMAs need A and B of one format and the probability operand must be fp16 -- bf16 would
  *                  cost 1.6e-3 on the gradients -- hence fp16 rows for bf16 inputs too.)
- *   fp32 inputs:   f_g = fp16(x_g / max(||x_g||, 1e-12)), q_g = 1 (operand rounding 2^-12: gradients within ~2e-5 / tau).
- * The SIMT path keeps plain fp32 normalised rows, pitch dim, no tail. */
+ *   fp32 inputs:   the same rescale, then rounded to fp16 (operand rounding 2^-12: gradients within ~2e-5 / tau of the
+ *                  reference; exact again if the values happen to be 16-bit representable).
+ * The SIMT path keeps plain fp32 normalised rows, pitch dim, bseg rows per segment, no tail. */
 #define CROSSCLR_ROW_TAIL 64
 
 typedef struct crossclr_problem {
@@ -83,15 +91,24 @@ CROSSCLR_API const char* crossclr_last_error(void);
 /* 1 if `device` can run this library (compute capability 10.x), 0 otherwise, <0 on error. */
 CROSSCLR_API int crossclr_device_supported(int device);
 
-/* Resolve CROSSCLR_PATH_AUTO for a problem and input dtype: CROSSCLR_PATH_TC when the shape allows it, else
- * CROSSCLR_PATH_SIMT.  exact != 0 forces the fp32 SIMT path. */
+/* Resolve CROSSCLR_PATH_AUTO for a problem and input dtype: CROSSCLR_PATH_TC when the temperature allows it and the shape
+ * is not so small that the zero padding would dominate (bseg >= 96 and dim >= 48), else CROSSCLR_PATH_SIMT.  exact != 0
+ * forces the fp32 SIMT path.
+ * Temperature: the TC kernels use ONE log2-domain shift for all rows, which keeps every row representable while
+ * log2e * max(1,|w|) / tau <= 200 (tau >= ~0.0073 at |w| <= 1); they return CROSSCLR_EINVAL beyond.  The SIMT path switches to
+ * per-row online maxima in the log2 domain there and follows the reference's max-subtracted float64 softmax
+ * (trainer/loss.py:59-60) at any temperature; in that mode stats[2g+0] = log2 X_g (not X_g / 2^shift) and
+ * coef[2g+0] = log2 Z_g (not 1 / Z_g). */
 CROSSCLR_API int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact);
 
 /* Stacked-row element type a path consumes: SIMT -> CROSSCLR_F32, TC -> CROSSCLR_F16. */
 CROSSCLR_API int crossclr_feature_dtype(int path);
 
-/* Row pitch (in elements) of the stacked matrix of a path: dim for SIMT, dim + CROSSCLR_ROW_TAIL for TC. */
+/* Row pitch (in elements) of the stacked matrix of a path: dim for SIMT, roundup(dim, 64) + CROSSCLR_ROW_TAIL for TC. */
 CROSSCLR_API int64_t crossclr_feature_pitch(int path, int32_t dim);
+
+/* Rows per segment of the stacked matrix (and of stats / coef) of a path: bseg for SIMT, roundup(bseg, 128) for TC. */
+CROSSCLR_API int64_t crossclr_segment_rows(int path, int32_t bseg);
 
 /* Bytes of scratch crossclr_bwd needs for this problem and path (crossclr_fwd needs none). */
 CROSSCLR_API size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int path);
@@ -100,7 +117,8 @@ CROSSCLR_API size_t crossclr_workspace_bytes(const crossclr_problem_t* p, int pa
  * L2-normalise one modality block `x` ([rows][dim], element stride 1, row stride `x_row_stride`
  * elements, dtype `in_dtype`) into its segment of the stacked matrix: `feat_out` points at the first
  * row of that segment (dtype `feat_dtype`; CROSSCLR_F32: row stride dim, receives x / max(||x||_2, 1e-12);
- * CROSSCLR_F16 / CROSSCLR_BF16: row stride dim + CROSSCLR_ROW_TAIL, receives (f, q) as described above);
+ * CROSSCLR_F16: the padded TC layout -- roundup(rows, 128) rows of pitch roundup(dim, 64) + CROSSCLR_ROW_TAIL are written,
+ * (f, q) as described above and zeros for the padding);
  * `rnorm_out[rows]` receives 1 / max(||x||_2, 1e-12) (kept by the caller for the backward).
  * Replaces: trainer/loss.py:79-80 (F.normalize x2).
  */
@@ -109,7 +127,8 @@ CROSSCLR_API int crossclr_pack(const void* x, int in_dtype, int64_t x_row_stride
 
 /*
  * Both modality blocks of one rank in one launch: rows of `video` then rows of `text` are normalised into the
- * rank's two consecutive segments starting at `feat_out` ([2*rows][pitch]); `rnorm_out[2*rows]`.
+ * rank's two consecutive segments starting at `feat_out` ([2*crossclr_segment_rows][pitch], padding rows and columns
+ * written as zeros when feat_dtype is the TC path's); `rnorm_out[2*rows]`.
  * Replaces: trainer/loss.py:79-80.
  */
 CROSSCLR_API int crossclr_pack2(const void* video, const void* text, int in_dtype, int64_t video_row_stride,
@@ -118,8 +137,9 @@ CROSSCLR_API int crossclr_pack2(const void* video, const void* text, int in_dtyp
 
 /*
  * Single-rank forward in one call (nseg == 2): crossclr_pack2 -> crossclr_fwd -> crossclr_finalize on `stream`.
- * Buffers as in the individual calls: feat [2*bseg][crossclr_feature_pitch(path, dim)] (dtype
- * crossclr_feature_dtype(path)), rnorm [2*bseg], stats / coef [2*bseg][2], scal [4], loss_out double[1].  Replaces: trainer/loss.py:79-114 (forward).
+ * Buffers as in the individual calls, S = crossclr_segment_rows(path, bseg): feat [2*S][crossclr_feature_pitch(path, dim)]
+ * (dtype crossclr_feature_dtype(path)), rnorm [2*bseg], stats / coef [2*S][2], scal [4], loss_out double[1].
+ * Replaces: trainer/loss.py:79-114 (forward).
  */
 CROSSCLR_API int crossclr_forward(const crossclr_problem_t* p, int path, const void* video, const void* text, int in_dtype,
                      int64_t video_row_stride, int64_t text_row_stride, void* feat, float* rnorm, float* stats,
@@ -131,7 +151,7 @@ CROSSCLR_API int crossclr_forward(const crossclr_problem_t* p, int path, const v
  *                          (includes the intra-modal diagonal, which is logit 0: loss.py:65,96-97)
  *   stats[2g+1] = xpos_g = positive logit * log2e - shift
  * with shift = crossclr_shift(p).  `feat` is the full stacked matrix [nseg*bseg][pitch] in the layout of
- * `path`; `stats` has room for [nseg*bseg][2] floats (only the owned rows are written).
+ * `path`; `stats` has room for [nseg*crossclr_segment_rows(path, bseg)][2] floats (only the owned segments are written).
  * Replaces: trainer/loss.py:83-100 (4 GEMMs, /tau, mask, weight, concat) and the row reductions of
  * :59-60; no B x B intermediate is written to memory.
  */
@@ -139,14 +159,15 @@ CROSSCLR_API int crossclr_fwd(const crossclr_problem_t* p, int path, const void*
                  size_t workspace_bytes, void* stream);
 
 /*
- * Loss and backward coefficients from the (all-gathered) statistics of ALL nseg*bseg rows:
+ * Loss and backward coefficients from the (all-gathered) statistics of ALL nseg*crossclr_segment_rows(path, bseg) rows
+ * (`path`: the one crossclr_fwd ran on -- it fixes the row layout and the meaning of stats[.,0]):
  *   loss_out[0] (double) = (1/2B) sum_g log1p(X_g * 2^-xpos_g)          trainer/loss.py:60,:111-114
  *   coef[2g+0] = 1/Z_g, coef[2g+1] = X_g/Z_g   with Z_g = X_g + 2^xpos_g (shifted units)
  *   scal[0] = sigma (power-of-two scale applied to the fp16 probability tiles), scal[1] = 1/sigma,
  *   scal[2] = max_g X_g/Z_g, scal[3] scratch (the single-rank forward's finalize ticket)
  */
-CROSSCLR_API int crossclr_finalize(const crossclr_problem_t* p, const float* stats, float* coef, double* loss_out,
-                      float* scal, void* stream);
+CROSSCLR_API int crossclr_finalize(const crossclr_problem_t* p, int path, const float* stats, float* coef,
+                      double* loss_out, float* scal, void* stream);
 
 /*
  * Gradients of loss * (*grad_out) * grad_scale w.r.t. the caller's own video/text rows.

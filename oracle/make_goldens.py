@@ -63,6 +63,11 @@ def main():
         ("tau01_b64_d64",    8,  64,  64,  0.0, 0.01, 0.8, True),     # small temperature
         ("rand_b256_d256",   9, 256, 256,  1.0, 0.03, 0.8, True),
         ("b1_d16",          10,   1,  16,  0.0, 0.03, 0.8, True),     # B = 1
+        # temperatures below the constant-shift range (reference float64 softmax subtracts the row max, loss.py:59-60)
+        ("tau0075_b128_d128", 12, 128, 128, 0.0, 0.0075, 0.8, True),  # weakly aligned rows: every cosine small
+        ("tau005_b128_d128",  13, 128, 128, 0.0, 0.005, 0.8, True),
+        ("tau005_align_b128_d64", 14, 128, 64, 2.0, 0.005, 0.8, True),   # mixed: some rows converged, some not
+        ("tau005_w2_b96_d48", 15,  96,  48, 2.0, 0.005, 2.0, True),   # |w| > 1, ragged
     ]
     for name, seed, B, D, al, tau, w, rep in spec:
         v, t = randn_case(seed, B, D, al)

@@ -60,7 +60,7 @@ def run_ranks(v, t, world, tau=0.03, w=0.8, path="tc", reps=1):
             ops.pack2(v[r * B:(r + 1) * B], t[r * B:(r + 1) * B], feat_all[2 * r:2 * r + 2], rnorm[r])
         for r in range(world):
             ops.fwd(probs[r], code, feat_all, stats)
-        ops.finalize(probs[0], stats, coef, loss, scal)
+        ops.finalize(probs[0], code, stats, coef, loss, scal)
         for r in range(world):
             ops.bwd(probs[r], code, feat_all, rnorm[r], coef, scal, go, 1.0, dv[r * B:(r + 1) * B], dt[r * B:(r + 1) * B])
     torch.cuda.synchronize()

@@ -26,7 +26,7 @@ for r in range(world):
     ops.pack2(v[r * Bl:(r + 1) * Bl], t[r * Bl:(r + 1) * Bl], feat[2 * r:2 * r + 2], rn[r])
 for r in range(world):
     ops.fwd(probs[r], code, feat, stats)
-ops.finalize(probs[0], stats, coef, loss, scal)
+ops.finalize(probs[0], code, stats, coef, loss, scal)
 lib = M.load_native()
 ws_bytes = int(lib.crossclr_workspace_bytes(ctypes.byref(probs[0]), code))
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(N.EXPORTS) == names           # the ctypes binding covers exactly the header
-    assert lib.crossclr_version() == 120
+    assert lib.crossclr_version() == 130
 
 
 def test_planning_and_validation_without_a_device():
@@ -37,8 +37,20 @@ def test_planning_and_validation_without_a_device():
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.F16, 0) == N.PATH_TC
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.F32, 0) == N.PATH_TC
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 1) == N.PATH_SIMT
+    # ragged shapes ride the tensor-core path on a zero-padded layout; tiny ones (padding would dominate) stay exact
     ragged = P(2, 100, 72, 0, 200, 0.03, 0.8)
-    assert lib.crossclr_choose_path(ctypes.byref(ragged), N.F32, 0) == N.PATH_SIMT
+    assert lib.crossclr_choose_path(ctypes.byref(ragged), N.F32, 0) == N.PATH_TC
+    assert lib.crossclr_segment_rows(N.PATH_TC, 100) == 128 and lib.crossclr_segment_rows(N.PATH_SIMT, 100) == 100
+    assert lib.crossclr_feature_pitch(N.PATH_TC, 72) == 128 + N.ROW_TAIL and lib.crossclr_feature_pitch(N.PATH_SIMT, 72) == 72
+    assert lib.crossclr_segment_rows(N.PATH_TC, 4000) == 4096 and lib.crossclr_feature_pitch(N.PATH_TC, 500) == 512 + N.ROW_TAIL
+    assert lib.crossclr_workspace_bytes(ctypes.byref(ragged), N.PATH_TC) >= 2 * 256 * 128 * 4
+    tiny = P(2, 8, 4, 0, 16, 0.03, 0.8)
+    assert lib.crossclr_choose_path(ctypes.byref(tiny), N.F32, 0) == N.PATH_SIMT
+    # temperatures below the tensor-core kernels' range go to the exact path's online-maximum mode
+    cold = P(2, 4096, 512, 0, 8192, 0.005, 0.8)
+    assert lib.crossclr_choose_path(ctypes.byref(cold), N.BF16, 0) == N.PATH_SIMT
+    assert lib.crossclr_fwd(ctypes.byref(cold), N.PATH_TC, ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0, None) == -1
+    assert b"temperature" in lib.crossclr_last_error()
     assert lib.crossclr_feature_dtype(N.PATH_TC) == N.F16 and lib.crossclr_feature_dtype(N.PATH_SIMT) == N.F32
     assert lib.crossclr_feature_pitch(N.PATH_SIMT, 512) == 512 and lib.crossclr_feature_pitch(N.PATH_TC, 512) == 512 + N.ROW_TAIL
     assert lib.crossclr_workspace_bytes(ctypes.byref(ok), N.PATH_TC) >= 8192 * 512 * 4

@@ -19,11 +19,23 @@ LOG2E = 1.4426950408889634
 
 
 class NumpyOps:
-    """The contract of include/crossclr_b200.h, restated in numpy float64 (test stand-in for _NativeOps)."""
+    """The contract of include/crossclr_b200.h, restated in numpy float64 (test stand-in for _NativeOps).  `pad` > 1 mimics the
+    tensor-core layout: every segment of the stacked matrix / stats / coef is padded with zero rows to a multiple of `pad`."""
 
-    def plan(self, prob, in_dtype, exact):
+    def __init__(self, pad=1):
+        self.pad = pad
+
+    def plan(self, prob, in_dtype, exact, force_tc=False):
         from crossmodal_contrastive_learning_b200 import _native as N
         return N.PATH_SIMT, torch.float32, prob.dim
+
+    def seg_rows(self, code, bseg):
+        return (bseg + self.pad - 1) // self.pad * self.pad
+
+    def _real(self, prob):
+        """padded stacked indices of the real rows, in stacked order"""
+        S = self.seg_rows(None, prob.bseg)
+        return (np.arange(prob.nseg)[:, None] * S + np.arange(prob.bseg)[None, :]).reshape(-1)
 
     @staticmethod
     def _shift(prob):
@@ -31,15 +43,16 @@ class NumpyOps:
 
     def pack2(self, v, t, feat_out, rnorm_out):
         B = v.shape[0]
+        feat_out.zero_()
         for k, x in enumerate((v, t)):
             x64 = x.double().numpy()
             n = np.maximum(np.sqrt((x64 * x64).sum(1)), 1e-12)
-            feat_out[k].copy_(torch.from_numpy(x64 / n[:, None]).to(feat_out.dtype))
+            feat_out[k, :B].copy_(torch.from_numpy(x64 / n[:, None]).to(feat_out.dtype))
             rnorm_out[k * B:(k + 1) * B].copy_(torch.from_numpy(1.0 / n).float())
 
     @staticmethod
     def _logits(prob, F, g_rows):
-        """log2-domain shifted logits of the given stacked rows against all rows, plus masks."""
+        """log2-domain shifted logits of the given (unpadded) stacked rows against all rows, plus masks."""
         bseg = prob.bseg
         R = F.shape[0]
         g_all = np.arange(R)
@@ -52,33 +65,37 @@ class NumpyOps:
         return G * k - NumpyOps._shift(prob), same_mod, same_samp
 
     def fwd(self, prob, code, feat_all, stats):
-        F = feat_all.reshape(-1, prob.dim).double().numpy()
+        real = self._real(prob)
+        F = feat_all.reshape(-1, prob.dim).double().numpy()[real]
         rows = np.arange(prob.row_begin, prob.row_begin + prob.row_count)
         x, same_mod, same_samp = self._logits(prob, F, rows)
         e = np.exp2(x)
         X = np.where(same_samp, 0.0, e).sum(1) + 2.0 ** (-self._shift(prob))     # + the masked intra diagonal (logit 0)
         xpos = x[same_samp & ~same_mod]
-        stats[rows] = torch.from_numpy(np.stack([X, xpos], 1)).float()
+        stats[real[rows]] = torch.from_numpy(np.stack([X, xpos], 1)).float()
 
-    def finalize(self, prob, stats, coef, loss, scal):
-        s = stats.double().numpy()
+    def finalize(self, prob, code, stats, coef, loss, scal):
+        real = self._real(prob)
+        s = stats.double().numpy()[real]
         X, xp = s[:, 0], s[:, 1]
         Z = X + np.exp2(xp)
-        coef.copy_(torch.from_numpy(np.stack([1.0 / Z, X / Z], 1)).float())
+        coef.zero_()
+        coef[real] = torch.from_numpy(np.stack([1.0 / Z, X / Z], 1)).float()
         loss.copy_(torch.tensor(np.log1p(X * np.exp2(-xp)).sum() / len(X), dtype=torch.float64))
         scal.copy_(torch.tensor([1.0, 1.0, float((X / Z).max()), 0.0]))
 
     def forward_single(self, prob, code, v, t, feat_all, rnorm, stats, coef, scal, loss):
         self.pack2(v, t, feat_all, rnorm)
         self.fwd(prob, code, feat_all, stats)
-        self.finalize(prob, stats, coef, loss, scal)
+        self.finalize(prob, code, stats, coef, loss, scal)
 
     def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt):
-        F = feat_all.reshape(-1, prob.dim).double().numpy()
+        real = self._real(prob)
+        F = feat_all.reshape(-1, prob.dim).double().numpy()[real]
         R, bseg = F.shape[0], prob.bseg
         rows = np.arange(prob.row_begin, prob.row_begin + prob.row_count)
         x, same_mod, same_samp = self._logits(prob, F, rows)
-        c = coef.double().numpy()
+        c = coef.double().numpy()[real]
         iz, rho = c[:, 0], c[:, 1]
         P = np.exp2(x) * (iz[rows][:, None] + iz[None, :]) * np.where(same_mod, prob.negative_weight, 1.0)
         P[same_samp] = 0.0
@@ -101,7 +118,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, B, D, tau, w, grad_scale, out):
+def _worker(rank, world, port, B, D, tau, w, grad_scale, out, pad=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -111,7 +128,7 @@ def _worker(rank, world, port, B, D, tau, w, grad_scale, out):
         t = v + 2.0 * torch.randn(B, D, generator=g)
         bl = B // world
         vl, tl = v[rank * bl:(rank + 1) * bl].contiguous(), t[rank * bl:(rank + 1) * bl].contiguous()
-        ops = NumpyOps()
+        ops = NumpyOps(pad)
         loss, prob, code, saved = L._forward_impl(ops, vl, tl, tau, w, "auto", dist.group.WORLD)
         assert (prob.nseg, prob.bseg, prob.row_begin, prob.row_count) == (2 * world, bl, 2 * rank * bl, 2 * bl)
         dv, dt = L._backward_impl(ops, prob, code, saved, torch.tensor(1.0, dtype=torch.float64), grad_scale,
@@ -121,14 +138,15 @@ def _worker(rank, world, port, B, D, tau, w, grad_scale, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,B,D,grad_scale", [(2, 64, 32, 1.0), (2, 96, 24, 2.0)])
-def test_sharded_matches_global_oracle(world, B, D, grad_scale):
+@pytest.mark.parametrize("world,B,D,grad_scale,pad", [(2, 64, 32, 1.0, 1), (2, 96, 24, 2.0, 1), (2, 72, 24, 1.0, 16)],
+                         ids=["b64", "b96", "b72_padded_segments"])
+def test_sharded_matches_global_oracle(world, B, D, grad_scale, pad):
     from oracle import crossclr_oracle as O
     tau, w = 0.05, 0.8
     mgr = mp.Manager()
     out = mgr.dict()
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, B, D, tau, w, grad_scale, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, B, D, tau, w, grad_scale, out, pad), nprocs=world, join=True)
     g = torch.Generator().manual_seed(123)
     v = torch.randn(B, D, generator=g)
     t = v + 2.0 * torch.randn(B, D, generator=g)

@@ -20,6 +20,8 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-3
 TOL_SIMT = 5e-5
+# below tau ~ 0.0073 the fp32 logits reach log2e max(1,|w|)/tau = 300..600 in magnitude: one ulp there is 3e-5..6e-5 of a probability
+TOL_SMALL_TAU = 3e-4
 
 
 def _mod():
@@ -53,7 +55,11 @@ def check(loss, dv, dt, rloss, rdv, rdt, tol):
 
 FULL = sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
               if not os.path.basename(p).startswith(("kat_", "c1_")))
-TC_OK = [p for p in FULL if (lambda g: g["v"].shape[0] % 128 == 0 and g["v"].shape[1] % 64 == 0)(np.load(p))]
+TC_SHAPED = [p for p in FULL if (lambda g: g["v"].shape[0] % 128 == 0 and g["v"].shape[1] % 64 == 0)(np.load(p))]
+# the tensor-core kernels use one shift for all rows: log2e max(1,|w|)/tau <= 200 (include/crossclr_b200.h, crossclr_choose_path)
+_in_tc_range = lambda g: 1.4426950408889634 * max(1.0, abs(float(g["w"]))) / float(g["tau"]) <= 200.0
+TC_OK = [p for p in FULL if _in_tc_range(np.load(p))]       # any shape: the tensor-core layout zero-pads B to 128 and D to 64
+SMALL_TAU = [p for p in FULL if not _in_tc_range(np.load(p))]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -90,14 +96,60 @@ def test_simt_matches_reference_goldens(path):
         check(loss, dv[keep], dt, float(g["loss"]), g["dv"][keep], g["dt"], TOL_SIMT)
         assert np.linalg.norm(dv[z] - g["dv"][z]) <= 1e-3 * np.linalg.norm(g["dv"][z])
     else:
-        check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL_SIMT)
+        check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64),
+              TOL_SMALL_TAU if path in SMALL_TAU else TOL_SIMT)
 
 
 @pytest.mark.parametrize("path", TC_OK, ids=[os.path.basename(p)[:-4] for p in TC_OK])
 def test_tc_matches_reference_goldens(path):
+    """Every reference golden inside the temperature range on the tensor-core path, ragged shapes included (B = 1, 8, 160;
+    D = 4, 16, 192): the zero-padded layout must give the reference's numbers for the caller's rows."""
     g = np.load(path)
     loss, dv, dt = run_gpu(g["v"], g["t"], float(g["tau"]), float(g["w"]), path="tc")
-    check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL)
+    if "zero_row" in path:
+        z = 3                     # its gradient (~1e13, through the eps clamp) dominates every norm: compare rows separately
+        keep = np.arange(len(dv)) != z
+        check(loss, dv[keep], dt, float(g["loss"]), g["dv"][keep].astype(np.float64), g["dt"].astype(np.float64), TOL)
+        assert np.linalg.norm(dv[z] - g["dv"][z]) <= 1e-3 * np.linalg.norm(g["dv"][z])
+    else:
+        check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL)
+
+
+@pytest.mark.parametrize("B,D,world", [(4000, 500, 1), (333, 77, 1), (1000, 200, 1), (130, 70, 1), (2100, 520, 1), (600, 72, 4),
+                                       (3000, 500, 3), (4000, 1000, 2)])
+def test_ragged_shapes_on_the_tensor_core_path(B, D, world):
+    """trainer/loss.py:83-88 takes any [B, D].  `auto` keeps ragged shapes on the tensor-core kernels (segments zero-padded to
+    128 rows, rows to 64 columns; the forward masks the padded columns out of the row sums, zero rows drop out of the
+    backward); results equal the oracle's on the caller's rows at the exact-operand tolerance, single rank (symmetric
+    schedules, fused finalize) and row-band ranks."""
+    from oracle import crossclr_oracle as O
+    from crossmodal_contrastive_learning_b200 import _native as N, loss as L
+    Bl = B // world
+    prob = N.Problem(2 * world, Bl, D, 0, 2 * Bl, 0.03, 0.8)
+    assert L._ops().plan(prob, torch.bfloat16, False)[0] == N.PATH_TC
+    v, t = _seeded(B, D, 77 + B + D, aligned=2.0)
+    rows = None if B <= 2048 else np.arange(0, B, B // 24) + 1
+    rloss, rdv, rdt = O.loss_and_grads(v, t, 0.03, 0.8, rows=rows, row_block=2048)
+    loss, dv, dt = _run_ranks_on_one_gpu(torch.from_numpy(v).to("cuda", torch.bfloat16), torch.from_numpy(t).to("cuda", torch.bfloat16),
+                                         world, 0.03, 0.8, "auto")
+    if rows is not None:
+        dv, dt = dv[rows], dt[rows]
+    # the fp16 rounding of a probability tile (2^-11 per element) averages over D products: a little less at D < 128
+    check(loss, dv, dt, rloss, rdv, rdt, TOL_RAW if D >= 128 else 3e-4)
+
+
+@pytest.mark.parametrize("path", SMALL_TAU, ids=[os.path.basename(p)[:-4] for p in SMALL_TAU])
+def test_small_temperature_goldens_route_to_row_shift(path):
+    """tau = 0.005 (the low end of the reference's range): `auto` takes the exact path's online-maximum mode and matches the
+    reference's float64 max-subtracted softmax; forcing the tensor-core path is refused, not silently flushed."""
+    g = np.load(path)
+    assert len(SMALL_TAU) >= 3
+    loss, dv, dt = run_gpu(g["v"], g["t"], float(g["tau"]), float(g["w"]), path="auto")
+    assert np.isfinite(loss) and np.isfinite(dv).all() and np.isfinite(dt).all()
+    check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL_SMALL_TAU)
+    if path in TC_SHAPED:
+        with pytest.raises(RuntimeError, match="temperature"):
+            run_gpu(g["v"], g["t"], float(g["tau"]), float(g["w"]), path="tc")
 
 
 @pytest.mark.parametrize("path", ["simt", "tc"])
@@ -239,9 +291,10 @@ def _abi_step(v, t, tau=0.03, w=0.8, want_stats=False):
     B, D = v.shape
     prob = N.Problem(2, B, D, 0, 2 * B, tau, w)
     code, fdt, pitch = ops.plan(prob, v.dtype, False)
-    feat = torch.empty((2, B, pitch), dtype=fdt, device="cuda")
+    S = ops.seg_rows(code, B)
+    feat = torch.empty((2, S, pitch), dtype=fdt, device="cuda")
     rnorm = torch.empty(2 * B, dtype=torch.float32, device="cuda")
-    stats = torch.empty((2 * B, 2), dtype=torch.float32, device="cuda")
+    stats = torch.empty((2 * S, 2), dtype=torch.float32, device="cuda")
     coef = torch.empty_like(stats)
     scal = torch.empty(4, dtype=torch.float32, device="cuda")
     loss = torch.empty((), dtype=torch.float64, device="cuda")
@@ -335,10 +388,11 @@ def _run_ranks_on_one_gpu(v, t, world, tau, w, path):
     Bg, D = v.shape
     B = Bg // world
     probs = [N.Problem(2 * world, B, D, 2 * r * B, 2 * B, tau, w) for r in range(world)]
-    code, fdt, pitch = ops.plan(probs[0], v.dtype, path == "simt")
-    feat = torch.empty((2 * world, B, pitch), dtype=fdt, device="cuda")
+    code, fdt, pitch = ops.plan(probs[0], v.dtype, path == "simt", path == "tc")
+    S = ops.seg_rows(code, B)                 # the tensor-core layout pads every segment to a multiple of 128 rows
+    feat = torch.empty((2 * world, S, pitch), dtype=fdt, device="cuda")
     rnorm = torch.empty((world, 2 * B), dtype=torch.float32, device="cuda")
-    stats = torch.empty((2 * world * B, 2), dtype=torch.float32, device="cuda")
+    stats = torch.empty((2 * world * S, 2), dtype=torch.float32, device="cuda")
     coef = torch.empty_like(stats)
     scal = torch.empty(4, dtype=torch.float32, device="cuda")
     loss = torch.empty((), dtype=torch.float64, device="cuda")
@@ -348,7 +402,7 @@ def _run_ranks_on_one_gpu(v, t, world, tau, w, path):
         ops.pack2(v[r * B:(r + 1) * B], t[r * B:(r + 1) * B], feat[2 * r:2 * r + 2], rnorm[r])
     for r in range(world):
         ops.fwd(probs[r], code, feat, stats)
-    ops.finalize(probs[0], stats, coef, loss, scal)
+    ops.finalize(probs[0], code, stats, coef, loss, scal)
     for r in range(world):
         ops.bwd(probs[r], code, feat, rnorm[r], coef, scal, go, 1.0, dv[r * B:(r + 1) * B], dt[r * B:(r + 1) * B])
     torch.cuda.synchronize()
