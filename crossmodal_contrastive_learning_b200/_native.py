@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcrossclr_b200.so")
 
 # element types / paths (mirror include/crossclr_b200.h)
-F32, F16, BF16 = 0, 1, 2
-PATH_AUTO, PATH_SIMT, PATH_TC = 0, 1, 2
+F32, F16, BF16, F16X2 = 0, 1, 2, 3      # F16X2: fp16 hi + lo rows of PATH_TC_SPLIT (stacked matrix only)
+PATH_AUTO, PATH_SIMT, PATH_TC, PATH_TC_SPLIT = 0, 1, 2, 3
 ROW_TAIL = 64      # CROSSCLR_ROW_TAIL: extra elements per stacked row on the tensor-core paths (residual scale)
 
 EXPORTS = (

@@ -70,6 +70,13 @@ int validate_problem(const crossclr_problem_t* p) {
 // `auto` takes the tensor-core path unless the zero padding (segments to 128 rows, rows to 64 columns) would dominate the work
 static bool tc_worthwhile(const crossclr_problem_t* p) { return p->bseg >= 96 && p->dim >= 48; }
 
+// CROSSCLR_PATH_TC_SPLIT runs its backward on the dataflow kernel only (flow_kernels.cu: flow_plan's shape rule, restated
+// here as a pure function of the problem so that planning needs no device)
+static bool split_shape_ok(const crossclr_problem_t* p) {
+  const Geometry g = make_geometry(p, CROSSCLR_PATH_TC_SPLIT);
+  return g.dim <= 1024 && g.rows >= 2048 && g.rows / 256 < (1 << 20);
+}
+
 // gradient accumulator of the owned rows, in the path's own (for TC: padded) geometry
 static size_t dfhat_bytes(const Geometry& g) {
   return ((size_t)g.row_count * (size_t)g.dim * sizeof(float) + 255) & ~(size_t)255;
@@ -102,27 +109,31 @@ int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact) {
              "crossclr_choose_path: unsupported input dtype %d", in_dtype);
   if (!tc_worthwhile(p) || exact) return CROSSCLR_PATH_SIMT;
   if (problem_needs_row_shift(p)) return CROSSCLR_PATH_SIMT;      // temperature below the constant shift's range (~0.0073)
+  if (in_dtype == CROSSCLR_F32)     // fp32 values are not rounded to fp16 unasked: hi + lo operands where they apply, else exact
+    return split_shape_ok(p) ? CROSSCLR_PATH_TC_SPLIT : CROSSCLR_PATH_SIMT;
   return CROSSCLR_PATH_TC;
 }
 
 int crossclr_feature_dtype(int path) {
   if (path == CROSSCLR_PATH_SIMT) return CROSSCLR_F32;
   if (path == CROSSCLR_PATH_TC) return CROSSCLR_F16;
-  set_error("crossclr_feature_dtype: path must be SIMT or TC");
+  if (path == CROSSCLR_PATH_TC_SPLIT) return CROSSCLR_F16X2;
+  set_error("crossclr_feature_dtype: path must be SIMT, TC or TC_SPLIT");
   return CROSSCLR_EINVAL;
 }
 
 int64_t crossclr_feature_pitch(int path, int32_t dim) {
   if (path == CROSSCLR_PATH_SIMT) return dim;
-  if (path_is_tc(path)) return (int64_t)tc_pad_dim(dim) + CROSSCLR_ROW_TAIL;
-  set_error("crossclr_feature_pitch: path must be SIMT or TC");
+  if (path == CROSSCLR_PATH_TC) return (int64_t)tc_pad_dim(dim) + CROSSCLR_ROW_TAIL;
+  if (path == CROSSCLR_PATH_TC_SPLIT) return 2 * (int64_t)tc_pad_dim(dim, true) + CROSSCLR_ROW_TAIL;
+  set_error("crossclr_feature_pitch: path must be SIMT, TC or TC_SPLIT");
   return CROSSCLR_EINVAL;
 }
 
 int64_t crossclr_segment_rows(int path, int32_t bseg) {
   if (path == CROSSCLR_PATH_SIMT) return bseg;
   if (path_is_tc(path)) return tc_pad_rows(bseg);
-  set_error("crossclr_segment_rows: path must be SIMT or TC");
+  set_error("crossclr_segment_rows: path must be SIMT, TC or TC_SPLIT");
   return CROSSCLR_EINVAL;
 }
 
@@ -266,7 +277,7 @@ int crossclr_bwd_finish(const crossclr_problem_t* p, int path, const void* feat,
   const Geometry g = make_geometry(p, path);
   // TC paths: the second partial (late consumers of the dataflow kernel) counts iff the flag word says so (read on device)
   const float* dfhat2 = tc ? (const float*)((const char*)workspace + dfhat_bytes(g)) : nullptr;
-  return launch_grad_finish(g, feat, tc ? CROSSCLR_F16 : CROSSCLR_F32, rnorm_owned, coef, scal, tc, grad_out,
+  return launch_grad_finish(g, feat, tc ? crossclr_feature_dtype(path) : CROSSCLR_F32, rnorm_owned, coef, scal, tc, grad_out,
                             grad_scale, (const float*)workspace, dv, dv_row_stride, dt, dt_row_stride, out_dtype,
                             (cudaStream_t)stream, dfhat2);
 }

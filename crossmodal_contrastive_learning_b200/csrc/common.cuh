@@ -75,6 +75,7 @@ struct Geometry {
   int nseg, bseg, dim, rows;       // rows = nseg * bseg
   int row_begin, row_count;
   int bvalid, dvalid, rows_valid;  // the caller's rows per segment, columns, and nseg * bvalid
+  int split;                       // CROSSCLR_PATH_TC_SPLIT: rows are [hi | lo | tail], the S product runs over 3 dim / 64 K chunks
   int pitch;                       // row pitch of the stacked matrix in elements (dim, or dim + CROSSCLR_ROW_TAIL on the TC path)
   int row_shift;                   // SIMT path, small temperatures: no common shift; the forward keeps an online (max, sum) per row
                                    // and stats = (log2 X_g, xpos_g), coef = (log2 Z_g, rho_g); the backward forms
@@ -93,24 +94,28 @@ inline float problem_max_logit(const crossclr_problem_t* p) {
 inline float problem_shift(const crossclr_problem_t* p) { return fmaxf(0.0f, problem_max_logit(p) - kShiftHeadroom); }
 inline bool problem_needs_row_shift(const crossclr_problem_t* p) { return problem_max_logit(p) > kConstShiftMaxLogit; }
 
-inline bool path_is_tc(int path) { return path == CROSSCLR_PATH_TC; }
+inline bool path_is_tc(int path) { return path == CROSSCLR_PATH_TC || path == CROSSCLR_PATH_TC_SPLIT; }
 
 inline int tc_pad_rows(int bseg) { return (bseg + 127) / 128 * 128; }
-inline int tc_pad_dim(int dim) { return (dim + 63) / 64 * 64; }
+inline int tc_pad_dim(int dim, bool split = false) {
+  if (!split) return (dim + 63) / 64 * 64;
+  return dim <= 512 ? (dim + 127) / 128 * 128 : (dim + 255) / 256 * 256;     // what the dataflow backward tiles
+}
 
 inline Geometry make_geometry(const crossclr_problem_t* p, int path = CROSSCLR_PATH_SIMT) {
   Geometry g;
   g.nseg = p->nseg; g.bseg = p->bseg; g.dim = p->dim; g.rows = p->nseg * p->bseg;
   g.row_begin = p->row_begin; g.row_count = p->row_count;
   g.bvalid = p->bseg; g.dvalid = p->dim; g.rows_valid = g.rows;
+  g.split = path == CROSSCLR_PATH_TC_SPLIT ? 1 : 0;
   if (path_is_tc(path)) {
     g.bseg = tc_pad_rows(p->bseg);
-    g.dim = tc_pad_dim(p->dim);
+    g.dim = tc_pad_dim(p->dim, g.split);
     g.rows = p->nseg * g.bseg;
     g.row_begin = p->row_begin / p->bseg * g.bseg;       // owned rows are whole segments (validate_problem)
     g.row_count = p->row_count / p->bseg * g.bseg;
   }
-  g.pitch = path_is_tc(path) ? g.dim + CROSSCLR_ROW_TAIL : g.dim;
+  g.pitch = path_is_tc(path) ? g.dim * (1 + g.split) + CROSSCLR_ROW_TAIL : g.dim;
   g.row_shift = (path == CROSSCLR_PATH_SIMT && problem_needs_row_shift(p)) ? 1 : 0;
   g.inv_tau = 1.0f / p->temperature;
   g.k_inter = kLog2e / p->temperature;

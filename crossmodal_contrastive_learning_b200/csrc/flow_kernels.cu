@@ -52,7 +52,7 @@ struct FlowParams {
   int ds, dw;            // consumers split D into ds slabs of dw columns (D <= 512: 1 x D; else 2 x D/2): physical ring =
                          // logical ring * ds + slab, every tile is consumed once per slab
   int a_res;             // producer keeps its 128 rows of A resident (nk <= 8); else A streams beside B
-  int nk;                // dim / 64
+  int nk;                // K chunks of the similarity product: dim / 64, or 3 dim / 64 for split rows
   int s_stages;          // producer ring depth
   uint32_t* ring;        // [nrb * parts (+ nb late)][cnt] descriptors, zero = not yet published
   uint32_t* tail;        // [nrb * parts (+ nb late)]
@@ -223,7 +223,8 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   const bool is_prod = pair >= P.n_g;
   const int prod = pair - P.n_g;
   const uint32_t data = base + (is_prod ? FLOW_HDR : 1024);
-  const int nk = P.nk;
+  const int nk = P.nk;                   // K chunks of the similarity product (3 dim / 64 for split rows, streamed only)
+  const int nkd = g.dim / KC;
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap); prefetch_tmap(&tmap64); prefetch_tmap(&tmap_p); }
   if (warp == 1 && lane == 0) {
@@ -445,8 +446,8 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             uint32_t st = ring_base + ring.stage * stage_bytes;
             const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), 0);
             if (sub == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * stage_bytes);
-            if (!a_res) { tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, row0); st += CHUNK_BYTES; }
-            tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, tl.J * FLOW_TN + (int)sub * TM);
+            if (!a_res) { tma_load_2d_2sm(st, &tmap, full_ldr, a_kcol(kc, nkd), row0); st += CHUNK_BYTES; }
+            tma_load_2d_2sm(st, &tmap, full_ldr, b_kcol(kc, nkd), tl.J * FLOW_TN + (int)sub * TM);
           }
           __syncwarp();
           ring.advance();
@@ -900,9 +901,9 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   P.d0 = f.d0; P.cnt_main = f.cnt_main; P.cnt_late = f.cnt_late;
   const bool late_on = f.d0 <= f.nb;
   const size_t n_rings = (size_t)f.nrb * f.parts * f.ds + (late_on ? f.nb : 0);
-  P.nk = g.dim / KC;
+  P.nk = s_chunks(g);
   P.ds = f.ds; P.dw = g.dim / f.ds;
-  P.a_res = P.nk <= MAX_RES_CHUNKS ? 1 : 0;
+  P.a_res = (P.nk <= MAX_RES_CHUNKS && !g.split) ? 1 : 0;
   P.s_stages = P.a_res ? std::min((int)((kMaxSmem - FLOW_HDR - (size_t)P.nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS)
                        : std::min((int)((kMaxSmem - FLOW_HDR) / (2 * CHUNK_BYTES)), MAX_SLOTS);
   P.ring = (uint32_t*)scratch;

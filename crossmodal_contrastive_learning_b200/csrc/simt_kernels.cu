@@ -31,9 +31,10 @@ __device__ __forceinline__ void split_rnorm(float norm, float rn, float& pow2, f
 // d >= dim are zero padding (tensor-core layout); rnorm is compact: m * rows + r.
 template <typename Tin, typename Tout, bool kRaw>
 __global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ xv, const Tin* __restrict__ xt, int64_t sv,
-                                                  int64_t st_, int rows, int rows_pad, int nmod, int dim, int dimp,
+                                                  int64_t st_, int rows, int rows_pad, int nmod, int dim, int dimp, int split,
                                                   Tout* __restrict__ out, int64_t pitch, float* __restrict__ rnorm,
                                                   float2* __restrict__ stats_zero, unsigned int* __restrict__ ticket_zero) {
+  const int fw = dimp * (1 + split);                            // feature elements per row: [hi] or [hi | lo]
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= nmod * rows_pad) return;
@@ -42,8 +43,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ xv, c
   const int mod = row >= rows_pad ? 1 : 0, r = row - mod * rows_pad;
   Tout* dst = out + (int64_t)row * pitch;
   if (r >= rows) {                                             // padding row: zero features, q = 1
-    for (int d = lane; d < dimp; d += 32) dst[d] = from_float<Tout>(0.f);
-    if (lane == 0 && pitch > dimp) *reinterpret_cast<float*>(dst + dimp) = 1.0f;
+    for (int d = lane; d < fw; d += 32) dst[d] = from_float<Tout>(0.f);
+    if (lane == 0 && pitch > fw) *reinterpret_cast<float*>(dst + fw) = 1.0f;
     return;
   }
   const Tin* src = mod == 0 ? xv + (int64_t)r * sv : xt + (int64_t)r * st_;
@@ -57,10 +58,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const Tin* __restrict__ xv, c
   const float rn = 1.0f / fmaxf(norm, kEps);
   float mul = rn, q = 1.0f;
   if (kRaw) split_rnorm(norm, rn, mul, q);
-  for (int d = lane; d < dimp; d += 32) dst[d] = from_float<Tout>(d < dim ? to_float<Tin>(src[d]) * mul : 0.f);
+  for (int d = lane; d < dimp; d += 32) {
+    const float f = d < dim ? to_float<Tin>(src[d]) * mul : 0.f;
+    const Tout hi = from_float<Tout>(f);
+    dst[d] = hi;
+    if (split) dst[dimp + d] = from_float<Tout>(f - to_float<Tout>(hi));    // lo: what the fp16 rounding of f dropped
+  }
   if (lane == 0) {
     rnorm[mod * rows + r] = rn;
-    if (pitch > dimp) *reinterpret_cast<float*>(dst + dimp) = q;
+    if (pitch > fw) *reinterpret_cast<float*>(dst + fw) = q;
   }
 }
 
@@ -132,14 +138,15 @@ template <typename Tin>
 static int pack_dispatch(const void* xv, const void* xt, int64_t sv, int64_t st_, int rows, int nmod, int dim,
                          void* out, int out_dtype, float* rnorm, cudaStream_t st, float* stats_zero, unsigned int* ticket_zero) {
   const bool tc = out_dtype != CROSSCLR_F32;                       // the tensor-core layout is padded (Geometry)
-  const int rows_pad = tc ? tc_pad_rows(rows) : rows, dimp = tc ? tc_pad_dim(dim) : dim;
+  const int split = out_dtype == CROSSCLR_F16X2 ? 1 : 0;           // [hi | lo] rows of CROSSCLR_PATH_TC_SPLIT
+  const int rows_pad = tc ? tc_pad_rows(rows) : rows, dimp = tc ? tc_pad_dim(dim, split) : dim;
   dim3 block(256), grid((nmod * rows_pad + 7) / 8);
-  const int64_t pitch = tc ? dimp + CROSSCLR_ROW_TAIL : dimp;
+  const int64_t pitch = tc ? dimp * (1 + split) + CROSSCLR_ROW_TAIL : dimp;
 #define CC_PACK(Tout, kRaw)                                                                                              \
   pack_kernel<Tin, Tout, kRaw><<<grid, block, 0, st>>>((const Tin*)xv, (const Tin*)xt, sv, st_, rows, rows_pad, nmod, dim, \
-                                                       dimp, (Tout*)out, pitch, rnorm, (float2*)stats_zero, ticket_zero)
+                                                       dimp, split, (Tout*)out, pitch, rnorm, (float2*)stats_zero, ticket_zero)
   if (out_dtype == CROSSCLR_F32) CC_PACK(float, false);
-  else if (out_dtype == CROSSCLR_F16) CC_PACK(__half, true);     // power-of-two rescale: exact for 16-bit-representable values
+  else if (out_dtype == CROSSCLR_F16 || out_dtype == CROSSCLR_F16X2) CC_PACK(__half, true);   // power-of-two rescale: exact for 16-bit values
   else { set_error("crossclr_pack: unsupported stacked dtype %d", out_dtype); return CROSSCLR_EINVAL; }
 #undef CC_PACK
   return check_launch("pack_kernel");
@@ -461,8 +468,13 @@ int launch_finalize(const Geometry& g, const float* stats, float* coef, double* 
 // One warp per owned row.
 // kTail: the rows are (f, q) rows of the TC paths (pitch dim + tail, normalised row = q * f); else plain normalised rows.
 template <typename TF, bool kTail>
-__device__ __forceinline__ float row_scale(const TF* row, int dim) {
-  return kTail ? *reinterpret_cast<const float*>(row + dim) : 1.0f;
+__device__ __forceinline__ float row_scale(const TF* row, const Geometry& g) {
+  return kTail ? *reinterpret_cast<const float*>(row + (g.pitch - CROSSCLR_ROW_TAIL)) : 1.0f;
+}
+// element d of a stored row: hi (+ lo for the split rows of CROSSCLR_PATH_TC_SPLIT)
+template <typename TF>
+__device__ __forceinline__ float row_elem(const TF* row, int d, const Geometry& g) {
+  return g.split ? to_float<TF>(row[d]) + to_float<TF>(row[g.dim + d]) : to_float<TF>(row[d]);
 }
 
 template <typename TF, typename TO, bool kTail>
@@ -484,15 +496,15 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   const float* dh2 = (dfhat2 != nullptr && two != nullptr && *two != 0u) ? dfhat2 + (int64_t)l * g.dim : nullptr;
   const TF* fg = F + (int64_t)gr * g.pitch;
   const TF* fp = F + (int64_t)pg * g.pitch;
-  const float qg = row_scale<TF, kTail>(fg, g.dim), qp = row_scale<TF, kTail>(fp, g.dim);
+  const float qg = row_scale<TF, kTail>(fg, g), qp = row_scale<TF, kTail>(fp, g);
   const float acc_scale = (use_sigma ? scal[1] : 1.0f) / qg;       // TC paths accumulate sum_j (P q_g q_j) f_j = q_g dFhat_g
   const float pos_coef = -(coef[2 * (int64_t)gr + 1] + coef[2 * (int64_t)pg + 1]) * qp;
   const float* dh = dfhat + (int64_t)l * g.dim;
   float dot = 0.f;
   for (int d = lane; d < g.dim; d += 32) {
     const float acc = dh2 ? dh[d] + dh2[d] : dh[d];
-    const float h = acc * acc_scale + pos_coef * to_float<TF>(fp[d]);
-    dot = fmaf(h, to_float<TF>(fg[d]), dot);
+    const float h = acc * acc_scale + pos_coef * row_elem<TF>(fp, d, g);
+    dot = fmaf(h, row_elem<TF>(fg, d, g), dot);
   }
   dot = warp_sum(dot) * qg * qg;        // (h . Fhat_g) Fhat_g with Fhat_g = q_g f_g
   if (rn_g >= 1.0f / kEps) dot = 0.f;   // ||x|| < eps: the clamp in F.normalize is active, no norm gradient
@@ -503,8 +515,8 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(Geometry g, const TF* 
   TO* out = mod == 0 ? dv + (int64_t)r * dv_stride : dt + (int64_t)r * dt_stride;
   for (int d = lane; d < g.dvalid; d += 32) {
     const float acc = dh2 ? dh[d] + dh2[d] : dh[d];
-    const float h = acc * acc_scale + pos_coef * to_float<TF>(fp[d]);
-    out[d] = from_float<TO>(mult * (h - dot * to_float<TF>(fg[d])));
+    const float h = acc * acc_scale + pos_coef * row_elem<TF>(fp, d, g);
+    out[d] = from_float<TO>(mult * (h - dot * row_elem<TF>(fg, d, g)));
   }
 }
 
@@ -595,7 +607,7 @@ static bool grad_finish_vec(const Geometry& g, const void* feat, const float* rn
                             const float* dfhat, void* dv, int64_t dvs, void* dt, int64_t dts, cudaStream_t st,
                             const float* dfhat2, const unsigned int* two) {
   const size_t osz = sizeof(TO);
-  if (g.dim % 256 != 0 || g.dim > 1024 || g.dvalid != g.dim || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
+  if (g.dim % 256 != 0 || g.dim > 1024 || g.dvalid != g.dim || g.split || ((uintptr_t)feat | (uintptr_t)dfhat | (uintptr_t)dv | (uintptr_t)dt) % 16 != 0 ||
       (dvs * osz) % 16 != 0 || (dts * osz) % 16 != 0 || (g.pitch * sizeof(TF)) % 16 != 0)
     return false;
   dim3 block(256), grid((g.row_count + 7) / 8);
@@ -659,7 +671,7 @@ int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, cons
   if (feat_dtype == CROSSCLR_F32)
     return grad_finish_out<float, false>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv,
                                          dv_stride, dt, dt_stride, out_dtype, st);
-  if (feat_dtype == CROSSCLR_F16)
+  if (feat_dtype == CROSSCLR_F16 || feat_dtype == CROSSCLR_F16X2)
     return grad_finish_16<__half>(g, feat, rnorm, coef, scal, use_sigma, grad_out, grad_scale, dfhat, dv, dv_stride, dt,
                                   dt_stride, out_dtype, st, dfhat2, two);
   set_error("crossclr_bwd: unsupported stacked dtype %d", feat_dtype);

@@ -59,12 +59,19 @@ __device__ __forceinline__ BlockSeg block_seg(int r0, int bseg) {
 
 // residual scale q_j of stacked row j (normalised row = q_j * stored row; include/crossclr_b200.h), first word of the row tail
 __device__ __forceinline__ float row_q(const uint8_t* __restrict__ feat, const Geometry& g, int64_t j) {
-  return __ldg(reinterpret_cast<const float*>(feat + (j * g.pitch + g.dim) * 2));
+  return __ldg(reinterpret_cast<const float*>(feat + (j * g.pitch + (g.pitch - CROSSCLR_ROW_TAIL)) * 2));
 }
+
+// K chunks of the similarity product and the stacked-row column each one reads.  Plain rows: chunk kc of A and of B is
+// column 64 kc.  Split rows [hi | lo]: K = 3 dim, A = [hi | lo | hi], B = [hi | hi | lo] (hi.hi + lo.hi + hi.lo); with
+// nk = dim / 64 both maps below reduce to 64 kc in the plain case (kc < nk).
+__host__ __device__ __forceinline__ int s_chunks(const Geometry& g) { return (g.dim / KC) * (g.split ? 3 : 1); }
+__device__ __forceinline__ int a_kcol(int kc, int nk) { return (kc < 2 * nk ? kc : kc - 2 * nk) * KC; }
+__device__ __forceinline__ int b_kcol(int kc, int nk) { return (kc < nk ? kc : kc - nk) * KC; }
 
 // stacked-matrix tensor map of a geometry: {64, box_rows} boxes of the [rows][dim] operand inside the pitched rows
 #define CC_FEAT_TMAP(m, feat, g, box_rows) \
-  make_tmap_f16(m, feat, (uint64_t)(g).rows, (uint64_t)(g).dim, box_rows, true, (uint64_t)(g).pitch, false)
+  make_tmap_f16(m, feat, (uint64_t)(g).rows, (uint64_t)((g).pitch - CROSSCLR_ROW_TAIL), box_rows, true, (uint64_t)(g).pitch, false)
 
 constexpr int kBarBytes = 8 * (2 * MAX_SLOTS) + 128;   // mbarrier block of the forward / single-CTA backward kernels
 constexpr int PTILE_BYTES = TM * 128 * 2;   // a [128 rows][128 columns] fp16 probability tile: 32 KiB

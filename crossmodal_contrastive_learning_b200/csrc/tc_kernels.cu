@@ -223,6 +223,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int t_begin = (int)((long long)pair * tiles_total / npairs);
   const int t_end = (int)((long long)(pair + 1) * tiles_total / npairs);
+  const int nkd = g.dim / KC;            // nk counts the K chunks of the product (3 nkd for split rows, streamed only)
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
   if (warp == 1 && lane == 0) {
@@ -287,8 +288,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
           uint32_t st = ring_base + ring.stage * stage_bytes;
           const uint32_t full_ldr = mapa_cluster(full_bar(ring.stage), 0);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(ring.stage), 2 * stage_bytes);
-          if (!kResident) { tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, row0); st += CHUNK_BYTES; }
-          tma_load_2d_2sm(st, &tmap, full_ldr, kc * KC, col0);
+          if (!kResident) { tma_load_2d_2sm(st, &tmap, full_ldr, a_kcol(kc, nkd), row0); st += CHUNK_BYTES; }
+          tma_load_2d_2sm(st, &tmap, full_ldr, b_kcol(kc, nkd), col0);
         }
         __syncwarp();
         ring.advance();
@@ -1450,7 +1451,7 @@ constexpr int kFwdQvBytes = FWD_QSTAGES * FWD_TN * 4;   // ring of per-tile colu
 template <bool kResident, bool kSym>
 static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, float* stats, cudaStream_t st,
                             const FwdFinalize& fin) {
-  const int nk = g.dim / KC, ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
+  const int nk = s_chunks(g), ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
   const int tiles = kSym ? ncb * (ncb + 1) / 2 : nrbp * ncb;
   const size_t a_bytes = kResident ? (size_t)nk * CHUNK_BYTES : 0;
   const size_t stage_bytes = (size_t)(kResident ? 1 : 2) * CHUNK_BYTES;
@@ -1482,7 +1483,7 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   CUtensorMap tmap;
   int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
-  const bool resident = g.dim / KC <= MAX_RES_CHUNKS;
+  const bool resident = s_chunks(g) <= MAX_RES_CHUNKS && !g.split;    // split rows: A's K chunks are not B's, stream both
   // single rank: all rows are owned, the Gram matrix is square and symmetric -> upper triangle of pair tiles only
   const bool sym = g.row_count == g.rows && g.row_begin == 0 && fwd_sym_enabled();
   if (sym) return resident ? launch_fwd_tc2_t<true, true>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, true>(tmap, feat, g, stats, st, fin);
@@ -1597,6 +1598,11 @@ int launch_bwd_tc(const Geometry& g, const void* feat, const float* coef, const 
   CUtensorMap tmap;
   int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
+  if (g.split && !bwd_flow_applies(g)) {
+    set_error("CROSSCLR_PATH_TC_SPLIT needs the dataflow backward: >= 2048 stacked rows and dim <= 1024 (got %d rows, dim %d)",
+              g.rows, g.dvalid);
+    return CROSSCLR_EINVAL;
+  }
   if (bwd_flow_applies(g))                             // producer pairs -> P-tile pool -> consumer pairs (flow_kernels.cu)
     return launch_bwd_flow(g, feat, coef, scal, dfhat, dfhat_late, two_partials, scratch, st);
   if (const int csize = pair_cluster_size(g.dim)) {    // > 1 slab would recompute S: role-specialised CTA clusters

@@ -26,8 +26,9 @@ import torch.nn as nn
 from . import _native as N
 
 _DTYPE_CODE = {torch.float32: N.F32, torch.float16: N.F16, torch.bfloat16: N.BF16}
-_FEAT_TORCH = {N.F32: torch.float32, N.F16: torch.float16}
-_PATH_CODE = {"auto": N.PATH_AUTO, "simt": N.PATH_SIMT, "tc": N.PATH_TC}
+_FEAT_TORCH = {N.F32: torch.float32, N.F16: torch.float16, N.F16X2: torch.float16}
+_PATH_CODE = {"auto": N.PATH_AUTO, "simt": N.PATH_SIMT, "tc": N.PATH_TC, "split": N.PATH_TC_SPLIT}
+_FORCED = {"tc": N.PATH_TC, "split": N.PATH_TC_SPLIT}       # "simt" goes through crossclr_choose_path(exact=1)
 
 
 def _ptr(t):
@@ -74,10 +75,11 @@ class _NativeOps:
     def __init__(self):
         self.lib = N.load()
 
-    def plan(self, prob, in_dtype, exact, force_tc=False):
-        """(path code, stacked-row dtype, stacked-row pitch in elements) the library picks for this problem."""
-        if force_tc:
-            code = N.PATH_TC          # any shape (zero padding); a temperature outside its range is refused at launch
+    def plan(self, prob, in_dtype, exact, force=None):
+        """(path code, stacked-row dtype, stacked-row pitch in elements) the library picks for this problem; `force`: a path
+        code to take as is (a shape or temperature outside its range is refused at launch)."""
+        if force:
+            code = force
         else:
             code = self.lib.crossclr_choose_path(ctypes.byref(prob), _DTYPE_CODE[in_dtype], 1 if exact else 0)
             if code < 0:
@@ -88,15 +90,19 @@ class _NativeOps:
         """Rows per segment of the stacked matrix / stats / coef of a path (the tensor-core layout pads segments to 128 rows)."""
         return int(self.lib.crossclr_segment_rows(code, bseg))
 
-    def pack(self, x, feat_out, rnorm_out):
+    def _feat_code(self, feat_out, code):
+        return _DTYPE_CODE[feat_out.dtype] if code is None else self.lib.crossclr_feature_dtype(code)
+
+    def pack(self, x, feat_out, rnorm_out, code=None):
         B, D = x.shape
         N.check(self.lib.crossclr_pack(_ptr(x), _DTYPE_CODE[x.dtype], x.stride(0), B, D, _ptr(feat_out),
-                                       _DTYPE_CODE[feat_out.dtype], _ptr(rnorm_out), _stream()), "crossclr_pack")
+                                       self._feat_code(feat_out, code), _ptr(rnorm_out), _stream()), "crossclr_pack")
 
-    def pack2(self, v, t, feat_out, rnorm_out):
+    def pack2(self, v, t, feat_out, rnorm_out, code=None):
+        """`code`: the path the rows are for (fixes the row layout); None: plain rows of feat_out's dtype."""
         B, D = v.shape
         N.check(self.lib.crossclr_pack2(_ptr(v), _ptr(t), _DTYPE_CODE[v.dtype], v.stride(0), t.stride(0), B, D,
-                                        _ptr(feat_out), _DTYPE_CODE[feat_out.dtype], _ptr(rnorm_out), _stream()),
+                                        _ptr(feat_out), self._feat_code(feat_out, code), _ptr(rnorm_out), _stream()),
                 "crossclr_pack2")
 
     def forward_single(self, prob, code, v, t, feat_all, rnorm, stats, coef, scal, loss):
@@ -137,7 +143,7 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     dev = v.device
     world, rank = _group_info(group)
     prob = N.Problem(2 * world, B, D, 2 * rank * B, 2 * B, float(temperature), float(negative_weight))
-    code, feat_dtype, pitch = ops.plan(prob, v.dtype, path == "simt", path == "tc")
+    code, feat_dtype, pitch = ops.plan(prob, v.dtype, path == "simt", _FORCED.get(path))
     S = ops.seg_rows(code, B)                                   # rows per segment in the path's layout (>= B: zero padding)
     rows = 2 * world * S
     feat_all = torch.empty((2 * world, S, pitch), dtype=feat_dtype, device=dev)
@@ -151,7 +157,7 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
         return loss, prob, code, (feat_all, rnorm, coef, scal)
     import torch.distributed as dist
     feat_loc = feat_all[2 * rank:2 * rank + 2]
-    ops.pack2(v, t, feat_loc, rnorm)
+    ops.pack2(v, t, feat_loc, rnorm, code)
     # in-place all-gather: rank r's block already sits at its slot of the output
     dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1), group=group)
     ops.fwd(prob, code, feat_all, stats)
@@ -222,7 +228,7 @@ def _plan_py(B, D, path, in_dtype, temperature, negative_weight):
     kernels' rule."""
     prob = N.Problem(2, B, D, 0, 2 * B, float(temperature), float(negative_weight))
     ops = _ops()
-    code, fdt, pitch = ops.plan(prob, torch.float32 if in_dtype == torch.float64 else in_dtype, path == "simt", path == "tc")
+    code, fdt, pitch = ops.plan(prob, torch.float32 if in_dtype == torch.float64 else in_dtype, path == "simt", _FORCED.get(path))
     return fdt, pitch, ops.seg_rows(code, B)
 
 
@@ -251,7 +257,11 @@ def _op_backward(feat: torch.Tensor, rnorm: torch.Tensor, coef: torch.Tensor, sc
                  batch: int, dim: int, temperature: float, negative_weight: float, path: str, grad_scale: float,
                  out_dtype: int) -> tuple[torch.Tensor, torch.Tensor]:
     prob = N.Problem(2, batch, dim, 0, 2 * batch, float(temperature), float(negative_weight))
-    code = N.PATH_SIMT if feat.dtype == torch.float32 else N.PATH_TC
+    if feat.dtype == torch.float32:
+        code = N.PATH_SIMT
+    else:                                  # the saved rows tell which tensor-core layout the forward used
+        split_pitch = int(_ops().lib.crossclr_feature_pitch(N.PATH_TC_SPLIT, dim))
+        code = N.PATH_TC_SPLIT if path == "split" or (path == "auto" and feat.shape[-1] == split_pitch) else N.PATH_TC
     with torch.cuda.device(feat.device):
         return _backward_impl(_ops(), prob, code, (feat, rnorm, coef, scal), grad_out, grad_scale,
                               _OUT_DTYPE[out_dtype])
@@ -315,7 +325,10 @@ class CrossCLR_onlyIntraModality(nn.Module):
     (defaults reproduce the reference's single-device behaviour):
       process_group  torch.distributed group whose ranks each hold a row shard of the global batch
       grad_scale     multiplies the returned gradients (set to world_size under DDP's gradient averaging)
-      path           "auto" | "tc" (tcgen05 kernels) | "simt" (exact-fp32 CUDA-core kernels)
+      path           "auto" | "tc" (tcgen05 kernels, fp16 operands) | "split" (tcgen05 kernels, fp32 inputs as fp16 hi + lo
+                     pairs) | "simt" (exact-fp32 CUDA-core kernels).  "auto": 16-bit inputs -> "tc"; fp32 inputs -> "split"
+                     where it applies (>= 1024 global samples, D <= 1024), else "simt"; temperatures below ~0.0073 and tiny
+                     shapes -> "simt"
     """
 
     def __init__(self, temperature=0.03, negative_weight=0.8, logger=None, *, process_group=None, grad_scale=1.0,

@@ -47,12 +47,17 @@ extern "C" {
 #define CROSSCLR_F32  0
 #define CROSSCLR_F16  1
 #define CROSSCLR_BF16 2
+#define CROSSCLR_F16X2 3              /* stacked rows only: fp16 hi + lo pairs of CROSSCLR_PATH_TC_SPLIT                */
 
 /* kernel families ("path") */
 #define CROSSCLR_PATH_AUTO 0          /* crossclr_choose_path decides                                 */
 #define CROSSCLR_PATH_SIMT 1          /* fp32 CUDA-core kernels, any B / D, fp32 stacked features     */
 #define CROSSCLR_PATH_TC   2          /* tcgen05 + TMA + TMEM kernels, fp16 stacked rows, any B / D:
                                          segments are zero-padded to 128 rows, rows to 64 columns     */
+#define CROSSCLR_PATH_TC_SPLIT 3      /* the same kernels on fp32 inputs kept as fp16 hi + lo pairs: the similarity
+                                         product runs over K = 3 D as [hi | lo | hi] x [hi | hi | lo], i.e.
+                                         hi.hi + lo.hi + hi.lo -- fp32-grade logits (the dropped lo.lo term is 2^-24).
+                                         Needs >= 2048 stacked rows and dim <= 1024 (dataflow backward only)        */
 
 /* Stacked rows of the tensor-core path.  The layout is PADDED: every segment holds crossclr_segment_rows(path, bseg) =
  * roundup(bseg, 128) rows, of which the first bseg are the caller's and the rest are zero rows (q = 1), and every row holds
@@ -72,6 +77,8 @@ extern "C" {
  *                  cost 1.6e-3 on the gradients -- hence fp16 rows for bf16 inputs too.)
  *   fp32 inputs:   the same rescale, then rounded to fp16 (operand rounding 2^-12: gradients within ~2e-5 / tau of the
  *                  reference; exact again if the values happen to be 16-bit representable).
+ * CROSSCLR_PATH_TC_SPLIT rows are [hi (Dp) | lo (Dp) | tail]: hi = fp16(f), lo = fp16(f - hi) of the rescaled fp32 row f; Dp here
+ * is roundup(dim, 128) (roundup(dim, 256) above 512) and the pitch 2 Dp + CROSSCLR_ROW_TAIL.
  * The SIMT path keeps plain fp32 normalised rows, pitch dim, bseg rows per segment, no tail. */
 #define CROSSCLR_ROW_TAIL 64
 
@@ -91,9 +98,11 @@ CROSSCLR_API const char* crossclr_last_error(void);
 /* 1 if `device` can run this library (compute capability 10.x), 0 otherwise, <0 on error. */
 CROSSCLR_API int crossclr_device_supported(int device);
 
-/* Resolve CROSSCLR_PATH_AUTO for a problem and input dtype: CROSSCLR_PATH_TC when the temperature allows it and the shape
- * is not so small that the zero padding would dominate (bseg >= 96 and dim >= 48), else CROSSCLR_PATH_SIMT.  exact != 0
- * forces the fp32 SIMT path.
+/* Resolve CROSSCLR_PATH_AUTO for a problem and input dtype.  16-bit inputs: CROSSCLR_PATH_TC when the temperature allows it
+ * and the shape is not so small that the zero padding would dominate (bseg >= 96 and dim >= 48), else CROSSCLR_PATH_SIMT.
+ * fp32 inputs are never rounded to fp16 behind the caller's back (the reference multiplies them in fp32,
+ * trainer/loss.py:83-88): CROSSCLR_PATH_TC_SPLIT where it applies, else CROSSCLR_PATH_SIMT; CROSSCLR_PATH_TC on fp32 inputs
+ * (operands rounded to fp16, gradients within ~2e-5 / tau) is an explicit opt-in.  exact != 0 forces the fp32 SIMT path.
  * Temperature: the TC kernels use ONE log2-domain shift for all rows, which keeps every row representable while
  * log2e * max(1,|w|) / tau <= 200 (tau >= ~0.0073 at |w| <= 1); they return CROSSCLR_EINVAL beyond.  The SIMT path switches to
  * per-row online maxima in the log2 domain there and follows the reference's max-subtracted float64 softmax
@@ -101,13 +110,14 @@ CROSSCLR_API int crossclr_device_supported(int device);
  * coef[2g+0] = log2 Z_g (not 1 / Z_g). */
 CROSSCLR_API int crossclr_choose_path(const crossclr_problem_t* p, int in_dtype, int exact);
 
-/* Stacked-row element type a path consumes: SIMT -> CROSSCLR_F32, TC -> CROSSCLR_F16. */
+/* Stacked-row element type a path consumes: SIMT -> CROSSCLR_F32, TC -> CROSSCLR_F16, TC_SPLIT -> CROSSCLR_F16X2 (fp16 storage). */
 CROSSCLR_API int crossclr_feature_dtype(int path);
 
-/* Row pitch (in elements) of the stacked matrix of a path: dim for SIMT, roundup(dim, 64) + CROSSCLR_ROW_TAIL for TC. */
+/* Row pitch (in elements) of the stacked matrix of a path: dim for SIMT, roundup(dim, 64) + CROSSCLR_ROW_TAIL for TC,
+ * 2 Dp + CROSSCLR_ROW_TAIL for TC_SPLIT. */
 CROSSCLR_API int64_t crossclr_feature_pitch(int path, int32_t dim);
 
-/* Rows per segment of the stacked matrix (and of stats / coef) of a path: bseg for SIMT, roundup(bseg, 128) for TC. */
+/* Rows per segment of the stacked matrix (and of stats / coef) of a path: bseg for SIMT, roundup(bseg, 128) for TC / TC_SPLIT. */
 CROSSCLR_API int64_t crossclr_segment_rows(int path, int32_t bseg);
 
 /* Bytes of scratch crossclr_bwd needs for this problem and path (crossclr_fwd needs none). */

@@ -16,14 +16,14 @@ from oracle import crossclr_oracle as O  # noqa: E402
 
 
 def main():
-    for B, D, al in ((512, 256, 2.0), (512, 256, 0.0), (2048, 512, 2.0), (1024, 128, 1.0)):
+    for B, D, al in ((2048, 512, 2.0), (1024, 128, 1.0), (4096, 512, 0.0)):
         g = torch.Generator().manual_seed(B + D)
         v = torch.randn(B, D, generator=g)
         t = v + al * torch.randn(B, D, generator=g) if al else torch.randn(B, D, generator=g)
         for tau in (0.07, 0.03, 0.02, 0.015, 0.01, 0.0075):
             rl, rdv, rdt = O.loss_and_grads(v.numpy(), t.numpy(), tau, 0.8)
             out = []
-            for path in ("tc", "simt"):
+            for path in ("tc", "auto", "simt"):
                 vd, td = v.cuda().requires_grad_(), t.cuda().requires_grad_()
                 loss = M.CrossCLR_onlyIntraModality(tau, 0.8, path=path)(vd, td)
                 loss.backward()

@@ -35,17 +35,25 @@ def test_planning_and_validation_without_a_device():
     ok = P(2, 4096, 512, 0, 8192, 0.03, 0.8)
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 0) == N.PATH_TC
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.F16, 0) == N.PATH_TC
-    assert lib.crossclr_choose_path(ctypes.byref(ok), N.F32, 0) == N.PATH_TC
+    # fp32 inputs are not rounded to fp16 unasked: hi + lo operands where the dataflow backward applies, else the exact path
+    assert lib.crossclr_choose_path(ctypes.byref(ok), N.F32, 0) == N.PATH_TC_SPLIT
+    assert lib.crossclr_choose_path(ctypes.byref(P(2, 256, 512, 0, 512, 0.03, 0.8)), N.F32, 0) == N.PATH_SIMT
+    assert lib.crossclr_choose_path(ctypes.byref(P(2, 4096, 2048, 0, 8192, 0.03, 0.8)), N.F32, 0) == N.PATH_SIMT
+    assert lib.crossclr_feature_dtype(N.PATH_TC_SPLIT) == N.F16X2
+    assert lib.crossclr_feature_pitch(N.PATH_TC_SPLIT, 512) == 2 * 512 + N.ROW_TAIL
+    assert lib.crossclr_feature_pitch(N.PATH_TC_SPLIT, 500) == 2 * 512 + N.ROW_TAIL
+    assert lib.crossclr_feature_pitch(N.PATH_TC_SPLIT, 600) == 2 * 768 + N.ROW_TAIL
+    assert lib.crossclr_segment_rows(N.PATH_TC_SPLIT, 1000) == 1024
     assert lib.crossclr_choose_path(ctypes.byref(ok), N.BF16, 1) == N.PATH_SIMT
     # ragged shapes ride the tensor-core path on a zero-padded layout; tiny ones (padding would dominate) stay exact
     ragged = P(2, 100, 72, 0, 200, 0.03, 0.8)
-    assert lib.crossclr_choose_path(ctypes.byref(ragged), N.F32, 0) == N.PATH_TC
+    assert lib.crossclr_choose_path(ctypes.byref(ragged), N.BF16, 0) == N.PATH_TC
     assert lib.crossclr_segment_rows(N.PATH_TC, 100) == 128 and lib.crossclr_segment_rows(N.PATH_SIMT, 100) == 100
     assert lib.crossclr_feature_pitch(N.PATH_TC, 72) == 128 + N.ROW_TAIL and lib.crossclr_feature_pitch(N.PATH_SIMT, 72) == 72
     assert lib.crossclr_segment_rows(N.PATH_TC, 4000) == 4096 and lib.crossclr_feature_pitch(N.PATH_TC, 500) == 512 + N.ROW_TAIL
     assert lib.crossclr_workspace_bytes(ctypes.byref(ragged), N.PATH_TC) >= 2 * 256 * 128 * 4
     tiny = P(2, 8, 4, 0, 16, 0.03, 0.8)
-    assert lib.crossclr_choose_path(ctypes.byref(tiny), N.F32, 0) == N.PATH_SIMT
+    assert lib.crossclr_choose_path(ctypes.byref(tiny), N.BF16, 0) == N.PATH_SIMT
     # temperatures below the tensor-core kernels' range go to the exact path's online-maximum mode
     cold = P(2, 4096, 512, 0, 8192, 0.005, 0.8)
     assert lib.crossclr_choose_path(ctypes.byref(cold), N.BF16, 0) == N.PATH_SIMT

@@ -25,7 +25,7 @@ class NumpyOps:
     def __init__(self, pad=1):
         self.pad = pad
 
-    def plan(self, prob, in_dtype, exact, force_tc=False):
+    def plan(self, prob, in_dtype, exact, force=None):
         from crossmodal_contrastive_learning_b200 import _native as N
         return N.PATH_SIMT, torch.float32, prob.dim
 
@@ -41,7 +41,7 @@ class NumpyOps:
     def _shift(prob):
         return max(0.0, LOG2E * max(1.0, abs(prob.negative_weight)) / prob.temperature - 96.0)
 
-    def pack2(self, v, t, feat_out, rnorm_out):
+    def pack2(self, v, t, feat_out, rnorm_out, code=None):
         B = v.shape[0]
         feat_out.zero_()
         for k, x in enumerate((v, t)):

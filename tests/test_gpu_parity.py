@@ -115,6 +115,42 @@ def test_tc_matches_reference_goldens(path):
         check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL)
 
 
+@pytest.mark.parametrize("B,D,world,tau,noise", [(1024, 512, 1, 0.03, 2.0), (4096, 512, 1, 0.03, 2.0), (4096, 512, 1, 0.01, 4.0),
+                                                 (2048, 256, 2, 0.03, 2.0), (1500, 500, 1, 0.02, 2.0), (2048, 1024, 1, 0.03, 2.0),
+                                                 (4096, 640, 4, 0.0075, 8.0)])
+def test_fp32_inputs_take_the_split_path(B, D, world, tau, noise):
+    """The reference multiplies fp32 features in fp32 (trainer/loss.py:83-88).  `auto` keeps fp32 inputs on the tensor cores as
+    fp16 hi + lo pairs -- S = hi.hi + lo.hi + hi.lo over K = 3 D -- so that nothing the caller passed is rounded to fp16:
+    full-precision random inputs, several temperatures, single rank and row bands, against the float64 oracle at the
+    tolerance the exact-operand path holds for 16-bit inputs (what is left is the fp16 probability tile)."""
+    from oracle import crossclr_oracle as O
+    from crossmodal_contrastive_learning_b200 import _native as N, loss as L
+    Bl = B // world
+    prob = N.Problem(2 * world, Bl, D, 0, 2 * Bl, tau, 0.8)
+    assert L._ops().plan(prob, torch.float32, False)[0] == N.PATH_TC_SPLIT
+    # `noise` keeps the problem un-converged at the small temperatures: at a loss of ~1e-12 the float64 reference itself is
+    # rounding noise (its softmax - onehot cancels to the last bits), and so is the oracle that restates it
+    g = torch.Generator().manual_seed(B + D + world)
+    v = torch.randn(B, D, generator=g)
+    t = v + noise * torch.randn(B, D, generator=g)
+    rows = None if B <= 2048 else np.arange(0, B, B // 24) + 1
+    rloss, rdv, rdt = O.loss_and_grads(v.numpy(), t.numpy(), tau, 0.8, rows=rows, row_block=2048)
+    assert rloss > 1e-6
+    loss, dv, dt = _run_ranks_on_one_gpu(v.cuda(), t.cuda(), world, tau, 0.8, "auto")
+    if rows is not None:
+        dv, dt = dv[rows], dt[rows]
+    # below tau ~ 0.02 the softmax of this data is peaky: a few dominant probabilities carry their own fp16 rounding (2^-11)
+    # and the tensor cores' fp32 accumulation error (~1e-6 of a logit's cosine, times log2e / tau) shows; still inside 1e-3
+    tol = TOL_RAW if tau >= 0.02 else 5e-4
+    check(loss, dv, dt, rloss, rdv, rdt, tol)
+    # the module takes the same path and returns the same numbers
+    if world == 1:
+        lm, dvm, dtm = run_gpu(v.numpy(), t.numpy(), tau, 0.8, path="auto")
+        if rows is not None:
+            dvm, dtm = dvm[rows], dtm[rows]
+        check(lm, dvm, dtm, rloss, rdv, rdt, tol)
+
+
 @pytest.mark.parametrize("B,D,world", [(4000, 500, 1), (333, 77, 1), (1000, 200, 1), (130, 70, 1), (2100, 520, 1), (600, 72, 4),
                                        (3000, 500, 3), (4000, 1000, 2)])
 def test_ragged_shapes_on_the_tensor_core_path(B, D, world):
@@ -388,7 +424,7 @@ def _run_ranks_on_one_gpu(v, t, world, tau, w, path):
     Bg, D = v.shape
     B = Bg // world
     probs = [N.Problem(2 * world, B, D, 2 * r * B, 2 * B, tau, w) for r in range(world)]
-    code, fdt, pitch = ops.plan(probs[0], v.dtype, path == "simt", path == "tc")
+    code, fdt, pitch = ops.plan(probs[0], v.dtype, path == "simt", L._FORCED.get(path))
     S = ops.seg_rows(code, B)                 # the tensor-core layout pads every segment to a multiple of 128 rows
     feat = torch.empty((2 * world, S, pitch), dtype=fdt, device="cuda")
     rnorm = torch.empty((world, 2 * B), dtype=torch.float32, device="cuda")
@@ -399,7 +435,7 @@ def _run_ranks_on_one_gpu(v, t, world, tau, w, path):
     go = torch.ones((), dtype=torch.float64, device="cuda")
     dv, dt = torch.empty_like(v, dtype=torch.float32), torch.empty_like(t, dtype=torch.float32)
     for r in range(world):
-        ops.pack2(v[r * B:(r + 1) * B], t[r * B:(r + 1) * B], feat[2 * r:2 * r + 2], rnorm[r])
+        ops.pack2(v[r * B:(r + 1) * B], t[r * B:(r + 1) * B], feat[2 * r:2 * r + 2], rnorm[r], code)
     for r in range(world):
         ops.fwd(probs[r], code, feat, stats)
     ops.finalize(probs[0], code, stats, coef, loss, scal)
