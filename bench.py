@@ -370,6 +370,52 @@ def run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush
     return out
 
 
+def run_shape_variant(M, NAT, torch, dev, flush, B, D, dtype, what, steps=20):
+    """A variant of the headline shape on ONE GPU -- ragged B / D, or fp32 features -- as the same one-graph-launch step
+    (`HostFedCrossCLR`, device-resident inputs): ms/step, the path the library chose, and parity of the eager module against
+    the CPU oracle on 64 sampled rows (fp32 gradients; checker use of oracle/ only)."""
+    import ctypes
+    import numpy as np
+    from oracle import crossclr_oracle as O
+    g = torch.Generator().manual_seed(B + D)
+    v = torch.randn(B, D, generator=g).to(dtype)
+    t = (v.float() + 2.0 * torch.randn(B, D, generator=g)).to(dtype)
+    crit = M.CrossCLR_onlyIntraModality(TAU, W).to(dev)
+    pipe = M.HostFedCrossCLR(crit, B, D, dtype=dtype, device=dev, feed="device")
+    for s_ in range(2):
+        pipe.video[s_].detach().copy_(v.to(dev))
+        pipe.text[s_].detach().copy_(t.to(dev))
+    for _ in range(3):
+        pipe.step()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a_, b_ in evs:
+        flush.zero_()
+        a_.record()
+        pipe.step()
+        b_.record()
+    torch.cuda.synchronize()
+    ts = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
+    prob = NAT.Problem(2, B, D, 0, 2 * B, TAU, W)
+    lib = M.load_native()
+    code = lib.crossclr_choose_path(ctypes.byref(prob), {torch.float32: NAT.F32, torch.float16: NAT.F16, torch.bfloat16: NAT.BF16}[dtype], 0)
+    rows = np.arange(0, B, max(1, B // 64))[:64]
+    rl, rdv, rdt = O.loss_and_grads(v.float().numpy(), t.float().numpy(), TAU, W, rows=rows, row_block=2048)
+    vd = v.float().to(dev).requires_grad_()       # fp32 tensors of the same values: fp32 gradients out
+    td = t.float().to(dev).requires_grad_()
+    loss = crit(vd, td)
+    loss.backward()
+    dv, dt = vd.grad.double().cpu().numpy()[rows], td.grad.double().cpu().numpy()[rows]
+    del pipe
+    return {"what": what, "B": B, "D": D, "in_dtype": str(dtype).replace("torch.", ""), "ms_per_step": ts[len(ts) // 2],
+            "ms_per_step_is": f"median of {steps} one-graph-launch steps (pack + forward + backward), device events, L2 flushed",
+            "path": {NAT.PATH_SIMT: "simt", NAT.PATH_TC: "tc", NAT.PATH_TC_SPLIT: "tc_split"}.get(code, str(code)),
+            "bwd_kernel": lib.crossclr_bwd_kernel_name(ctypes.byref(prob), code).decode() if code > 0 else "",
+            "parity": {"loss_rel": abs(float(loss.item()) - rl) / abs(rl), "dv_rel": float(np.linalg.norm(dv - rdv) / np.linalg.norm(rdv)),
+                       "dt_rel": float(np.linalg.norm(dt - rdt) / np.linalg.norm(rdt)), "rows_checked": int(len(rows)),
+                       "inputs": "the timed values as fp32 tensors through the eager module (fp32 inputs take the fp32 rule of `auto`)"}}
+
+
 def bwd_kernel_from_library(M, NAT, world, rank, Bl, D):
     import ctypes
     lib = M.load_native()
@@ -575,6 +621,18 @@ def run_b200_arm(args):
                 extras[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
             barrier()
 
+    shapes = {}
+    if not args.no_extras and world == 1 and args.workload in (None, "c2"):
+        # f3 coverage next to the headline: the same step on ragged B / D and on fp32 features (reference: any [B, D], fp32 GEMMs)
+        for key, (B_, D_, dt_, what) in {
+                "c2_ragged": (4000, 500, torch.bfloat16, "ragged neighbour of c2 on the tensor-core path (zero-padded layout)"),
+                "c2_fp32": (4096, 512, torch.float32, "c2 with fp32 features: fp16 hi + lo operand pairs, K = 3 D"),
+                "c2_fp32_ragged": (4000, 500, torch.float32, "both")}.items():
+            try:
+                shapes[key] = run_shape_variant(M, NAT, torch, dev, flush, B_, D_, dt_, what)
+            except Exception as exc:
+                shapes[key] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
     cb = None
     if rank == 0 and not args.no_cpu_baseline:
         cb, _, _ = time_reference(Bg, D, steps=3, warmup=1, max_seconds=30.0)
@@ -632,6 +690,8 @@ def run_b200_arm(args):
             line["parity"] = parity
         if extras:
             line["workloads"] = extras
+        if shapes:
+            line["shapes"] = shapes
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

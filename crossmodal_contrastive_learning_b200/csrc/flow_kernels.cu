@@ -216,7 +216,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   auto TR = [&](int role, uint32_t tile, int ev) {
     if (P.trace != nullptr && tile < 64) P.trace[(role * 64 + tile) * 8 + ev] = global_ns();
   };
-  unsigned long long* const pair_stamp = P.trace != nullptr ? P.trace + 2 * 64 * 8 + (blockIdx.x >> 1) * 4 : nullptr;
+  unsigned long long* const pair_stamp = P.trace != nullptr ? P.trace + 3 * 64 * 8 + (blockIdx.x >> 1) * 4 : nullptr;
   const uint32_t sub = cluster_ctarank();              // position in the pair = which 128 rows of a 256-row block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x >> 1;
@@ -591,7 +591,9 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
         tmem_ld32(lane_base, va);
       }
       uint32_t t = 0;
+      const bool tracer = prod == 0 && sub == 0 && r == 0 && wg == 0;
       while (have) {
+        if (tracer) TR(2, t, 0);
         const bool have_next = walk.next(nx);
         if (tl.I != cur_I) {
           cur_I = tl.I;
@@ -623,6 +625,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           }
         }
         __syncwarp();
+        if (tracer) TR(2, t, 1);
         const float a_i = iz_i * ks;
         const uint32_t buf = t & 1;
         const uint32_t tb = lane_base + buf * FLOW_TN;
@@ -643,6 +646,10 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           uint32_t packed[16];
           const float4* cv4 = reinterpret_cast<const float4*>(cv) + c * 16;
           const uint64_t k2 = pack2(k, k), ns2 = pack2(nshift_i, nshift_i), a2 = pack2(a_i, a_i);
+          if (P.exp & 16) {                                          // perf experiment: no arithmetic (wrong results)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) packed[q] = v[2 * q] ^ v[2 * q + 1];
+          } else
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
             const float4 cc = cv4[q >> 1];                         // (q_j, q_j+1, w_j, w_j+1) of columns q, q + 1
@@ -663,25 +670,35 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
             for (int i = 0; i < 16; ++i)
               if (i == pi) packed[i] &= keep;
           }
+          if (P.exp & 32) {                                          // perf experiment: one store instead of four
+            st_global_v4(prow + (c * 4) * (TM * 16), packed[0] ^ packed[4] ^ packed[8] ^ packed[12], packed[1] ^ packed[5] ^ packed[9] ^ packed[13],
+                         packed[2] ^ packed[6] ^ packed[10] ^ packed[14], packed[3] ^ packed[7] ^ packed[11] ^ packed[15]);
+            return;
+          }
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
             st_global_v4(prow + (c * 4 + ch) * (TM * 16), packed[ch * 4 + 0], packed[ch * 4 + 1], packed[ch * 4 + 2],
                          packed[ch * 4 + 3]);
         };
         tmem_ld_wait();                          // chunk 0 (va)
+        if (tracer) TR(2, t, 2);
         tmem_ld32(tb + 32, vb);
         p_chunk(va, 0);
+        if (tracer) TR(2, t, 3);
         tmem_ld_wait();                          // chunk 1 (vb)
         tmem_ld32(tb + 64, va);
         p_chunk(vb, 1);
+        if (tracer) TR(2, t, 4);
         tmem_ld_wait();                          // chunk 2 (va)
         tmem_ld32(tb + 96, vb);
         p_chunk(va, 2);
+        if (tracer) TR(2, t, 5);
         tmem_ld_wait();                          // chunk 3 (vb): this warp's part of the S tile is in registers
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_relaxed(buf ? sempty_ldr1 : sempty_ldr0);   // TMEM hand-back: relaxed (a release
                                                                               // arrive is a MEMBAR behind this warp's P stores)
+        if (tracer) TR(2, t, 6);
         bool prefetched = false;
         if (have_next && mbar_try_wait(sfull_bar(buf ^ 1), ((t + 1) >> 1) & 1)) {
           tc_fence_after();
@@ -699,6 +716,7 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           tc_fence_after();
           tmem_ld32(tb_next, va);
         }
+        if (tracer) TR(2, t, 7);
         ++t;
         tl = nx;
         have = have_next;
@@ -827,23 +845,24 @@ unsigned long long* flow_trace_buffer(cudaStream_t st) {
   static unsigned long long* trace = nullptr;
   static const bool want = getenv("CROSSCLR_FLOW_TRACE") != nullptr;
   if (!want) return nullptr;
-  if (trace == nullptr) cudaMalloc(&trace, (2 * 64 * 8 + 128 * 4) * 8);
-  cudaMemsetAsync(trace, 0, (2 * 64 * 8 + 128 * 4) * 8, st);
+  if (trace == nullptr) cudaMalloc(&trace, (3 * 64 * 8 + 128 * 4) * 8);
+  cudaMemsetAsync(trace, 0, (3 * 64 * 8 + 128 * 4) * 8, st);
   return trace;
 }
 void flow_trace_dump(unsigned long long* trace, cudaStream_t st, const FlowPlan& f) {
   if (trace == nullptr) return;
-  static unsigned long long host[2 * 64 * 8 + 128 * 4];
+  static unsigned long long host[3 * 64 * 8 + 128 * 4];
   cudaStreamSynchronize(st);
   cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
   FILE* fp = fopen(getenv("CROSSCLR_FLOW_TRACE"), "w");
   if (!fp) return;
   unsigned long long t0 = ~0ull;
-  for (int i = 0; i < 2 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
+  for (int i = 0; i < 3 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
   fprintf(fp, "# n_g %d n_s %d parts %d cnt %d sym %d nb %d nrb %d ds %d d0 %d cnt_main %d cnt_late %d\n", f.n_g, f.n_s, f.parts, f.cnt, f.sym, f.nb, f.nrb, f.ds, f.d0, f.cnt_main, f.cnt_late);
   fprintf(fp, "# role 0 = producer 0: mma_wait_sempty mma_start mma_issued epi_start staged_seen published epi_slot_ok epi_done\n");
   fprintf(fp, "# role 1 = consumer 0: poll_start desc_seen p_issued mma_wait_p p0_landed p1_landed mma_issued -   (ns since first stamp)\n");
-  for (int role = 0; role < 2; ++role)
+  fprintf(fp, "# role 2 = producer 0, epilogue warp 0: loop_top coef_staged chunk0_in_regs chunk0_done chunk1_done chunk2_done tmem_released next_tile_ready\n");
+  for (int role = 0; role < 3; ++role)
     for (int t = 0; t < 64; ++t) {
       fprintf(fp, "%d %2d", role, t);
       for (int e = 0; e < 8; ++e) {
@@ -854,7 +873,7 @@ void flow_trace_dump(unsigned long long* trace, cudaStream_t st, const FlowPlan&
     }
   fprintf(fp, "# per pair (consumers first, then producers): first_ns last_ns waited_ns late_consumer_done_ns\n");
   for (int p = 0; p < f.n_g + f.n_s && p < 128; ++p) {
-    const unsigned long long* q = host + 2 * 64 * 8 + p * 4;
+    const unsigned long long* q = host + 3 * 64 * 8 + p * 4;
     fprintf(fp, "P %3d %s %8lld %8lld %8lld %4lld\n", p, p < f.n_g ? "cons" : "prod", q[0] ? (long long)(q[0] - t0) : -1ll,
             q[1] ? (long long)(q[1] - t0) : -1ll, (long long)q[2], q[3] ? (long long)(q[3] - t0) : -1ll);
   }
