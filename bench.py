@@ -610,17 +610,7 @@ def run_b200_arm(args):
         parity = parity_vs_oracle(crit, v_dev, t_dev, va.float().numpy(), ta.float().numpy(), lo, torch, dist, world, dev)
         del va, ta
 
-    extras = {}
-    if not args.no_extras:
-        for name in (["c3"] if world == 1 else []) + ["c4", "c5"]:
-            if name == args.workload:
-                continue
-            try:
-                extras[name] = run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush)
-            except Exception as exc:
-                extras[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
-            barrier()
-
+    # (before the large workloads: the seconds after c5's 0.3 s steps run at reduced clocks under the power cap)
     shapes = {}
     if not args.no_extras and world == 1 and args.workload in (None, "c2"):
         # f3 coverage next to the headline: the same step on ragged B / D and on fp32 features (reference: any [B, D], fp32 GEMMs)
@@ -632,6 +622,17 @@ def run_b200_arm(args):
                 shapes[key] = run_shape_variant(M, NAT, torch, dev, flush, B_, D_, dt_, what)
             except Exception as exc:
                 shapes[key] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+
+    extras = {}
+    if not args.no_extras:
+        for name in (["c3"] if world == 1 else []) + ["c4", "c5"]:
+            if name == args.workload:
+                continue
+            try:
+                extras[name] = run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush)
+            except Exception as exc:
+                extras[name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            barrier()
 
     cb = None
     if rank == 0 and not args.no_cpu_baseline:

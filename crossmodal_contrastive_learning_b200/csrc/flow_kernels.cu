@@ -646,10 +646,6 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
           uint32_t packed[16];
           const float4* cv4 = reinterpret_cast<const float4*>(cv) + c * 16;
           const uint64_t k2 = pack2(k, k), ns2 = pack2(nshift_i, nshift_i), a2 = pack2(a_i, a_i);
-          if (P.exp & 16) {                                          // perf experiment: no arithmetic (wrong results)
-#pragma unroll
-            for (int q = 0; q < 16; ++q) packed[q] = v[2 * q] ^ v[2 * q + 1];
-          } else
 #pragma unroll
           for (int q = 0; q < 32; q += 2) {
             const float4 cc = cv4[q >> 1];                         // (q_j, q_j+1, w_j, w_j+1) of columns q, q + 1
@@ -669,11 +665,6 @@ bwd_flow_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i == pi) packed[i] &= keep;
-          }
-          if (P.exp & 32) {                                          // perf experiment: one store instead of four
-            st_global_v4(prow + (c * 4) * (TM * 16), packed[0] ^ packed[4] ^ packed[8] ^ packed[12], packed[1] ^ packed[5] ^ packed[9] ^ packed[13],
-                         packed[2] ^ packed[6] ^ packed[10] ^ packed[14], packed[3] ^ packed[7] ^ packed[11] ^ packed[15]);
-            return;
           }
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
