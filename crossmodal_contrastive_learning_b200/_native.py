@@ -24,7 +24,7 @@ EXPORTS = (
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
     "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
-    "crossclr_bwd_kernel_name", "crossclr_feature_pitch", "crossclr_segment_rows", "crossclr_bwd_accumulate", "crossclr_bwd_finish",
+    "crossclr_bwd_kernel_name", "crossclr_feature_pitch", "crossclr_segment_rows", "crossclr_bwd_accumulate", "crossclr_bwd_finish", "crossclr_bwd_scale_grad",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
 
@@ -83,6 +83,8 @@ def _declare(lib):
     lib.crossclr_bwd_accumulate.argtypes = [P, c.c_int, vp, vp, vp, vp, c.c_size_t, vp]
     lib.crossclr_bwd_finish.restype = c.c_int
     lib.crossclr_bwd_finish.argtypes = [P, c.c_int, vp, vp, vp, vp, vp, c.c_float, vp, c.c_int64, vp, c.c_int64, c.c_int, vp, vp]
+    lib.crossclr_bwd_scale_grad.restype = c.c_int
+    lib.crossclr_bwd_scale_grad.argtypes = [P, c.c_int, vp, vp, vp, vp, c.c_float, c.c_float, vp, vp, vp]
     lib.crossclr_shift.restype = c.c_float
     lib.crossclr_shift.argtypes = [P]
     lib.crossclr_bwd_kernel_name.restype = c.c_char_p

@@ -282,6 +282,23 @@ int crossclr_bwd_finish(const crossclr_problem_t* p, int path, const void* feat,
                             (cudaStream_t)stream, dfhat2);
 }
 
+int crossclr_bwd_scale_grad(const crossclr_problem_t* p, int path, const void* feat, const float* coef, const float* scal,
+                            const double* grad_out, float grad_scale, float logit_scale, const void* workspace,
+                            double* dscale_out, void* stream) {
+  int rc = validate_problem(p);
+  if (rc) return rc;
+  CC_REQUIRE(feat && coef && scal && workspace && dscale_out, "crossclr_bwd_scale_grad: NULL pointer");
+  CC_REQUIRE(path == CROSSCLR_PATH_SIMT || path_is_tc(path), "crossclr_bwd_scale_grad: path must be SIMT or TC (got %d)", path);
+  CC_REQUIRE(std::isfinite(logit_scale) && logit_scale != 0.f, "crossclr_bwd_scale_grad: logit_scale must be finite and non-zero");
+  const bool tc = path_is_tc(path);
+  const Geometry g = make_geometry(p, path);
+  const float* dfhat2 = tc ? (const float*)((const char*)workspace + dfhat_bytes(g)) : nullptr;
+  // p->temperature is the EFFECTIVE temperature tau / s the kernels ran at
+  const double mult = (double)grad_scale / ((double)logit_scale * (double)g.rows_valid * (double)p->temperature);
+  return launch_scale_grad(g, feat, tc ? crossclr_feature_dtype(path) : CROSSCLR_F32, coef, scal, tc, grad_out, mult,
+                           (const float*)workspace, dfhat2, dscale_out, (cudaStream_t)stream);
+}
+
 int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const float* rnorm_owned, const float* coef,
                  const float* scal, const double* grad_out, float grad_scale, void* dv, int64_t dv_row_stride,
                  void* dt, int64_t dt_row_stride, int out_dtype, void* workspace, size_t workspace_bytes,

@@ -195,6 +195,8 @@ const char* bwd_tc_kernel_name(const Geometry& g);   // the backward kernel laun
 // flow_kernels.cu: dataflow backward (producer pairs -> P-tile pool -> consumer pairs), D <= 512
 size_t bwd_flow_scratch_bytes(int rows, int row_count);
 bool bwd_flow_applies(const Geometry& g);
+int launch_scale_grad(const Geometry& g, const void* feat, int feat_dtype, const float* coef, const float* scal, bool use_sigma,
+                      const double* grad_out, double mult, const float* dfhat, const float* dfhat2, double* out, cudaStream_t st);
 // dfhat_late: a second [row_count][dim] partial that the kernel fills when its plan uses late consumers (*used_late)
 int launch_bwd_flow(const Geometry& g, const void* feat_f16, const float* coef, const float* scal, float* dfhat,
                     float* dfhat_late, bool* used_late, void* scratch, cudaStream_t st);

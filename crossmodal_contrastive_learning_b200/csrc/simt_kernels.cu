@@ -660,6 +660,62 @@ static int grad_finish_16(const Geometry& g, const void* feat, const float* rnor
                                    dt_stride, out_dtype, st, dfhat2, two);
 }
 
+// ================================================================================================
+// scale_grad: d loss / d s for logits multiplied by a scalar s (an opt-in learnable temperature: the kernels ran at the effective
+// temperature tau / s).  With A_g = sum_j P_gj Fhat_j (the accumulated row, before the positive-pair term):
+//   sum_{g,j} P_gj cos_gj = 2 tau sum_g sum_{j in negatives} p_gj a_gj      (P, cos, kappa symmetric; a = kappa cos / tau)
+//   dL/ds = (1 / (s R)) sum_g [ sum_j p_gj a_gj - a_g,pos ] = (1 / (s R tau)) sum_g [ (A_g . Fhat_g) / 2 - rho_g (Fhat_g . Fhat_partner) ]
+// (the positive enters with p_pos - 1 = -rho_g; the masked diagonal has logit 0).  One warp per owned row, one double atomic per
+// warp; summing the ranks' results gives the gradient of the global loss.
+template <typename TF, bool kTail>
+__global__ void __launch_bounds__(256) scale_grad_kernel(Geometry g, const TF* __restrict__ F, const float* __restrict__ coef,
+                                                        const float* __restrict__ scal, bool use_sigma,
+                                                        const double* __restrict__ grad_out, double mult,
+                                                        const float* __restrict__ dfhat, const float* __restrict__ dfhat2,
+                                                        const unsigned int* __restrict__ two, double* __restrict__ out) {
+  const int l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (l >= g.row_count) return;
+  const int gr = g.row_begin + l;
+  if (gr % g.bseg >= g.bvalid) return;         // zero-padding row
+  const int pg = row_partner(gr, g.bseg);
+  const TF* fg = F + (int64_t)gr * g.pitch;
+  const TF* fp = F + (int64_t)pg * g.pitch;
+  const float qg = row_scale<TF, kTail>(fg, g), qp = row_scale<TF, kTail>(fp, g);
+  const float* dh = dfhat + (int64_t)l * g.dim;
+  const float* dh2 = (dfhat2 != nullptr && two != nullptr && *two != 0u) ? dfhat2 + (int64_t)l * g.dim : nullptr;
+  float d1 = 0.f, d2 = 0.f;
+  for (int d = lane; d < g.dim; d += 32) {
+    const float a = dh2 ? dh[d] + dh2[d] : dh[d];
+    const float f = row_elem<TF>(fg, d, g);
+    d1 = fmaf(a, f, d1);
+    d2 = fmaf(f, row_elem<TF>(fp, d, g), d2);
+  }
+  d1 = warp_sum(d1);
+  d2 = warp_sum(d2);
+  if (lane == 0) {
+    // the accumulated row is q_g sigma A_g on the tensor-core paths (A_g . Fhat_g = acc . f_g / sigma), A_g on the exact path
+    const double aa = (double)d1 * (use_sigma ? (double)scal[1] : 1.0);
+    const double pp = (double)d2 * (double)qg * (double)qp;
+    double c = (0.5 * aa - (double)coef[2 * (int64_t)gr + 1] * pp) * mult;
+    if (grad_out != nullptr) c *= grad_out[0];
+    atomicAdd(out, c);
+  }
+}
+
+int launch_scale_grad(const Geometry& g, const void* feat, int feat_dtype, const float* coef, const float* scal, bool use_sigma,
+                      const double* grad_out, double mult, const float* dfhat, const float* dfhat2, double* out, cudaStream_t st) {
+  const size_t part_bytes = ((size_t)g.row_count * (size_t)g.dim * sizeof(float) + 255) & ~(size_t)255;
+  const unsigned int* two = dfhat2 ? reinterpret_cast<const unsigned int*>(reinterpret_cast<const char*>(dfhat) + 2 * part_bytes) : nullptr;
+  cudaMemsetAsync(out, 0, sizeof(double), st);
+  dim3 block(256), grid((g.row_count + 7) / 8);
+  if (feat_dtype == CROSSCLR_F32)
+    scale_grad_kernel<float, false><<<grid, block, 0, st>>>(g, (const float*)feat, coef, scal, use_sigma, grad_out, mult, dfhat, nullptr, nullptr, out);
+  else
+    scale_grad_kernel<__half, true><<<grid, block, 0, st>>>(g, (const __half*)feat, coef, scal, use_sigma, grad_out, mult, dfhat, dfhat2, two, out);
+  return check_launch("scale_grad_kernel");
+}
+
 int launch_grad_finish(const Geometry& g, const void* feat, int feat_dtype, const float* rnorm,
                        const float* coef, const float* scal, bool use_sigma, const double* grad_out,
                        float grad_scale, const float* dfhat, void* dv, int64_t dv_stride, void* dt,

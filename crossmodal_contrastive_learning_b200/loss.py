@@ -119,12 +119,24 @@ class _NativeOps:
         N.check(self.lib.crossclr_finalize(ctypes.byref(prob), code, _ptr(stats), _ptr(coef), _ptr(loss), _ptr(scal),
                                            _stream()), "crossclr_finalize")
 
-    def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt):
+    def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt, dscale=None, logit_scale=1.0):
+        """dscale: optional 0-dim float64 tensor receiving d loss / d logit_scale (the problem then carries the effective
+        temperature tau / logit_scale); the gradient kernel, the scale gradient and the finish stage run as separate calls."""
         ws_bytes = int(self.lib.crossclr_workspace_bytes(ctypes.byref(prob), code))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feat_all.device)
-        N.check(self.lib.crossclr_bwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(rnorm), _ptr(coef), _ptr(scal),
-                                      _ptr(grad_out), grad_scale, _ptr(dv), dv.stride(0), _ptr(dt), dt.stride(0),
-                                      _DTYPE_CODE[dv.dtype], _ptr(ws), ws_bytes, _stream()), "crossclr_bwd")
+        if dscale is None:
+            N.check(self.lib.crossclr_bwd(ctypes.byref(prob), code, _ptr(feat_all), _ptr(rnorm), _ptr(coef), _ptr(scal),
+                                          _ptr(grad_out), grad_scale, _ptr(dv), dv.stride(0), _ptr(dt), dt.stride(0),
+                                          _DTYPE_CODE[dv.dtype], _ptr(ws), ws_bytes, _stream()), "crossclr_bwd")
+            return
+        N.check(self.lib.crossclr_bwd_accumulate(ctypes.byref(prob), code, _ptr(feat_all), _ptr(coef), _ptr(scal), _ptr(ws),
+                                                 ws_bytes, _stream()), "crossclr_bwd_accumulate")
+        N.check(self.lib.crossclr_bwd_scale_grad(ctypes.byref(prob), code, _ptr(feat_all), _ptr(coef), _ptr(scal), _ptr(grad_out),
+                                                 grad_scale, logit_scale, _ptr(ws), _ptr(dscale), _stream()),
+                "crossclr_bwd_scale_grad")
+        N.check(self.lib.crossclr_bwd_finish(ctypes.byref(prob), code, _ptr(feat_all), _ptr(rnorm), _ptr(coef), _ptr(scal),
+                                             _ptr(grad_out), grad_scale, _ptr(dv), dv.stride(0), _ptr(dt), dt.stride(0),
+                                             _DTYPE_CODE[dv.dtype], _ptr(ws), _stream()), "crossclr_bwd_finish")
 
 
 def _group_info(group):
@@ -166,14 +178,20 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     return loss, prob, code, (feat_all, rnorm, coef, scal)
 
 
-def _backward_impl(ops, prob, code, saved, grad_out, grad_scale, out_dtype):
+def _backward_impl(ops, prob, code, saved, grad_out, grad_scale, out_dtype, logit_scale=None):
+    """logit_scale: None, or the float value s the forward ran at (prob.temperature = tau / s); then a third result,
+    d loss / d s as a 0-dim float64 tensor, is returned."""
     feat_all, rnorm, coef, scal = saved
     dev = feat_all.device
     go = grad_out.detach().to(device=dev, dtype=torch.float64).contiguous()
     dv = torch.empty((prob.bseg, prob.dim), dtype=out_dtype, device=dev)
     dt = torch.empty((prob.bseg, prob.dim), dtype=out_dtype, device=dev)
-    ops.bwd(prob, code, feat_all, rnorm, coef, scal, go, float(grad_scale), dv, dt)
-    return dv, dt
+    if logit_scale is None:
+        ops.bwd(prob, code, feat_all, rnorm, coef, scal, go, float(grad_scale), dv, dt)
+        return dv, dt
+    ds = torch.empty((), dtype=torch.float64, device=dev)
+    ops.bwd(prob, code, feat_all, rnorm, coef, scal, go, float(grad_scale), dv, dt, ds, float(logit_scale))
+    return dv, dt, ds
 
 
 _native_ops = None
@@ -187,14 +205,24 @@ def _ops():
 
 
 class _CrossCLRFunction(torch.autograd.Function):
+    """logit_scale: None, or the module's `logit_scale` Parameter (opt-in learnable temperature): the kernels then run at the
+    effective temperature tau / logit_scale and the Parameter receives d loss / d logit_scale."""
+
     @staticmethod
-    def forward(ctx, video, text, temperature, negative_weight, path, group, grad_scale):
+    def forward(ctx, video, text, temperature, negative_weight, path, group, grad_scale, logit_scale=None):
         ops = _ops()
         _check_inputs(video, text)
         in_dtype = video.dtype
         if in_dtype == torch.float64:          # kernels compute in fp32; the reference's f64 inputs are down-cast
             video, text = video.float(), text.float()
         v, t = _rowmajor(video.detach()), _rowmajor(text.detach())
+        ctx.scale = None
+        if logit_scale is not None:
+            ctx.scale = float(logit_scale.detach())      # one host read per step: the kernels take the temperature by value
+            if not (ctx.scale > 0.0):
+                raise RuntimeError(f"logit_scale must stay positive (got {ctx.scale})")
+            ctx.scale_dtype = logit_scale.dtype
+            temperature = float(temperature) / ctx.scale
         with torch.cuda.device(v.device):
             loss, prob, code, saved = _forward_impl(ops, v, t, temperature, negative_weight, path, group)
         ctx.save_for_backward(*saved)
@@ -206,10 +234,12 @@ class _CrossCLRFunction(torch.autograd.Function):
         saved = ctx.saved_tensors
         out_dtype = torch.float32 if ctx.in_dtype == torch.float64 else ctx.in_dtype
         with torch.cuda.device(saved[0].device):
-            dv, dt = _backward_impl(_ops(), ctx.prob, ctx.code, saved, grad_out, ctx.grad_scale, out_dtype)
+            res = _backward_impl(_ops(), ctx.prob, ctx.code, saved, grad_out, ctx.grad_scale, out_dtype, ctx.scale)
+        dv, dt = res[0], res[1]
         if ctx.in_dtype == torch.float64:
             dv, dt = dv.double(), dt.double()
-        return dv, dt, None, None, None, None, None
+        ds = res[2].to(ctx.scale_dtype) if ctx.scale is not None else None
+        return dv, dt, None, None, None, None, None, ds
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -294,10 +324,10 @@ def _op_backward_formula(ctx, g_loss, g_feat, g_rnorm, g_coef, g_scal):
 _op_forward.register_autograd(_op_backward_formula, setup_context=_op_setup_context)
 
 
-def _criterion(video, text, temperature, negative_weight, path, group, grad_scale):
-    """Dispatch: custom ops on a single rank (traceable), the autograd.Function with a process group."""
-    if group is not None:
-        return _CrossCLRFunction.apply(video, text, temperature, negative_weight, path, group, grad_scale)
+def _criterion(video, text, temperature, negative_weight, path, group, grad_scale, logit_scale=None):
+    """Dispatch: custom ops on a single rank (traceable), the autograd.Function with a process group or a learnable scale."""
+    if group is not None or logit_scale is not None:
+        return _CrossCLRFunction.apply(video, text, temperature, negative_weight, path, group, grad_scale, logit_scale)
     _check_inputs(video, text)
     if video.dtype == torch.float64:          # kernels compute in fp32; autograd casts the gradients back
         video, text = video.float(), text.float()
@@ -329,10 +359,16 @@ class CrossCLR_onlyIntraModality(nn.Module):
                      pairs) | "simt" (exact-fp32 CUDA-core kernels).  "auto": 16-bit inputs -> "tc"; fp32 inputs -> "split"
                      where it applies (>= 1024 global samples, D <= 1024), else "simt"; temperatures below ~0.0073 and tiny
                      shapes -> "simt"
+      learnable_temperature  False (the reference: `logit_scale` is registered at trainer/loss.py:52 and never used) | True:
+                     every logit is multiplied by the `logit_scale` Parameter (effective temperature
+                     `temperature / logit_scale`) and the Parameter receives its gradient.  Costs one host read of the
+                     scalar per step (the kernels take the temperature by value), so such a step is not graph-capturable;
+                     with a process group each rank holds its own rows' share of the gradient, which DDP's all-reduce sums
+                     like any other parameter gradient (times `grad_scale`).
     """
 
     def __init__(self, temperature=0.03, negative_weight=0.8, logger=None, *, process_group=None, grad_scale=1.0,
-                 path="auto"):
+                 path="auto", learnable_temperature=False):
         super().__init__()
         self.logit_scale = nn.Parameter(torch.ones([]))            # trainer/loss.py:52 (registered, never used)
         self.criterion = torch.nn.CrossEntropyLoss(reduction='none')  # :53 (registered, never used)
@@ -344,6 +380,7 @@ class CrossCLR_onlyIntraModality(nn.Module):
         self.process_group = process_group
         self.grad_scale = grad_scale
         self.path = path
+        self.learnable_temperature = bool(learnable_temperature)
 
     def forward(self, video_features, text_features):
         """
@@ -355,7 +392,7 @@ class CrossCLR_onlyIntraModality(nn.Module):
         """
         # temperature / negative_w are read per call (trainer/loss.py:90-93, :99-100)
         return _criterion(video_features, text_features, self.temperature, self.negative_w, self.path,
-                          self.process_group, self.grad_scale)
+                          self.process_group, self.grad_scale, self.logit_scale if self.learnable_temperature else None)
 
 
 def crossclr_loss(video_features, text_features, temperature=0.03, negative_weight=0.8, *, process_group=None,

@@ -192,6 +192,17 @@ CROSSCLR_API int crossclr_bwd(const crossclr_problem_t* p, int path, const void*
                  size_t workspace_bytes, void* stream);
 
 /*
+ * Opt-in learnable temperature (the reference registers `logit_scale`, trainer/loss.py:52, and never uses it; SURVEY.md
+ * section 8 f3).  If the caller ran the problem at the effective temperature p->temperature = tau / logit_scale -- i.e. with every
+ * logit multiplied by the scalar s = logit_scale -- this writes d loss / d s of the OWNED rows' share of the global loss to
+ * dscale_out[0] (device double; summing the ranks' values gives the gradient), times grad_out[0] (NULL = 1) and grad_scale.
+ * Call it between crossclr_bwd_accumulate and the next use of `workspace` (it reads the accumulated rows): O(B D).
+ */
+CROSSCLR_API int crossclr_bwd_scale_grad(const crossclr_problem_t* p, int path, const void* feat, const float* coef,
+                            const float* scal, const double* grad_out, float grad_scale, float logit_scale,
+                            const void* workspace, double* dscale_out, void* stream);
+
+/*
  * The two stages of crossclr_bwd, callable on their own (crossclr_bwd == accumulate, then finish, on one stream):
  *   crossclr_bwd_accumulate  the similarity / gradient kernel: workspace[0 .. row_count*dim) (fp32) = for every owned row g
  *                            q_g sigma sum_j P_gj Fhat_j without the positive-pair term -- the O(B^2 D) part, the kernel

@@ -89,7 +89,7 @@ class NumpyOps:
         self.fwd(prob, code, feat_all, stats)
         self.finalize(prob, code, stats, coef, loss, scal)
 
-    def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt):
+    def bwd(self, prob, code, feat_all, rnorm, coef, scal, grad_out, grad_scale, dv, dt, dscale=None, logit_scale=1.0):
         real = self._real(prob)
         F = feat_all.reshape(-1, prob.dim).double().numpy()[real]
         R, bseg = F.shape[0], prob.bseg

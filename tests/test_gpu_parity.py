@@ -115,6 +115,78 @@ def test_tc_matches_reference_goldens(path):
         check(loss, dv, dt, float(g["loss"]), g["dv"].astype(np.float64), g["dt"].astype(np.float64), TOL)
 
 
+@pytest.mark.parametrize("B,D,dtype,path,tau,s0", [
+    (512, 256, torch.bfloat16, "tc", 0.03, 1.3), (512, 256, torch.bfloat16, "tc", 0.03, 0.4), (100, 40, torch.float32, "simt", 0.05, 1.3),
+    (2048, 256, torch.float32, "auto", 0.03, 1.3), (2048, 256, torch.float32, "auto", 0.03, 0.5), (333, 77, torch.bfloat16, "auto", 0.03, 0.6),
+    (128, 64, torch.float32, "auto", 0.006, 1.3)])
+def test_learnable_temperature_gradient(B, D, dtype, path, tau, s0):
+    """Opt-in extension: with learnable_temperature=True every logit is multiplied by the dormant
+    `logit_scale` Parameter (trainer/loss.py:52).  Loss and feature gradients equal the oracle's at temperature tau / s, and
+    d loss / d s equals the central difference of the float64 oracle loss in s."""
+    from oracle import crossclr_oracle as O
+    M = _mod()
+    h = 1e-4
+    v, t = _seeded(B, D, 5 + B + D, aligned=2.0, dtype=torch.bfloat16)
+    rloss, rdv, rdt = O.loss_and_grads(v, t, tau / s0, 0.8)
+    lp = O.loss_and_grads(v, t, tau / (s0 + h), 0.8)[0]
+    lm = O.loss_and_grads(v, t, tau / (s0 - h), 0.8)[0]
+    rds = (lp - lm) / (2 * h)
+    crit = M.CrossCLR_onlyIntraModality(tau, 0.8, path=path, learnable_temperature=True).cuda()
+    with torch.no_grad():
+        crit.logit_scale.fill_(s0)
+    vd = torch.from_numpy(v).to("cuda", dtype).requires_grad_()
+    td = torch.from_numpy(t).to("cuda", dtype).requires_grad_()
+    loss = crit(vd, td)
+    (2.0 * loss).backward()
+    tol = TOL if dtype == torch.float32 else 5e-3          # 16-bit gradients are rounded to the input dtype on the way out
+    check(loss.item(), vd.grad.double().cpu().numpy() / 2, td.grad.double().cpu().numpy() / 2, rloss, rdv, rdt, tol)
+    ds = crit.logit_scale.grad.item() / 2
+    # d loss / d s = (1/s) [ E_softmax(logit) - positive logit ], averaged over rows: the difference of two sums of size
+    # ~1/tau_eff that nearly cancel around the loss-optimal scale (s0 = 1.3 here: they are ~300 x their difference).  The bar is
+    # 1e-3 of the value plus 5e-6 of that size -- the tensor-core paths' ~1e-5 accuracy on each sum
+    assert abs(ds - rds) <= 1e-3 * abs(rds) + 5e-6 * s0 / tau, (ds, rds)
+    # the default stays the reference's: the Parameter is dormant and gets no gradient
+    ref = M.CrossCLR_onlyIntraModality(tau / s0, 0.8, path=path).cuda()
+    l2 = ref(vd.detach().requires_grad_(), td.detach().requires_grad_())
+    l2.backward()
+    assert abs(l2.item() - loss.item()) <= 1e-6 * abs(loss.item()) and ref.logit_scale.grad is None   # s0 is an fp32 Parameter
+
+
+def test_learnable_temperature_gradient_sums_over_ranks():
+    """Every rank's crossclr_bwd_scale_grad holds its own rows' share: the shares of a 4-rank job sum to the single-rank value."""
+    import ctypes
+    from crossmodal_contrastive_learning_b200 import _native as N, loss as L
+    ops = L._ops()
+    Bg, D, tau, s0 = 2048, 256, 0.03, 0.9
+    v, t = _seeded(Bg, D, 3, aligned=2.0)
+    vd, td = torch.from_numpy(v).to("cuda", torch.bfloat16), torch.from_numpy(t).to("cuda", torch.bfloat16)
+    totals = []
+    for world in (1, 4):
+        B = Bg // world
+        probs = [N.Problem(2 * world, B, D, 2 * r * B, 2 * B, tau / s0, 0.8) for r in range(world)]
+        code, fdt, pitch = ops.plan(probs[0], vd.dtype, False)
+        S = ops.seg_rows(code, B)
+        feat = torch.empty((2 * world, S, pitch), dtype=fdt, device="cuda")
+        rnorm = torch.empty((world, 2 * B), dtype=torch.float32, device="cuda")
+        stats = torch.empty((2 * world * S, 2), dtype=torch.float32, device="cuda")
+        coef = torch.empty_like(stats)
+        scal = torch.empty(4, dtype=torch.float32, device="cuda")
+        loss = torch.empty((), dtype=torch.float64, device="cuda")
+        go = torch.ones((), dtype=torch.float64, device="cuda")
+        dv, dt = torch.empty((Bg, D), dtype=torch.float32, device="cuda"), torch.empty((Bg, D), dtype=torch.float32, device="cuda")
+        ds = torch.zeros(world, dtype=torch.float64, device="cuda")
+        for r in range(world):
+            ops.pack2(vd[r * B:(r + 1) * B], td[r * B:(r + 1) * B], feat[2 * r:2 * r + 2], rnorm[r], code)
+        for r in range(world):
+            ops.fwd(probs[r], code, feat, stats)
+        ops.finalize(probs[0], code, stats, coef, loss, scal)
+        for r in range(world):
+            ops.bwd(probs[r], code, feat, rnorm[r], coef, scal, go, 1.0, dv[r * B:(r + 1) * B], dt[r * B:(r + 1) * B], ds[r], s0)
+        torch.cuda.synchronize()
+        totals.append(ds.sum().item())
+    assert abs(totals[0] - totals[1]) <= 1e-4 * abs(totals[0]), totals
+
+
 @pytest.mark.parametrize("B,D,world,tau,noise", [(1024, 512, 1, 0.03, 2.0), (4096, 512, 1, 0.03, 2.0), (4096, 512, 1, 0.01, 4.0),
                                                  (2048, 256, 2, 0.03, 2.0), (1500, 500, 1, 0.02, 2.0), (2048, 1024, 1, 0.03, 2.0),
                                                  (4096, 640, 4, 0.0075, 8.0)])
