@@ -92,26 +92,70 @@ __device__ __forceinline__ void fwd_special_chunk(const uint32_t (&v)[32], float
 constexpr int FWD_QSTAGES = 4;        // tiles of column scales in flight (shared-memory ring of the producer warp)
 constexpr int FWD2_THREADS = 640;       // warps 0-3: producer / MMA / TMEM alloc / idle; warps 4-19: epilogue
 
-// Tiles (row-block pair ib, column block jb) of a linear range, row-major.  Symmetric mode (single rank: the owned rows
-// are all rows, so the Gram matrix is square and symmetric): only jb >= ib, i.e. the upper triangle of 256 x 256 pair
-// tiles including the diagonal -- an off-diagonal tile then feeds the row sums of its rows AND, through its column sums,
-// the row sums of its columns' rows.
+// Tiles (row-block pair ib, column block jb) of one CTA pair.  Symmetric mode (single rank: the owned rows are all rows, so the
+// Gram matrix is square and symmetric): only jb >= ib, i.e. the upper triangle of 256 x 256 pair tiles including the
+// diagonal -- an off-diagonal tile then feeds the row sums of its rows AND, through its column sums, the row sums of its
+// columns' rows.
+//  * linear order (matrix fits the L2): pair p owns a contiguous range of the row-major tile list, so a row block stays
+//    resident over a sweep of column blocks;
+//  * blocked order (stacked matrix larger than the L2: c4 / c5): the tile list runs super-tile by super-tile (8 x 8 tiles)
+//    and pair p takes every npairs-th entry, so that at any moment all pairs work inside the same one or two super-tiles and
+//    their 16 row / column blocks are read from HBM once instead of once per tile.  Entries outside the matrix (edges, the
+//    lower half of diagonal super-tiles) are skipped.
+template <bool kSymW, bool kBlockedW>
 struct FwdTileWalk {
-  int ib, jb, ncb;
-  bool sym;
-  __device__ FwdTileWalk(int t0, int ncb_, bool sym_) : ncb(ncb_), sym(sym_) {
-    if (!sym) { ib = t0 / ncb; jb = t0 - ib * ncb; }
-    else {
-      ib = 0;
-      int rem = t0;
-      while (rem >= ncb - ib) { rem -= ncb - ib; ++ib; }
-      jb = ib + rem;
+  int ib, jb;
+  bool valid;
+  int t, t_end;                 // linear: index in the tile list;  blocked: index in the padded super-tile list
+  int ncb, nrbp, npairs, nsc;   // (nrbp, npairs, nsc: blocked order only)
+  static constexpr int SB = 8;
+  __device__ FwdTileWalk(int pair, int npairs_, int tiles_total, int ncb_, int nrbp_) : ncb(ncb_) {
+    if (!kBlockedW) {
+      t = (int)((long long)pair * tiles_total / npairs_);
+      t_end = (int)((long long)(pair + 1) * tiles_total / npairs_);
+      valid = t < t_end;
+      if (!kSymW) { ib = t / ncb; jb = t - ib * ncb; }
+      else {
+        ib = 0;
+        int rem = t;
+        while (rem >= ncb - ib) { rem -= ncb - ib; ++ib; }
+        jb = ib + rem;
+      }
+    } else {
+      nrbp = nrbp_; npairs = npairs_;
+      nsc = (ncb + SB - 1) / SB;
+      const int nsr = (nrbp + SB - 1) / SB;
+      t_end = (kSymW ? nsc * (nsc + 1) / 2 : nsr * nsc) * (SB * SB);
+      t = pair - npairs;
+      ib = jb = 0;
+      valid = true;
+      advance();
     }
   }
-  __device__ __forceinline__ void next() {
-    if (++jb == ncb) { ++ib; jb = sym ? ib : 0; }
+  __device__ __forceinline__ bool advance() {
+    if (!kBlockedW) {
+      if (++t >= t_end) return valid = false;
+      if (++jb == ncb) { ++ib; jb = kSymW ? ib : 0; }
+      return true;
+    }
+    for (;;) {
+      t += npairs;
+      if (t >= t_end) return valid = false;
+      const int st = t >> 6, w = t & 63;
+      int sr, sc;
+      if (!kSymW) { sr = st / nsc; sc = st - sr * nsc; }
+      else {                                         // st = sr nsc - sr (sr - 1) / 2 + (sc - sr), sc >= sr
+        const float bq = 2.0f * nsc + 1.0f;
+        sr = (int)((bq - sqrtf(bq * bq - 8.0f * st)) * 0.5f);
+        while (sr > 0 && sr * nsc - sr * (sr - 1) / 2 > st) --sr;
+        while ((sr + 1) * nsc - (sr + 1) * sr / 2 <= st) ++sr;
+        sc = sr + (st - (sr * nsc - sr * (sr - 1) / 2));
+      }
+      ib = sr * SB + (w >> 3);
+      jb = sc * SB + (w & 7);
+      if (ib < nrbp && jb < ncb && (!kSymW || jb >= ib)) return true;
+    }
   }
-  __device__ __forceinline__ int next_ib() const { return (jb + 1 == ncb) ? ib + 1 : ib; }
 };
 
 // fire-and-forget fp32 add (REDG; atomicAdd with an unused result still compiles to ATOMG for .f32)
@@ -193,10 +237,11 @@ __device__ __forceinline__ void warp_column_sums(const uint32_t (&a)[32], const 
   c0 = y[0]; c1 = y[1];
 }
 
-template <bool kResident, bool kSym>
+template <bool kResident, bool kSym, bool kBlocked>
 __global__ void __launch_bounds__(FWD2_THREADS, 1)
 fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ feat, Geometry g,
-               float* __restrict__ stats, int tiles_total, int ncb, int nk, int num_stages, int exp_flags, FwdFinalize fin) {
+               float* __restrict__ stats, int tiles_total, int ncb, int nrbp, int nk, int num_stages, int exp_flags,
+               FwdFinalize fin) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
@@ -221,8 +266,6 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int t_begin = (int)((long long)pair * tiles_total / npairs);
-  const int t_end = (int)((long long)(pair + 1) * tiles_total / npairs);
   const int nkd = g.dim / KC;            // nk counts the K chunks of the product (3 nkd for split rows, streamed only)
 
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
@@ -246,10 +289,10 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     int cur_ib = -1;
     uint32_t a_cnt = 0;
     const uint32_t a_full_ldr = mapa_cluster(a_full, 0);
-    FwdTileWalk w(t_begin, ncb, kSym);
+    FwdTileWalk<kSym, kBlocked> w(pair, npairs, tiles_total, ncb, nrbp);
     // column scales of tile t + 1 are gathered (8 per lane) while tile t's chunks are issued, and published afterwards
     float qn[8];
-    if (t_begin < t_end) {
+    if (w.valid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) qn[i] = row_q(feat, g, w.jb * FWD_TN + 32 * i + lane);
     }
@@ -263,15 +306,14 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
       if (lane == 0) mbar_arrive(qfull_bar(qs));
       ++qt;
     };
-    if (t_begin < t_end) publish_q();
-    for (int t = t_begin; t < t_end; ++t, w.next()) {
+    if (w.valid) publish_q();
+    while (w.valid) {
       const int ib = w.ib, jb = w.jb;
       const int row0 = g.row_begin + (2 * ib + (int)rank) * TM, col0 = jb * FWD_TN + (int)rank * TM;
-      if (t + 1 < t_end) {
-        FwdTileWalk wn = w;
-        wn.next();
+      w.advance();                                   // w is now the NEXT tile (if any)
+      if (w.valid) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) qn[i] = row_q(feat, g, wn.jb * FWD_TN + 32 * i + lane);
+        for (int i = 0; i < 8; ++i) qn[i] = row_q(feat, g, w.jb * FWD_TN + 32 * i + lane);
       }
       if (kResident && ib != cur_ib) {
         mbar_wait(a_empty, (a_cnt & 1) ^ 1);
@@ -294,15 +336,15 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         __syncwarp();
         ring.advance();
       }
-      if (t + 1 < t_end) publish_q();
+      if (w.valid) publish_q();
     }
   } else if (warp == 1 && rank == 0) {
     // MMA issuer (leader only)
     Ring ring(num_stages);
     int cur_ib = -1;
     uint32_t a_cnt = 0, iter = 0;
-    FwdTileWalk w(t_begin, ncb, kSym);
-    for (int t = t_begin; t < t_end; ++t, ++iter, w.next()) {
+    FwdTileWalk<kSym, kBlocked> w(pair, npairs, tiles_total, ncb, nrbp);
+    for (; w.valid; ++iter) {
       const int ib = w.ib;
       const uint32_t buf = iter & 1;
       mbar_wait_cluster(tempty_bar(buf), ((iter >> 1) & 1) ^ 1);
@@ -328,7 +370,8 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
         __syncwarp();
         ring.advance();
       }
-      const bool last_of_block = (t + 1 == t_end) || (w.next_ib() != ib);
+      w.advance();
+      const bool last_of_block = !w.valid || w.ib != ib;
       if (elect_one()) {
         umma_commit_2sm(tfull_bar(buf), (uint16_t)3);
         if (kResident && last_of_block) umma_commit_2sm(a_empty, (uint16_t)3);
@@ -350,13 +393,13 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     const float k_diag_term = fast_exp2(-g.shift);
     float nshift = -g.shift;                       // -inf for a zero-padding row: all its exponentials are 0
     const uint32_t tempty_ldr = mapa_cluster(tempty_bar(gsel), 0);
-    // running tile coordinates (no divisions in the loop): row-block pair ib, column block jb, and the segment / offset
-    // of this warp's half of the column block
-    FwdTileWalk w(t_begin, ncb, kSym);
+    // tile coordinates: row-block pair ib, column block jb, and the segment / offset of this warp's half of the column block
+    // (kept incrementally along a row sweep of the linear order: no divisions there)
+    FwdTileWalk<kSym, kBlocked> w(pair, npairs, tiles_total, ncb, nrbp);
     int ib = w.ib, jb = w.jb;
     int jseg = (jb * FWD_TN + half * TM) / g.bseg, joff = (jb * FWD_TN + half * TM) - jseg * g.bseg;
     uint32_t iter = 0;
-    for (int t = t_begin; t < t_end; ++t, ++iter) {
+    for (; w.valid; ++iter) {
       const bool mine = (iter & 1) == (uint32_t)gsel;
       if (mine && ib != cur_ib) {
         if (cur_ib >= 0) red_add_f32(&stats[2 * (int64_t)gi], (rs[0] + rs[1]) + (rs[2] + rs[3]));
@@ -376,9 +419,11 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
       const int col_row0 = jb * FWD_TN + half * TM;                  // stacked row of the warp's first column
       const uint32_t qs = iter % FWD_QSTAGES;
       const float* const qv = q_ring + qs * FWD_TN + half * TM;      // this half's column scales
-      w.next();
-      if (w.ib != ib) { ib = w.ib; jb = w.jb; jseg = (jb * FWD_TN + half * TM) / g.bseg; joff = (jb * FWD_TN + half * TM) - jseg * g.bseg; }
-      else { jb = w.jb; joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
+      w.advance();                                                   // (ib, jb, jseg, joff) of the next tile; locals above are this tile's
+      if (w.valid) {
+        if (w.ib != ib || w.jb != jb + 1) { ib = w.ib; jb = w.jb; jseg = (jb * FWD_TN + half * TM) / g.bseg; joff = (jb * FWD_TN + half * TM) - jseg * g.bseg; }
+        else { jb = w.jb; joff += FWD_TN; while (joff >= g.bseg) { joff -= g.bseg; ++jseg; } }
+      }
       if (!mine) continue;
       mbar_wait(qfull_bar(qs), (iter / FWD_QSTAGES) & 1);
       mbar_wait(tfull_bar(gsel), (iter >> 1) & 1);
@@ -1448,7 +1493,7 @@ static bool fwd_sym_enabled() {
 
 constexpr int kFwdQvBytes = FWD_QSTAGES * FWD_TN * 4;   // ring of per-tile column scales
 
-template <bool kResident, bool kSym>
+template <bool kResident, bool kSym, bool kBlocked>
 static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, float* stats, cudaStream_t st,
                             const FwdFinalize& fin) {
   const int nk = s_chunks(g), ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
@@ -1458,7 +1503,7 @@ static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geo
   const size_t fixed = 1024 + kBarBytes + kFwdQvBytes + a_bytes;
   const int stages = (int)std::min<size_t>(MAX_SLOTS, (kMaxSmem - fixed) / stage_bytes);
   const size_t smem = fixed + (size_t)stages * stage_bytes;
-  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident, kSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident, kSym, kBlocked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * std::min(tiles, sm_count() / 2));
   cfg.blockDim = dim3(FWD2_THREADS);
@@ -1470,8 +1515,8 @@ static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geo
   cfg.attrs = &attr; cfg.numAttrs = 1;
   static const int exp_flags = getenv("CROSSCLR_FWD_EXP") ? atoi(getenv("CROSSCLR_FWD_EXP")) : 0;   // perf experiments only
   TimedLaunch timed(CROSSCLR_K_FWD, st);
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym>, tmap, (const uint8_t*)feat, g, stats, tiles, ncb, nk,
-                                   stages, exp_flags, fin));
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym, kBlocked>, tmap, (const uint8_t*)feat, g, stats, tiles, ncb,
+                                   nrbp, nk, stages, exp_flags, fin));
   return check_launch("fwd_tc2_kernel");
 }
 
@@ -1483,11 +1528,21 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   CUtensorMap tmap;
   int rc = CC_FEAT_TMAP(&tmap, feat, g, TM);
   if (rc) return rc;
-  const bool resident = s_chunks(g) <= MAX_RES_CHUNKS && !g.split;    // split rows: A's K chunks are not B's, stream both
+  // Super-tile order: every pair inside the same 8 x 8 tiles at a time, so that row / column blocks come from HBM once per
+  // super-tile instead of once per tile -- for problems whose stacked matrix is well beyond the 126 MB L2 AND whose row block
+  // cannot stay resident anyway (D > 512: c5).  Measured on B200: c5 79 -> 63 ms on one GPU, 35 -> 28 ms per rank at N = 4;
+  // with a resident row block (c4, D = 512) the linear order is as good or better (8.5 vs 9.0 ms).
+  // CROSSCLR_FWD_BLOCKED = 0 / 1 forces the order.
+  static const int force_blocked = getenv("CROSSCLR_FWD_BLOCKED") ? atoi(getenv("CROSSCLR_FWD_BLOCKED")) : -1;
+  const bool can_reside = s_chunks(g) <= MAX_RES_CHUNKS && !g.split;    // split rows: A's K chunks are not B's, stream both
+  const bool blocked = force_blocked >= 0 ? force_blocked != 0
+                                          : (!can_reside && (size_t)g.rows * g.pitch * 2 > ((size_t)100 << 20));
+  const bool resident = can_reside && !blocked;
   // single rank: all rows are owned, the Gram matrix is square and symmetric -> upper triangle of pair tiles only
   const bool sym = g.row_count == g.rows && g.row_begin == 0 && fwd_sym_enabled();
-  if (sym) return resident ? launch_fwd_tc2_t<true, true>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, true>(tmap, feat, g, stats, st, fin);
-  return resident ? launch_fwd_tc2_t<true, false>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, false>(tmap, feat, g, stats, st, fin);
+  if (blocked) return sym ? launch_fwd_tc2_t<false, true, true>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, false, true>(tmap, feat, g, stats, st, fin);
+  if (sym) return resident ? launch_fwd_tc2_t<true, true, false>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, true, false>(tmap, feat, g, stats, st, fin);
+  return resident ? launch_fwd_tc2_t<true, false, false>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, false, false>(tmap, feat, g, stats, st, fin);
 }
 
 // How many clusters of bwd_pair_kernel (1 S-CTA + csize-1 G-CTAs) can be resident at once.  Queried once per
