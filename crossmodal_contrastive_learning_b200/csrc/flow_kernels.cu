@@ -52,6 +52,9 @@ struct FlowParams {
   int ds, dw;            // consumers split D into ds slabs of dw columns (D <= 512: 1 x D; else 2 x D/2): physical ring =
                          // logical ring * ds + slab, every tile is consumed once per slab
   int a_res;             // producer keeps its 128 rows of A resident (nk <= 8); else A streams beside B
+  int jmajor;            // row-band schedule: a wave's tile list runs column block by column block and producer s takes every
+                         // n_s-th tile (all producers and consumers inside the same few column blocks at a time: one HBM read
+                         // per block and wave), instead of a contiguous range of one row block's sweep
   int nk;                // K chunks of the similarity product: dim / 64, or 3 dim / 64 for split rows
   int s_stages;          // producer ring depth
   uint32_t* ring;        // [nrb * parts (+ nb late)][cnt] descriptors, zero = not yet published
@@ -121,12 +124,13 @@ struct FlowTile {
 // main rings (d < d0), then its late tiles (d >= d0) -- fewer than FLOW_NSLOT, so the slots they hold until the late
 // consumers start are never needed again by this producer.
 struct FlowProdWalk {
-  int n_g, n_s, nb, parts, cnt, sym, s, nrings, nwaves, d0;
-  int wave, k, k0, k_end, c0, pass;
+  int n_g, n_s, nb, parts, cnt, sym, s, nrings, nwaves, d0, jmajor;
+  int wave, k, k0, k_end, c0, pass, kstep, nr_wave;
   int I, d;                                   // symmetric schedule: row block, cyclic distance
   __device__ FlowProdWalk(const FlowParams& P, int s_)
       : n_g(P.n_g), n_s(P.n_s), nb(P.nb), parts(P.parts), cnt(P.cnt), sym(P.sym), s(s_), nrings(P.nrb * P.parts),
-        wave(-1), k(0), k0(0), k_end(0), c0(0), pass(1), I(0), d(0) {
+        wave(-1), k(0), k0(0), k_end(0), c0(0), pass(1), kstep(1), nr_wave(1), I(0), d(0) {
+    jmajor = (!P.sym && P.jmajor) ? 1 : 0;
     n_g = P.n_g / P.ds;                        // logical rings per wave (n_g is a multiple of ds)
     nwaves = (nrings + n_g - 1) / n_g;
     d0 = P.d0;
@@ -149,19 +153,23 @@ struct FlowProdWalk {
         c0 = wave * n_g;
         const int nr = min(n_g, nrings - c0);
         const long long T = sym ? (long long)nb * (nb + 1) / 2 : (long long)nr * cnt;
-        k0 = k = (int)((long long)s * T / n_s);
-        k_end = (int)((long long)(s + 1) * T / n_s);
+        if (jmajor) { k0 = k = s; k_end = (int)T; kstep = n_s; nr_wave = nr; }
+        else {
+          k0 = k = (int)((long long)s * T / n_s);
+          k_end = (int)((long long)(s + 1) * T / n_s);
+        }
         pass = 0;
         if (sym) seek(k);
         continue;
       }
       if (!sym) {
-        const int c = c0 + k / cnt;
+        const int jdx = jmajor ? k / nr_wave : k % cnt;        // which of the ring's cnt column blocks
+        const int c = c0 + (jmajor ? k - jdx * nr_wave : k / cnt);
         t.I = c / parts;
-        t.J = (c - t.I * parts) + parts * (k % cnt);
+        t.J = (c - t.I * parts) + parts * jdx;
         t.ring_d = c;
         t.ring_t = -1;
-        ++k;
+        k += kstep;
         return true;
       }
       const int Ic = I, dc = d;
@@ -913,7 +921,14 @@ int launch_bwd_flow(const Geometry& g, const void* feat, const float* coef, cons
   const size_t n_rings = (size_t)f.nrb * f.parts * f.ds + (late_on ? f.nb : 0);
   P.nk = s_chunks(g);
   P.ds = f.ds; P.dw = g.dim / f.ds;
-  P.a_res = (P.nk <= MAX_RES_CHUNKS && !g.split) ? 1 : 0;
+  // Column-block-major producer order for row bands whose stacked matrix does not sit comfortably in the 126 MB L2: with
+  // contiguous sweeps every producer and consumer walks the column blocks at its own pace and each block comes from HBM
+  // once per tile (c5: ~1 TB per launch); interleaved, all of them are inside the same few column blocks.  Measured on B200
+  // (scripts/gpu_flow_jmajor.sh): c3 3.42 -> 3.17 ms, c4 34.6 -> 31.8 ms, c5 298 -> 236 ms; B = 16384, D = 512 (38 MB) unchanged.
+  // CROSSCLR_FLOW_JMAJOR = 0 / 1 forces the order.
+  static const int force_jmajor = env_int("CROSSCLR_FLOW_JMAJOR", -1);
+  P.jmajor = f.sym ? 0 : (force_jmajor >= 0 ? (force_jmajor != 0) : ((size_t)g.rows * g.pitch * 2 > ((size_t)48 << 20) ? 1 : 0));
+  P.a_res = (P.nk <= MAX_RES_CHUNKS && !g.split && !P.jmajor) ? 1 : 0;
   P.s_stages = P.a_res ? std::min((int)((kMaxSmem - FLOW_HDR - (size_t)P.nk * CHUNK_BYTES) / CHUNK_BYTES), MAX_SLOTS)
                        : std::min((int)((kMaxSmem - FLOW_HDR) / (2 * CHUNK_BYTES)), MAX_SLOTS);
   P.ring = (uint32_t*)scratch;

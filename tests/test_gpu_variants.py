@@ -3,7 +3,7 @@ CROSSCLR_*_VARIANT environment switches (read once per process, hence the child 
 kernels a given shape would not select stay covered: full-Gram (non-symmetric) paired forward, the forward's super-tile order
 (picked by itself only beyond the L2's size), single-CTA slab backward,
 1 S-CTA + G-CTA(s) cluster backward (also at a size the dataflow kernel would take), dataflow backward (variant 4) below
-its default size threshold."""
+its default size threshold, and its row-band schedule (SYM_MAX = 0) in both producer orders."""
 import os
 import subprocess
 import sys
@@ -22,6 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
     ({"CROSSCLR_BWD_VARIANT": "2"}, 384, 1024), ({"CROSSCLR_BWD_VARIANT": "2"}, 2048, 512),
     ({"CROSSCLR_BWD_VARIANT": "4"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "4"}, 640, 256),
     ({"CROSSCLR_BWD_VARIANT": "4"}, 384, 384), ({"CROSSCLR_BWD_VARIANT": "4"}, 256, 128),
+    ({"CROSSCLR_FLOW_JMAJOR": "1", "CROSSCLR_FLOW_SYM_MAX": "0"}, 2048, 512), ({"CROSSCLR_FLOW_JMAJOR": "1", "CROSSCLR_FLOW_SYM_MAX": "0"}, 1536, 1024),
+    ({"CROSSCLR_FLOW_JMAJOR": "0", "CROSSCLR_FLOW_SYM_MAX": "0"}, 2048, 512),
 ], ids=lambda x: "-".join(f"{k[9:]}{v}" for k, v in x.items()) if isinstance(x, dict) else str(x))  # noqa: E501
 def test_forced_variant_matches_oracle(env, B, D):
     e = dict(os.environ, **env)
