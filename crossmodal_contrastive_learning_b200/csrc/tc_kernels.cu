@@ -102,15 +102,20 @@ constexpr int FWD2_THREADS = 640;       // warps 0-3: producer / MMA / TMEM allo
 //    and pair p takes every npairs-th entry, so that at any moment all pairs work inside the same one or two super-tiles and
 //    their 16 row / column blocks are read from HBM once instead of once per tile.  Entries outside the matrix (edges, the
 //    lower half of diagonal super-tiles) are skipped.
-template <bool kSymW, bool kBlockedW>
+//  * row-interleaved order (matrix larger than the L2, row block resident: c4): pair p sweeps whole rows p, p + npairs, ...
+//    (every other round in reverse pair order, which evens out the triangle's row lengths), so that the row block stays
+//    resident AND all pairs move through the column blocks roughly in step.
+enum { FWD_ORDER_LINEAR = 0, FWD_ORDER_BLOCKED = 1, FWD_ORDER_ROWS = 2 };
+
+template <bool kSymW, int kOrderW>
 struct FwdTileWalk {
   int ib, jb;
   bool valid;
-  int t, t_end;                 // linear: index in the tile list;  blocked: index in the padded super-tile list
-  int ncb, nrbp, npairs, nsc;   // (nrbp, npairs, nsc: blocked order only)
+  int t, t_end;                 // linear: index in the tile list;  blocked: index in the padded super-tile list;  rows: round
+  int ncb, nrbp, npairs, nsc;   // (nrbp, npairs: blocked / rows orders; nsc: blocked; rows: nsc holds the pair index)
   static constexpr int SB = 8;
   __device__ FwdTileWalk(int pair, int npairs_, int tiles_total, int ncb_, int nrbp_) : ncb(ncb_) {
-    if (!kBlockedW) {
+    if (kOrderW == FWD_ORDER_LINEAR) {
       t = (int)((long long)pair * tiles_total / npairs_);
       t_end = (int)((long long)(pair + 1) * tiles_total / npairs_);
       valid = t < t_end;
@@ -121,6 +126,12 @@ struct FwdTileWalk {
         while (rem >= ncb - ib) { rem -= ncb - ib; ++ib; }
         jb = ib + rem;
       }
+    } else if (kOrderW == FWD_ORDER_ROWS) {
+      nrbp = nrbp_; npairs = npairs_; nsc = pair;
+      t = 0;
+      ib = pair;
+      jb = kSymW ? ib : 0;
+      valid = ib < nrbp;
     } else {
       nrbp = nrbp_; npairs = npairs_;
       nsc = (ncb + SB - 1) / SB;
@@ -133,10 +144,17 @@ struct FwdTileWalk {
     }
   }
   __device__ __forceinline__ bool advance() {
-    if (!kBlockedW) {
+    if (kOrderW == FWD_ORDER_LINEAR) {
       if (++t >= t_end) return valid = false;
       if (++jb == ncb) { ++ib; jb = kSymW ? ib : 0; }
       return true;
+    }
+    if (kOrderW == FWD_ORDER_ROWS) {
+      if (++jb < ncb) return true;
+      ++t;                                           // next round; odd rounds run the pairs in reverse
+      ib = t * npairs + ((t & 1) ? npairs - 1 - nsc : nsc);
+      jb = kSymW ? ib : 0;
+      return valid = ib < nrbp;
     }
     for (;;) {
       t += npairs;
@@ -237,7 +255,7 @@ __device__ __forceinline__ void warp_column_sums(const uint32_t (&a)[32], const 
   c0 = y[0]; c1 = y[1];
 }
 
-template <bool kResident, bool kSym, bool kBlocked>
+template <bool kResident, bool kSym, int kOrder>
 __global__ void __launch_bounds__(FWD2_THREADS, 1)
 fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ feat, Geometry g,
                float* __restrict__ stats, int tiles_total, int ncb, int nrbp, int nk, int num_stages, int exp_flags,
@@ -289,7 +307,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     int cur_ib = -1;
     uint32_t a_cnt = 0;
     const uint32_t a_full_ldr = mapa_cluster(a_full, 0);
-    FwdTileWalk<kSym, kBlocked> w(pair, npairs, tiles_total, ncb, nrbp);
+    FwdTileWalk<kSym, kOrder> w(pair, npairs, tiles_total, ncb, nrbp);
     // column scales of tile t + 1 are gathered (8 per lane) while tile t's chunks are issued, and published afterwards
     float qn[8];
     if (w.valid) {
@@ -343,7 +361,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     Ring ring(num_stages);
     int cur_ib = -1;
     uint32_t a_cnt = 0, iter = 0;
-    FwdTileWalk<kSym, kBlocked> w(pair, npairs, tiles_total, ncb, nrbp);
+    FwdTileWalk<kSym, kOrder> w(pair, npairs, tiles_total, ncb, nrbp);
     for (; w.valid; ++iter) {
       const int ib = w.ib;
       const uint32_t buf = iter & 1;
@@ -395,7 +413,7 @@ fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restri
     const uint32_t tempty_ldr = mapa_cluster(tempty_bar(gsel), 0);
     // tile coordinates: row-block pair ib, column block jb, and the segment / offset of this warp's half of the column block
     // (kept incrementally along a row sweep of the linear order: no divisions there)
-    FwdTileWalk<kSym, kBlocked> w(pair, npairs, tiles_total, ncb, nrbp);
+    FwdTileWalk<kSym, kOrder> w(pair, npairs, tiles_total, ncb, nrbp);
     int ib = w.ib, jb = w.jb;
     int jseg = (jb * FWD_TN + half * TM) / g.bseg, joff = (jb * FWD_TN + half * TM) - jseg * g.bseg;
     uint32_t iter = 0;
@@ -1493,7 +1511,7 @@ static bool fwd_sym_enabled() {
 
 constexpr int kFwdQvBytes = FWD_QSTAGES * FWD_TN * 4;   // ring of per-tile column scales
 
-template <bool kResident, bool kSym, bool kBlocked>
+template <bool kResident, bool kSym, int kOrder>
 static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geometry& g, float* stats, cudaStream_t st,
                             const FwdFinalize& fin) {
   const int nk = s_chunks(g), ncb = g.rows / FWD_TN, nrbp = g.row_count / (2 * TM);
@@ -1503,7 +1521,7 @@ static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geo
   const size_t fixed = 1024 + kBarBytes + kFwdQvBytes + a_bytes;
   const int stages = (int)std::min<size_t>(MAX_SLOTS, (kMaxSmem - fixed) / stage_bytes);
   const size_t smem = fixed + (size_t)stages * stage_bytes;
-  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident, kSym, kBlocked>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CC_CHECK_CUDA(cudaFuncSetAttribute(fwd_tc2_kernel<kResident, kSym, kOrder>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * std::min(tiles, sm_count() / 2));
   cfg.blockDim = dim3(FWD2_THREADS);
@@ -1515,7 +1533,7 @@ static int launch_fwd_tc2_t(const CUtensorMap& tmap, const void* feat, const Geo
   cfg.attrs = &attr; cfg.numAttrs = 1;
   static const int exp_flags = getenv("CROSSCLR_FWD_EXP") ? atoi(getenv("CROSSCLR_FWD_EXP")) : 0;   // perf experiments only
   TimedLaunch timed(CROSSCLR_K_FWD, st);
-  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym, kBlocked>, tmap, (const uint8_t*)feat, g, stats, tiles, ncb,
+  CC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fwd_tc2_kernel<kResident, kSym, kOrder>, tmap, (const uint8_t*)feat, g, stats, tiles, ncb,
                                    nrbp, nk, stages, exp_flags, fin));
   return check_launch("fwd_tc2_kernel");
 }
@@ -1532,17 +1550,29 @@ int launch_fwd_tc(const Geometry& g, const void* feat, float* stats, cudaStream_
   // super-tile instead of once per tile -- for problems whose stacked matrix is well beyond the 126 MB L2 AND whose row block
   // cannot stay resident anyway (D > 512: c5).  Measured on B200: c5 79 -> 63 ms on one GPU, 35 -> 28 ms per rank at N = 4;
   // with a resident row block (c4, D = 512) the linear order is as good or better (8.5 vs 9.0 ms).
-  // CROSSCLR_FWD_BLOCKED = 0 / 1 forces the order.
-  static const int force_blocked = getenv("CROSSCLR_FWD_BLOCKED") ? atoi(getenv("CROSSCLR_FWD_BLOCKED")) : -1;
+  // Row-interleaved order: large problems with a resident row block (D <= 512: c4) -- pairs sweep whole rows in step, the row
+  // block stays in shared memory and the column blocks are shared through the L2.  Measured (scripts/gpu_fwd_blocked.sh):
+  // c4 8.2 -> 6.7 ms on one GPU, 3.0 -> 2.7 ms per rank at N = 4; B = 32768, D = 512 (75 MB) 1.72 -> 1.65 ms.
+  // CROSSCLR_FWD_BLOCKED = 0 / 1 / 2 forces linear / super-tile / row-interleaved order.
+  static const int force_order = getenv("CROSSCLR_FWD_BLOCKED") ? atoi(getenv("CROSSCLR_FWD_BLOCKED")) : -1;
   const bool can_reside = s_chunks(g) <= MAX_RES_CHUNKS && !g.split;    // split rows: A's K chunks are not B's, stream both
-  const bool blocked = force_blocked >= 0 ? force_blocked != 0
-                                          : (!can_reside && (size_t)g.rows * g.pitch * 2 > ((size_t)100 << 20));
-  const bool resident = can_reside && !blocked;
+  const size_t bytes = (size_t)g.rows * g.pitch * 2;
+  int order = force_order >= 0 ? force_order
+                               : (can_reside ? (bytes > ((size_t)64 << 20) ? FWD_ORDER_ROWS : FWD_ORDER_LINEAR)
+                                             : (bytes > ((size_t)100 << 20) ? FWD_ORDER_BLOCKED : FWD_ORDER_LINEAR));
+  if (order == FWD_ORDER_ROWS && !can_reside) order = FWD_ORDER_BLOCKED;
   // single rank: all rows are owned, the Gram matrix is square and symmetric -> upper triangle of pair tiles only
   const bool sym = g.row_count == g.rows && g.row_begin == 0 && fwd_sym_enabled();
-  if (blocked) return sym ? launch_fwd_tc2_t<false, true, true>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, false, true>(tmap, feat, g, stats, st, fin);
-  if (sym) return resident ? launch_fwd_tc2_t<true, true, false>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, true, false>(tmap, feat, g, stats, st, fin);
-  return resident ? launch_fwd_tc2_t<true, false, false>(tmap, feat, g, stats, st, fin) : launch_fwd_tc2_t<false, false, false>(tmap, feat, g, stats, st, fin);
+  if (order == FWD_ORDER_BLOCKED)
+    return sym ? launch_fwd_tc2_t<false, true, FWD_ORDER_BLOCKED>(tmap, feat, g, stats, st, fin)
+               : launch_fwd_tc2_t<false, false, FWD_ORDER_BLOCKED>(tmap, feat, g, stats, st, fin);
+  if (order == FWD_ORDER_ROWS)
+    return sym ? launch_fwd_tc2_t<true, true, FWD_ORDER_ROWS>(tmap, feat, g, stats, st, fin)
+               : launch_fwd_tc2_t<true, false, FWD_ORDER_ROWS>(tmap, feat, g, stats, st, fin);
+  if (sym) return can_reside ? launch_fwd_tc2_t<true, true, FWD_ORDER_LINEAR>(tmap, feat, g, stats, st, fin)
+                             : launch_fwd_tc2_t<false, true, FWD_ORDER_LINEAR>(tmap, feat, g, stats, st, fin);
+  return can_reside ? launch_fwd_tc2_t<true, false, FWD_ORDER_LINEAR>(tmap, feat, g, stats, st, fin)
+                    : launch_fwd_tc2_t<false, false, FWD_ORDER_LINEAR>(tmap, feat, g, stats, st, fin);
 }
 
 // How many clusters of bwd_pair_kernel (1 S-CTA + csize-1 G-CTAs) can be resident at once.  Queried once per

@@ -1,7 +1,7 @@
 """Every tensor-core kernel variant against the oracle.  The library picks a forward / backward kernel by shape; the
 CROSSCLR_*_VARIANT environment switches (read once per process, hence the child processes) force the others so that the
-kernels a given shape would not select stay covered: full-Gram (non-symmetric) paired forward, the forward's super-tile order
-(picked by itself only beyond the L2's size), single-CTA slab backward,
+kernels a given shape would not select stay covered: full-Gram (non-symmetric) paired forward, the forward's super-tile and
+row-interleaved orders (picked by themselves only beyond the L2's size), single-CTA slab backward,
 1 S-CTA + G-CTA(s) cluster backward (also at a size the dataflow kernel would take), dataflow backward (variant 4) below
 its default size threshold, and its row-band schedule (SYM_MAX = 0) in both producer orders."""
 import os
@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
     ({"CROSSCLR_FWD_SYM": "0"}, 512, 512), ({"CROSSCLR_FWD_SYM": "0"}, 384, 1024),
     ({"CROSSCLR_FWD_BLOCKED": "1"}, 1536, 256), ({"CROSSCLR_FWD_BLOCKED": "1"}, 2432, 1024), ({"CROSSCLR_FWD_BLOCKED": "1"}, 333, 77),
     ({"CROSSCLR_FWD_BLOCKED": "1", "CROSSCLR_FWD_SYM": "0"}, 1280, 512),
+    ({"CROSSCLR_FWD_BLOCKED": "2"}, 1536, 256), ({"CROSSCLR_FWD_BLOCKED": "2"}, 333, 77), ({"CROSSCLR_FWD_BLOCKED": "2", "CROSSCLR_FWD_SYM": "0"}, 1280, 512),
     ({"CROSSCLR_BWD_VARIANT": "1"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "2"}, 512, 512),
     ({"CROSSCLR_BWD_VARIANT": "2"}, 384, 1024), ({"CROSSCLR_BWD_VARIANT": "2"}, 2048, 512),
     ({"CROSSCLR_BWD_VARIANT": "4"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "4"}, 640, 256),
