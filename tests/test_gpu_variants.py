@@ -31,3 +31,18 @@ def test_forced_variant_matches_oracle(env, B, D):
     p = subprocess.run([sys.executable, os.path.join(HERE, "_variant_check.py"), str(B), str(D)], env=e,
                        capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and p.stdout.strip().startswith("OK"), p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("env,B,D,world", [
+    ({"CROSSCLR_FWD_BLOCKED": "1", "CROSSCLR_FLOW_JMAJOR": "1"}, 2048, 512, 4),
+    ({"CROSSCLR_FWD_BLOCKED": "2", "CROSSCLR_FLOW_JMAJOR": "1"}, 3072, 256, 3),
+    ({"CROSSCLR_FWD_BLOCKED": "1", "CROSSCLR_FLOW_JMAJOR": "1"}, 2400, 1000, 2),
+    ({"CROSSCLR_FWD_BLOCKED": "2", "CROSSCLR_FLOW_JMAJOR": "0"}, 4096, 512, 8),
+], ids=lambda x: "-".join(f"{k[9:]}{v}" for k, v in x.items()) if isinstance(x, dict) else str(x))
+def test_forced_tile_orders_on_row_bands(env, B, D, world):
+    """The large-problem tile orders (forward super-tiles / row-interleaved, backward column-block-major producers) forced at
+    test sizes on the row bands of a multi-rank job (every rank's launches on one GPU), ragged shapes included."""
+    e = dict(os.environ, **env)
+    p = subprocess.run([sys.executable, os.path.join(HERE, "_variant_check_ranks.py"), str(B), str(D), str(world)], env=e,
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().startswith("OK"), p.stdout[-2000:] + p.stderr[-2000:]
