@@ -16,13 +16,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.parametrize("env,B,D", [
     ({"CROSSCLR_FWD_SYM": "0"}, 512, 512), ({"CROSSCLR_FWD_SYM": "0"}, 384, 1024),
-    ({"CROSSCLR_FWD_BLOCKED": "1"}, 1536, 256), ({"CROSSCLR_FWD_BLOCKED": "1"}, 2432, 1024), ({"CROSSCLR_FWD_BLOCKED": "1"}, 333, 77),
+    ({"CROSSCLR_FWD_BLOCKED": "1"}, 2432, 1024), ({"CROSSCLR_FWD_BLOCKED": "1"}, 333, 77),
     ({"CROSSCLR_FWD_BLOCKED": "1", "CROSSCLR_FWD_SYM": "0"}, 1280, 512),
-    ({"CROSSCLR_FWD_BLOCKED": "2"}, 1536, 256), ({"CROSSCLR_FWD_BLOCKED": "2"}, 333, 77), ({"CROSSCLR_FWD_BLOCKED": "2", "CROSSCLR_FWD_SYM": "0"}, 1280, 512),
+    ({"CROSSCLR_FWD_BLOCKED": "2"}, 1536, 256), ({"CROSSCLR_FWD_BLOCKED": "2", "CROSSCLR_FWD_SYM": "0"}, 1280, 512),
     ({"CROSSCLR_BWD_VARIANT": "1"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "2"}, 512, 512),
     ({"CROSSCLR_BWD_VARIANT": "2"}, 384, 1024), ({"CROSSCLR_BWD_VARIANT": "2"}, 2048, 512),
-    ({"CROSSCLR_BWD_VARIANT": "4"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "4"}, 640, 256),
-    ({"CROSSCLR_BWD_VARIANT": "4"}, 384, 384), ({"CROSSCLR_BWD_VARIANT": "4"}, 256, 128),
+    ({"CROSSCLR_BWD_VARIANT": "4"}, 512, 512), ({"CROSSCLR_BWD_VARIANT": "4"}, 384, 384),
     ({"CROSSCLR_FLOW_JMAJOR": "1", "CROSSCLR_FLOW_SYM_MAX": "0"}, 2048, 512), ({"CROSSCLR_FLOW_JMAJOR": "1", "CROSSCLR_FLOW_SYM_MAX": "0"}, 1536, 1024),
     ({"CROSSCLR_FLOW_JMAJOR": "0", "CROSSCLR_FLOW_SYM_MAX": "0"}, 2048, 512),
 ], ids=lambda x: "-".join(f"{k[9:]}{v}" for k, v in x.items()) if isinstance(x, dict) else str(x))  # noqa: E501
