@@ -416,6 +416,111 @@ def run_shape_variant(M, NAT, torch, dev, flush, B, D, dtype, what, steps=20):
                        "inputs": "the timed values as fp32 tensors through the eager module (fp32 inputs take the fp32 rule of `auto`)"}}
 
 
+def run_next_rows(M, NAT, torch, dev, flush, reps=10):
+    """SURVEY.md section 8 rows f1 / f4 beside the headline, on ONE GPU: `MaxMargin_coot` (trainer/loss.py:17-41) forward +
+    backward and the retrieval ranks over the same score tiles, bf16 embeddings, device events, L2 flushed before each call.
+    Algorithmic FLOPs: forward one B x B x D product (2 B^2 D), backward two (4 B^2 D).  Parity against the CPU oracle at
+    B = 4096 (checker use of oracle/ only) and the reference's own CPU forward + autograd backward timed beside it."""
+    import types
+    import numpy as np
+    from oracle.maxmargin_oracle import maxmargin_loss_and_grads
+    from oracle.retrieval_oracle import retrieval_ranks as oracle_ranks
+    burst, _, _ = measured_peaks()
+    lib = M.load_native()
+    out = {}
+    for B, D in ((4096, 512), (16384, 512)):
+        g = torch.Generator().manual_seed(B)
+        im = (torch.randn(B, D, generator=g) / D ** 0.5).to(torch.bfloat16)
+        s = (0.15 * im.float() + torch.randn(B, D, generator=g) / D ** 0.5).to(torch.bfloat16)
+        a = im.to(dev).requires_grad_()
+        b = s.to(dev).requires_grad_()
+        crit = M.MaxMargin_coot(True, 0.1)
+        go = torch.ones((), dtype=torch.bfloat16, device=dev)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for e0, e1 in evs:
+                flush.zero_()
+                e0.record()
+                fn()
+                e1.record()
+            torch.cuda.synchronize()
+            ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+            return ts[len(ts) // 2]
+
+        state = {}
+
+        def fwd():
+            state["loss"] = crit(a, b)
+
+        def bwd():
+            a.grad = b.grad = None
+            state["loss"].backward(go, retain_graph=True)
+
+        def step():
+            a.grad = b.grad = None
+            crit(a, b).backward()
+
+        t_fwd = timed(fwd)
+        t_bwd = timed(bwd)
+        t_step = timed(step)
+        t_rank = timed(lambda: M.retrieval_ranks(a.detach(), b.detach()))
+        code = NAT.BF16
+        rec = {"B": B, "D": D, "in_dtype": "bfloat16", "margin": 0.1,
+               "kernel": lib.crossclr_maxmargin_kernel_name(a.data_ptr(), b.data_ptr(), code, a.stride(0), b.stride(0), B, D).decode(),
+               "fwd_ms": t_fwd, "bwd_ms": t_bwd, "step_ms": t_step, "pairs_per_s": B / (t_step * 1e-3),
+               "fwd_tflops_alg": 2.0 * B * B * D / (t_fwd * 1e-3) / 1e12, "bwd_tflops_alg": 4.0 * B * B * D / (t_bwd * 1e-3) / 1e12,
+               "step_frac_of_peak": 6.0 * B * B * D / (t_step * 1e-3) / 1e12 / burst,
+               "retrieval_ranks_ms": t_rank, "retrieval_tflops_alg": 2.0 * B * B * D / (t_rank * 1e-3) / 1e12,
+               "timing": f"median of {reps} eager module calls (launches + autograd), device events, L2 flushed"}
+        if B == 4096:
+            rl, rda, rdb = maxmargin_loss_and_grads(im.float().numpy(), s.float().numpy(), 0.1)
+            af = im.float().to(dev).bfloat16()
+            ws_n = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
+            ws = torch.empty(ws_n, dtype=torch.uint8, device=dev)
+            loss64 = torch.empty((), dtype=torch.float64, device=dev)
+            da = torch.empty(B, D, dtype=torch.float32, device=dev)
+            db = torch.empty(B, D, dtype=torch.float32, device=dev)
+            bd = b.detach()
+            st = torch.cuda.current_stream().cuda_stream
+            NAT.check(lib.crossclr_maxmargin_fwd(af.data_ptr(), bd.data_ptr(), code, D, D, B, D, 0.1, ws.data_ptr(), ws_n,
+                                                 loss64.data_ptr(), st), "crossclr_maxmargin_fwd")
+            NAT.check(lib.crossclr_maxmargin_bwd(af.data_ptr(), bd.data_ptr(), code, D, D, B, D, 0.1, ws.data_ptr(), ws_n, None,
+                                                 da.data_ptr(), D, db.data_ptr(), D, NAT.F32, st), "crossclr_maxmargin_bwd")
+            torch.cuda.synchronize()
+            ra, rb, _ = oracle_ranks(im.float().numpy(), s.float().numpy())
+            ga, gb = M.retrieval_ranks(a.detach(), bd)
+            rec["parity"] = {"loss_rel": abs(loss64.item() - rl) / abs(rl),
+                             "dim_rel": float(np.linalg.norm(da.double().cpu().numpy() - rda) / np.linalg.norm(rda)),
+                             "ds_rel": float(np.linalg.norm(db.double().cpu().numpy() - rdb) / np.linalg.norm(rdb)),
+                             "rank_mismatches": int((ga.cpu().numpy() != ra).sum() + (gb.cpu().numpy() != rb).sum()),
+                             "recall_at_10": float((ga < 10).double().mean()), "oracle_recall_at_10": float((ra < 10).mean()),
+                             "against": "oracle/maxmargin_oracle.py, oracle/retrieval_oracle.py (float64), fp32 gradients out of the C ABI"}
+            ref_path = os.path.join(ROOT, "baseline", "_ref", "trainer", "loss.py")
+            if os.path.exists(ref_path):
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("_crossclr_reference_loss_mm", ref_path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                me = types.SimpleNamespace(margin=0.1, sim=mod.cosine_sim, use_cuda=False)   # the ctor is a NameError (:24)
+                x = im.float().requires_grad_()
+                y = s.float().requires_grad_()
+                best = None
+                for _ in range(3):
+                    x.grad = y.grad = None
+                    t0 = time.perf_counter()
+                    mod.MaxMargin_coot.forward(me, x, y).backward()
+                    dt_ = (time.perf_counter() - t0) * 1e3
+                    best = dt_ if best is None else min(best, dt_)
+                rec["cpu_reference"] = {"step_ms": best, "cores": torch.get_num_threads(), "dtype": "fp32",
+                                        "what": "unbound MaxMargin_coot.forward of baseline/_ref + autograd backward, best of 3"}
+        out[f"maxmargin_b{B}"] = rec
+        del a, b, crit
+    return out
+
+
 def bwd_kernel_from_library(M, NAT, world, rank, Bl, D):
     import ctypes
     lib = M.load_native()
@@ -623,6 +728,13 @@ def run_b200_arm(args):
             except Exception as exc:
                 shapes[key] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
 
+    next_rows = None
+    if not args.no_extras and world == 1 and args.workload in (None, "c2"):
+        try:
+            next_rows = run_next_rows(M, NAT, torch, dev, flush)
+        except Exception as exc:
+            next_rows = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+
     extras = {}
     if not args.no_extras:
         for name in (["c3"] if world == 1 else []) + ["c4", "c5"]:
@@ -693,6 +805,8 @@ def run_b200_arm(args):
             line["workloads"] = extras
         if shapes:
             line["shapes"] = shapes
+        if next_rows:
+            line["next_rows"] = next_rows
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

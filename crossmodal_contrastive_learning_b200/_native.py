@@ -24,6 +24,7 @@ EXPORTS = (
     "crossclr_finalize", "crossclr_bwd", "crossclr_shift", "crossclr_launch_count", "crossclr_selftest",
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
     "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
+    "crossclr_maxmargin_kernel_name", "crossclr_retrieval_ranks",
     "crossclr_bwd_kernel_name", "crossclr_feature_pitch", "crossclr_segment_rows", "crossclr_bwd_accumulate", "crossclr_bwd_finish", "crossclr_bwd_scale_grad",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
@@ -98,13 +99,18 @@ def _declare(lib):
     lib.crossclr_selftest.restype = c.c_int
     lib.crossclr_selftest.argtypes = [c.c_int, vp, vp, vp, c.c_int32, c.c_int32]
     lib.crossclr_maxmargin_workspace_bytes.restype = c.c_size_t
-    lib.crossclr_maxmargin_workspace_bytes.argtypes = [c.c_int32]
+    lib.crossclr_maxmargin_workspace_bytes.argtypes = [c.c_int32, c.c_int32]
+    lib.crossclr_maxmargin_kernel_name.restype = c.c_char_p
+    lib.crossclr_maxmargin_kernel_name.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32]
+    lib.crossclr_retrieval_ranks.restype = c.c_int
+    lib.crossclr_retrieval_ranks.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, vp, c.c_size_t,
+                                             vp, vp, vp]
     lib.crossclr_maxmargin_fwd.restype = c.c_int
     lib.crossclr_maxmargin_fwd.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_float, vp,
                                            c.c_size_t, vp, vp]
     lib.crossclr_maxmargin_bwd.restype = c.c_int
-    lib.crossclr_maxmargin_bwd.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_float, vp, vp,
-                                           vp, c.c_int64, vp, c.c_int64, c.c_int, vp]
+    lib.crossclr_maxmargin_bwd.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_float, vp,
+                                           c.c_size_t, vp, vp, c.c_int64, vp, c.c_int64, c.c_int, vp]
 
 
 def load(build_if_missing: bool = True):

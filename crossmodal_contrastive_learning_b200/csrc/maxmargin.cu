@@ -1,5 +1,6 @@
-// MaxMargin_coot (trainer/loss.py:17-41 of the reference), first correct CUDA path: fp32 CUDA-core kernels for any
-// B, D.  SURVEY.md section 8 row f1 -- next to the CrossCLR hot path, not part of it.
+// MaxMargin_coot (trainer/loss.py:17-41 of the reference): the exact fp32 CUDA-core kernels for any B, D (fp32 inputs, small
+// or unaligned problems) and the dispatch to the tensor-core kernels of maxmargin_tc.cu (16-bit inputs).  SURVEY.md section 8
+// row f1 -- next to the CrossCLR hot path, not part of it.  The same forward with margin 0 yields the retrieval ranks (f4).
 //
 //   scores = im s^T (plain dot products: `cosine_sim`, :7-15, does not normalise);  d_i = scores_ii
 //   loss   = (1/B^2) sum_{i != j} [ max(0, m + scores_ij - d_i) + max(0, m + scores_ij - d_j) ]          (:34-41)
@@ -10,6 +11,9 @@
 // No B x B array is stored: the forward keeps d[B] and the hinge counts cnt[B]; the backward recomputes score tiles.
 #include "common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace crossclr {
 
 namespace {
@@ -19,7 +23,8 @@ constexpr int MT = 32;           // score tile edge; 256 threads, each 4 scores 
 template <typename T>
 __global__ void __launch_bounds__(256) mm_diag_kernel(const T* __restrict__ im, int64_t im_stride, const T* __restrict__ s,
                                                      int64_t s_stride, int B, int D, float* __restrict__ diag,
-                                                     float* __restrict__ cnt, double* __restrict__ acc) {
+                                                     float* __restrict__ cnt, double* __restrict__ acc,
+                                                     int* __restrict__ rank_row, int* __restrict__ rank_col) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) acc[0] = 0.0;
@@ -28,7 +33,11 @@ __global__ void __launch_bounds__(256) mm_diag_kernel(const T* __restrict__ im, 
   for (int d = lane; d < D; d += 32)
     dot = fmaf(to_float<T>(im[(int64_t)row * im_stride + d]), to_float<T>(s[(int64_t)row * s_stride + d]), dot);
   dot = warp_sum(dot);
-  if (lane == 0) { diag[row] = dot; cnt[row] = 0.f; }
+  if (lane == 0) {
+    diag[row] = dot; cnt[row] = 0.f;
+    if (rank_row != nullptr) rank_row[row] = 0;
+    if (rank_col != nullptr) rank_col[row] = 0;
+  }
 }
 
 // 32 x 32 tile of A B^T (rows a0.., b0..) into sc[4] of each thread; the same summation order (d ascending, one fma per
@@ -63,7 +72,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) mm_fwd_kernel(const T* __restrict__ im, int64_t im_stride, const T* __restrict__ s,
                                                     int64_t s_stride, int B, int D, float margin,
                                                     const float* __restrict__ diag, float* __restrict__ cnt,
-                                                    double* __restrict__ acc) {
+                                                    double* __restrict__ acc, int* __restrict__ rank_row,
+                                                    int* __restrict__ rank_col) {
   __shared__ float As[MT][MT + 1], Bs[MT][MT + 1];
   __shared__ float colcnt[MT];
   __shared__ float wsum[8];
@@ -84,15 +94,20 @@ __global__ void __launch_bounds__(256) mm_fwd_kernel(const T* __restrict__ im, i
     const float ci = valid ? fmaxf(0.f, margin + sc[k] - dj) : 0.f;        // :35
     local += cs + ci;
     const unsigned rowmask = __ballot_sync(0xffffffffu, cs > 0.f);
-    if (tx == 0 && rowmask) atomicAdd(&cnt[i], (float)__popc(rowmask));    // active row hinges of i in this tile
+    if (tx == 0 && rowmask) {                                              // active row hinges of i in this tile
+      atomicAdd(&cnt[i], (float)__popc(rowmask));
+      if (rank_row != nullptr) atomicAdd(&rank_row[i], __popc(rowmask));
+    }
     if (ci > 0.f) ccol += 1.f;
   }
   if (ccol > 0.f) atomicAdd(&colcnt[tx], ccol);
   local = warp_sum(local);
   if (tx == 0) wsum[ty] = local;
   __syncthreads();
-  if (threadIdx.x < MT && colcnt[threadIdx.x] > 0.f && j0 + (int)threadIdx.x < B)
+  if (threadIdx.x < MT && colcnt[threadIdx.x] > 0.f && j0 + (int)threadIdx.x < B) {
     atomicAdd(&cnt[j0 + threadIdx.x], colcnt[threadIdx.x]);                // active column hinges of j in this tile
+    if (rank_col != nullptr) atomicAdd(&rank_col[j0 + threadIdx.x], (int)colcnt[threadIdx.x]);
+  }
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += wsum[w];
@@ -157,14 +172,16 @@ __global__ void __launch_bounds__(256) mm_grad_kernel(const T* __restrict__ A, i
 
 template <typename T>
 int fwd_t(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int B, int D, float margin, float* diag,
-          float* cnt, double* acc, double* loss, cudaStream_t st) {
-  mm_diag_kernel<T><<<(B + 7) / 8, 256, 0, st>>>((const T*)im, im_stride, (const T*)s, s_stride, B, D, diag, cnt, acc);
+          float* cnt, double* acc, int* rank_row, int* rank_col, double* loss, cudaStream_t st) {
+  mm_diag_kernel<T><<<(B + 7) / 8, 256, 0, st>>>((const T*)im, im_stride, (const T*)s, s_stride, B, D, diag, cnt, acc,
+                                                 rank_row, rank_col);
   int rc = check_launch("mm_diag_kernel");
   if (rc) return rc;
   dim3 grid((B + MT - 1) / MT, (B + MT - 1) / MT);
-  mm_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)im, im_stride, (const T*)s, s_stride, B, D, margin, diag, cnt, acc);
+  mm_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)im, im_stride, (const T*)s, s_stride, B, D, margin, diag, cnt, acc,
+                                         rank_row, rank_col);
   rc = check_launch("mm_fwd_kernel");
-  if (rc) return rc;
+  if (rc || loss == nullptr) return rc;
   mm_finish_kernel<<<1, 1, 0, st>>>(acc, B, loss);
   return check_launch("mm_finish_kernel");
 }
@@ -190,30 +207,76 @@ int grad_out_t(const void* A, int64_t as, const void* Bm, int64_t bs, int B, int
   }
 }
 
+// 0 = by the rule of maxmargin_tc_applies, 1 = CUDA cores, 2 = tensor cores (an error where they do not apply)
+int maxmargin_path_override() {
+  const char* e = getenv("CROSSCLR_MAXMARGIN_PATH");
+  if (e == nullptr || !*e) return 0;
+  if (!strcmp(e, "simt")) return 1;
+  if (!strcmp(e, "tc")) return 2;
+  return 0;
+}
+
+// workspace layout: double acc | pad | float diag[B] | float cnt[B] | (256-byte aligned) float dacc[ceil128(B)][ceil64(D)]
+size_t mm_dacc_offset(int B) { return (16 + 2 * (size_t)B * sizeof(float) + 255) / 256 * 256; }
+
+// *use_tc: which kernels serve this problem; an explicit "tc" request for a problem they do not take is an error
+int mm_choose(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D, bool* use_tc) {
+  const int ov = maxmargin_path_override();
+  const bool can = maxmargin_tc_applies(im, im_stride, s, s_stride, dtype, B, D);
+  if (ov == 2 && !can) {
+    set_error("CROSSCLR_MAXMARGIN_PATH=tc: the tensor-core kernels need fp16 / bf16 inputs, batch >= 256, dim >= 64, "
+              "16-byte aligned rows (got dtype %d, batch %d, dim %d)", dtype, B, D);
+    return CROSSCLR_EINVAL;
+  }
+  *use_tc = can && ov != 1;
+  return CROSSCLR_OK;
+}
+
 }  // namespace
 
-// workspace layout: double acc | float diag[B] | float cnt[B]
-size_t maxmargin_workspace_bytes(int B) { return 16 + 2 * (size_t)B * sizeof(float); }
+size_t maxmargin_workspace_bytes(int B, int D) { return mm_dacc_offset(B) + maxmargin_tc_dacc_bytes(B, D); }
+
+const char* maxmargin_kernel_name(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D) {
+  bool tc = false;
+  if (mm_choose(im, im_stride, s, s_stride, dtype, B, D, &tc)) return "invalid";
+  return tc ? "mm_tc_kernel" : "mm_fwd_kernel";
+}
 
 int launch_maxmargin_fwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
-                         float margin, void* workspace, double* loss, cudaStream_t st) {
+                         float margin, void* workspace, int* rank_row, int* rank_col, double* loss, cudaStream_t st) {
   double* acc = (double*)workspace;
   float* diag = (float*)((char*)workspace + 16);
   float* cnt = diag + B;
+  bool tc = false;
+  int rc = mm_choose(im, im_stride, s, s_stride, dtype, B, D, &tc);
+  if (rc) return rc;
+  if (tc)
+    return launch_maxmargin_tc_fwd(im, im_stride, s, s_stride, dtype, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
   switch (dtype) {
-    case CROSSCLR_F32: return fwd_t<float>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, loss, st);
-    case CROSSCLR_F16: return fwd_t<__half>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, loss, st);
-    case CROSSCLR_BF16: return fwd_t<__nv_bfloat16>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, loss, st);
+    case CROSSCLR_F32: return fwd_t<float>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
+    case CROSSCLR_F16: return fwd_t<__half>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
+    case CROSSCLR_BF16:
+      return fwd_t<__nv_bfloat16>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
     default: set_error("crossclr_maxmargin_fwd: unsupported dtype %d", dtype); return CROSSCLR_EINVAL;
   }
 }
 
 int launch_maxmargin_bwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
-                         float margin, const void* workspace, const double* grad_out, void* d_im, int64_t d_im_stride,
+                         float margin, void* workspace, const double* grad_out, void* d_im, int64_t d_im_stride,
                          void* d_s, int64_t d_s_stride, int out_dtype, cudaStream_t st) {
   const float* diag = (const float*)((const char*)workspace + 16);
   const float* cnt = diag + B;
-  int rc;
+  bool tc = false;
+  int rc = mm_choose(im, im_stride, s, s_stride, dtype, B, D, &tc);
+  if (rc) return rc;
+  if (tc)
+    return launch_maxmargin_tc_bwd(im, im_stride, s, s_stride, dtype, B, D, margin, diag, cnt,
+                                   (float*)((char*)workspace + mm_dacc_offset(B)), grad_out, d_im, d_im_stride, d_s,
+                                   d_s_stride, out_dtype, st);
+  if ((size_t)D * MT * sizeof(float) > 200 * 1024) {
+    set_error("crossclr_maxmargin_bwd: dim %d too large for the CUDA-core path", D);
+    return CROSSCLR_EINVAL;
+  }
 #define CC_MM(T)                                                                                                           \
   rc = grad_out_t<T>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, grad_out, d_im, d_im_stride, out_dtype, st);     \
   if (!rc) rc = grad_out_t<T>(s, s_stride, im, im_stride, B, D, margin, diag, cnt, grad_out, d_s, d_s_stride, out_dtype, st)

@@ -4,8 +4,9 @@ Same constructor signature `(use_cuda: bool, margin: float = 0.1)`, attributes (
 `forward(im, s)` -> 0-dim loss in the input dtype, gradients in the input dtype.  One documented deviation: the reference
 class cannot be constructed at all (`trainer/loss.py:24` calls `super(ContrastiveLoss_coot, self)`, a name that does not
 exist, so `MaxMargin_coot(...)` raises NameError); this one constructs.  The arithmetic is `trainer/loss.py:29-41`
-(`cosine_sim`, :7-15, is a plain `mm`: no normalisation), computed by fp32 CUDA-core kernels behind the C ABI
-(`crossclr_maxmargin_fwd/bwd`); there is no CPU path.
+(`cosine_sim`, :7-15, is a plain `mm`: no normalisation) behind the C ABI (`crossclr_maxmargin_fwd/bwd`): fp16 / bf16
+inputs run on the tensor cores (tcgen05 score tiles with a hinge epilogue, csrc/maxmargin_tc.cu), fp32 inputs and small
+problems on exact fp32 CUDA-core kernels; there is no CPU path.
 """
 from __future__ import annotations
 
@@ -40,7 +41,7 @@ class _MaxMarginFunction(torch.autograd.Function):
         a, b = _rowmajor(im.detach()), _rowmajor(s.detach())
         B, D = a.shape
         with torch.cuda.device(a.device):
-            ws_bytes = int(lib.crossclr_maxmargin_workspace_bytes(B))
+            ws_bytes = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
             loss = torch.empty((), dtype=torch.float64, device=a.device)
             N.check(lib.crossclr_maxmargin_fwd(_ptr(a), _ptr(b), _DTYPE_CODE[a.dtype], a.stride(0), b.stride(0), B, D,
@@ -59,7 +60,7 @@ class _MaxMarginFunction(torch.autograd.Function):
             go = grad_out.detach().to(device=a.device, dtype=torch.float64).contiguous()
             da, db = torch.empty_like(a), torch.empty_like(b)
             N.check(lib.crossclr_maxmargin_bwd(_ptr(a), _ptr(b), _DTYPE_CODE[a.dtype], a.stride(0), b.stride(0), B, D,
-                                               ctx.margin, _ptr(ws), _ptr(go), _ptr(da), da.stride(0), _ptr(db),
+                                               ctx.margin, _ptr(ws), ws.numel(), _ptr(go), _ptr(da), da.stride(0), _ptr(db),
                                                db.stride(0), _DTYPE_CODE[a.dtype], _stream()), "crossclr_maxmargin_bwd")
         return da, db, None
 

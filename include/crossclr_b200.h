@@ -243,22 +243,41 @@ CROSSCLR_API int crossclr_timing_enable(int on);
 CROSSCLR_API int crossclr_timing_read(int kernel, double* total_ms, int64_t* launches);
 
 /*
- * MaxMargin_coot (trainer/loss.py:17-41; SURVEY.md section 8 row f1 -- beside the CrossCLR hot path).  First correct
- * path: fp32 CUDA-core kernels, any batch / dim (dim <= 1600), no batch x batch array stored.
+ * MaxMargin_coot (trainer/loss.py:17-41; SURVEY.md section 8 row f1 -- beside the CrossCLR hot path).  No batch x batch
+ * array is stored.
  *   loss_out[0] (double) = (1/B^2) sum_{i != j} [max(0, m + s_ij - s_ii) + max(0, m + s_ij - s_jj)],  s = im s^T
- * `im`, `s`: [batch][dim] device arrays of `dtype`, row strides in elements.  The forward leaves the diagonal and the
- * hinge counts in `workspace` (crossclr_maxmargin_workspace_bytes(batch) bytes), which the backward reads; `grad_out`
- * is a DEVICE pointer to the upstream scalar gradient (double) or NULL for 1.0.
+ * `im`, `s`: [batch][dim] device arrays of `dtype`, row strides in elements.  fp16 / bf16 inputs with batch >= 256,
+ * dim >= 64 and 16-byte aligned rows (base pointers and row strides) run on the tensor cores -- tcgen05 score tiles whose
+ * TMA boxes come straight out of the caller's tensors, a hinge epilogue, and for the backward the 0/1/2 indicator tile as the
+ * A operand of the gradient product; everything else (fp32 inputs: the reference multiplies them in fp32) on exact fp32
+ * CUDA-core kernels (dim <= 1600 there).  crossclr_maxmargin_kernel_name reports which (CROSSCLR_MAXMARGIN_PATH=simt|tc
+ * overrides).  The forward leaves the diagonal and the hinge counts in `workspace`
+ * (crossclr_maxmargin_workspace_bytes(batch, dim) bytes), which the backward reads and extends; `grad_out` is a DEVICE
+ * pointer to the upstream scalar gradient (double) or NULL for 1.0.
  * Replaces: trainer/loss.py:29-41 (forward) and its autograd backward.
  */
-CROSSCLR_API size_t crossclr_maxmargin_workspace_bytes(int32_t batch);
+CROSSCLR_API size_t crossclr_maxmargin_workspace_bytes(int32_t batch, int32_t dim);
+CROSSCLR_API const char* crossclr_maxmargin_kernel_name(const void* im, const void* s, int dtype, int64_t im_row_stride,
+                                           int64_t s_row_stride, int32_t batch, int32_t dim);
 CROSSCLR_API int crossclr_maxmargin_fwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
                            int32_t batch, int32_t dim, float margin, void* workspace, size_t workspace_bytes,
                            double* loss_out, void* stream);
 CROSSCLR_API int crossclr_maxmargin_bwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
-                           int32_t batch, int32_t dim, float margin, const void* workspace, const double* grad_out,
-                           void* d_im, int64_t d_im_row_stride, void* d_s, int64_t d_s_row_stride, int out_dtype,
-                           void* stream);
+                           int32_t batch, int32_t dim, float margin, void* workspace, size_t workspace_bytes,
+                           const double* grad_out, void* d_im, int64_t d_im_row_stride, void* d_s, int64_t d_s_row_stride,
+                           int out_dtype, void* stream);
+
+/*
+ * Retrieval ranks over the score matrix s = im s^T of two [batch][dim] embedding blocks (the
+ * reference only pictures retrieval, figures/qual_retriv.png, and scores with the plain mm of `cosine_sim`,
+ * trainer/loss.py:7-15 -- pass normalised rows for cosine ranking).  The MaxMargin forward at margin 0 counts exactly this:
+ *   rank_im2s[i] = #{j != i : s_ij > s_ii}   (0-based rank of item i's own partner among all s, query im_i)
+ *   rank_s2im[j] = #{i != j : s_ij > s_jj}   (query s_j against all im)
+ * recall@K = mean(rank < K).  Same kernels, workspace and path rule as crossclr_maxmargin_fwd; nothing batch x batch stored.
+ */
+CROSSCLR_API int crossclr_retrieval_ranks(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,
+                             int32_t batch, int32_t dim, void* workspace, size_t workspace_bytes, int32_t* rank_im2s,
+                             int32_t* rank_s2im, void* stream);
 
 /*
  * Hardware self-test of the tcgen05/TMA building blocks (descriptor encodings, TMEM layouts).

@@ -84,3 +84,127 @@ def test_gpu_against_oracle(B, D, dtype, scale):
     for got, ref in ((a.grad, rdim), (b.grad, rds)):
         got = got.double().cpu().numpy()
         assert np.linalg.norm(got - ref) <= tol_g * np.linalg.norm(ref) + 1e-12
+
+
+# ---- tensor-core path (csrc/maxmargin_tc.cu) and the retrieval ranks it also serves ----
+def _paired(B, D, seed, align=0.15):
+    """Unit-scale rows with a partial alignment, bf16-representable: a healthy share of the hinges is active at margin 0.1."""
+    g = torch.Generator().manual_seed(seed)
+    im = (torch.randn(B, D, generator=g) / D ** 0.5).to(torch.bfloat16).float()
+    s = (align * im + torch.randn(B, D, generator=g) / D ** 0.5).to(torch.bfloat16).float()
+    return im, s
+
+
+def _mm_raw(a, b, margin, grad_out=None):
+    """MaxMargin forward + backward through the C ABI with fp32 gradient outputs -> (loss, d_im, d_s, kernel name)."""
+    from crossmodal_contrastive_learning_b200 import _native as N
+    from crossmodal_contrastive_learning_b200.loss import _DTYPE_CODE, _ptr, _stream
+    lib = N.load()
+    B, D = a.shape
+    code = _DTYPE_CODE[a.dtype]
+    name = lib.crossclr_maxmargin_kernel_name(_ptr(a), _ptr(b), code, a.stride(0), b.stride(0), B, D).decode()
+    nb = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
+    ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
+    loss = torch.empty((), dtype=torch.float64, device=a.device)
+    N.check(lib.crossclr_maxmargin_fwd(_ptr(a), _ptr(b), code, a.stride(0), b.stride(0), B, D, float(margin), _ptr(ws), nb,
+                                       _ptr(loss), _stream()), "fwd")
+    da = torch.empty(B, D, dtype=torch.float32, device=a.device)
+    db = torch.empty(B, D, dtype=torch.float32, device=a.device)
+    go = None if grad_out is None else torch.tensor(grad_out, dtype=torch.float64, device=a.device)
+    N.check(lib.crossclr_maxmargin_bwd(_ptr(a), _ptr(b), code, a.stride(0), b.stride(0), B, D, float(margin), _ptr(ws), nb,
+                                       None if go is None else _ptr(go), _ptr(da), D, _ptr(db), D, N.F32, _stream()), "bwd")
+    torch.cuda.synchronize()
+    return loss.item(), da.double().cpu().numpy(), db.double().cpu().numpy(), name
+
+
+TC_SHAPES = [(512, 512, torch.bfloat16), (4096, 512, torch.bfloat16), (1000, 200, torch.float16),
+             (300, 72, torch.float16), (2048, 1024, torch.bfloat16), (1100, 640, torch.bfloat16), (256, 64, torch.float16)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,D,dtype", TC_SHAPES, ids=[f"{b}x{d}-{str(t)[6:]}" for b, d, t in TC_SHAPES])
+def test_tensor_core_path_against_oracle(B, D, dtype):
+    from oracle.maxmargin_oracle import maxmargin_loss_and_grads
+    im, s = _paired(B, D, seed=B + D)
+    if dtype == torch.float16:
+        im, s = im.half().float(), s.half().float()
+    rloss, rdim, rds = maxmargin_loss_and_grads(im.numpy(), s.numpy(), 0.1, grad_out=0.5)
+    assert rloss > 1e-3                                        # the case exercises active hinges
+    loss, da, db, name = _mm_raw(im.to(dtype).cuda(), s.to(dtype).cuda(), 0.1, grad_out=0.5)
+    assert name == "mm_tc_kernel"
+    # exact products, fp32 accumulation: the loss to rounding; a hinge within rounding of 0 may flip one 1/B^2 entry
+    assert abs(loss - rloss) <= 2e-6 * abs(rloss)
+    for got, ref in ((da, rdim), (db, rds)):
+        assert np.linalg.norm(got - ref) <= 1e-3 * np.linalg.norm(ref)
+
+
+@pytest.mark.gpu
+def test_tensor_core_and_cuda_core_paths_agree(monkeypatch):
+    im, s = _paired(768, 256, seed=5)
+    a, b = im.bfloat16().cuda(), s.bfloat16().cuda()
+    monkeypatch.setenv("CROSSCLR_MAXMARGIN_PATH", "simt")
+    l0, da0, db0, n0 = _mm_raw(a, b, 0.2)
+    monkeypatch.setenv("CROSSCLR_MAXMARGIN_PATH", "tc")
+    l1, da1, db1, n1 = _mm_raw(a, b, 0.2)
+    assert (n0, n1) == ("mm_fwd_kernel", "mm_tc_kernel")
+    assert abs(l0 - l1) <= 2e-6 * abs(l0)
+    assert np.linalg.norm(da0 - da1) <= 1e-3 * np.linalg.norm(da0) and np.linalg.norm(db0 - db1) <= 1e-3 * np.linalg.norm(db0)
+    # fp32 inputs are never rounded to 16 bits; asking for the tensor cores there is an error, not a silent downgrade
+    with pytest.raises(RuntimeError, match="tensor-core kernels need"):
+        _mm_raw(im.cuda(), s.cuda(), 0.2)
+    monkeypatch.delenv("CROSSCLR_MAXMARGIN_PATH")
+    assert _mm_raw(im.cuda(), s.cuda(), 0.2)[3] == "mm_fwd_kernel"
+    # a row pitch that breaks the 16-byte alignment of the TMA boxes falls back to the CUDA cores
+    wide = torch.zeros(768, 260, dtype=torch.bfloat16, device="cuda")
+    wide[:, :256] = a
+    assert _mm_raw(wide[:, :256], b, 0.2)[3] == "mm_fwd_kernel"
+
+
+@pytest.mark.gpu
+def test_module_on_tensor_cores_matches_closed_forms():
+    import crossmodal_contrastive_learning_b200 as M
+    # all rows equal: every score equals the diagonal, every hinge = m: loss = 2 m (n - 1) / n
+    n = 512
+    x = torch.tensor([[0.5, -0.25] * 64], dtype=torch.bfloat16).repeat(n, 1).cuda().requires_grad_()
+    loss = M.MaxMargin_coot(True, 0.25)(x, x.detach().clone())
+    assert abs(loss.float().item() - 2 * 0.25 * (n - 1) / n) < 4e-3        # bf16 result
+    # orthogonal pairs far apart: no active hinge, zero loss and zero gradient
+    e = torch.eye(512, dtype=torch.float16, device="cuda").requires_grad_()
+    loss = M.MaxMargin_coot(True, 0.1)(e, e.detach().clone())
+    loss.backward()
+    assert loss.item() == 0.0 and not e.grad.any()
+
+
+def test_retrieval_oracle_closed_forms():
+    from oracle.retrieval_oracle import recall_at_k, retrieval_ranks
+    ra, rb, _ = retrieval_ranks(np.eye(5), np.eye(5))
+    assert not ra.any() and not rb.any() and recall_at_k(ra)[1] == 1.0
+    # s = im rolled by one row: every query's partner scores 0, exactly one candidate scores 1
+    ra, rb, _ = retrieval_ranks(np.eye(5), np.roll(np.eye(5), 1, axis=0))
+    assert (ra == 1).all() and (rb == 1).all() and recall_at_k(ra, (1, 2)) == {1: 0.0, 2: 1.0}
+    # ties do not count against the partner
+    x = np.ones((4, 3))
+    ra, rb, _ = retrieval_ranks(x, x)
+    assert not ra.any() and not rb.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,D,dtype", [(2048, 512, torch.bfloat16), (1000, 200, torch.float16), (333, 77, torch.float32)])
+def test_retrieval_ranks_against_oracle(B, D, dtype):
+    import crossmodal_contrastive_learning_b200 as M
+    from oracle.retrieval_oracle import recall_at_k, retrieval_ranks
+    im, s = _paired(B, D, seed=B, align=0.12)
+    if dtype == torch.float16:
+        im, s = im.half().float(), s.half().float()
+    ra, rb, (gap_a, gap_b) = retrieval_ranks(im.numpy(), s.numpy())
+    assert 0.02 < recall_at_k(ra)[10] < 0.98                    # a non-trivial ranking problem
+    ga, gb = M.retrieval_ranks(im.to(dtype).cuda(), s.to(dtype).cuda())
+    assert ga.dtype == torch.int32 and ga.shape == (B,)
+    for got, ref, gap in ((ga, ra, gap_a), (gb, rb, gap_b)):
+        got = got.cpu().numpy().astype(np.int64)
+        bad = got != ref
+        # a rank may differ by one only where some candidate ties with the partner to within fp32 accumulation noise
+        assert np.abs(got - ref).max() <= 1 and (gap[bad] < 1e-6).all()
+    m = M.retrieval_metrics(im.to(dtype).cuda(), s.to(dtype).cuda())
+    assert abs(m["im2s_R@10"] - recall_at_k(ra)[10]) <= 2.0 / B and abs(m["s2im_R@1"] - recall_at_k(rb)[1]) <= 2.0 / B
+    assert m["im2s_MedR"] >= 1.0
