@@ -12,7 +12,7 @@
 // One persistent CTA per SM walks a balanced range of work units (128-row block, 256-wide slab of D, 128-column block):
 // TMA producer warp -> shared-memory ring (128-byte-swizzled [128][64] boxes straight out of the CALLER's tensors: 16-bit
 // inputs need no staging copy, rows / columns past the edge are zero-filled by TMA), one MMA-issuing lane, score tiles
-// double-buffered in TMEM, four epilogue warps.  Forward: hinge sums in registers, row counts in registers, column counts by
+// double-buffered in TMEM, eight epilogue warps (two per TMEM lane quadrant, one per 64-column half of the tile).  Forward: hinge sums in registers, row counts in registers, column counts by
 // warp ballots -> shared-memory atomics -> one global atomic per column and tile.  Backward: the indicator tile G (0 / 1 / 2:
 // exact in fp16 and bf16) is written IN PLACE over the score tile in TMEM (tcgen05.st) and is the A operand of
 // dA[128 x 256] += G(j) B_j[:, slab], B read MN-major from the same kind of boxes the score product uses; the diagonal
@@ -25,6 +25,8 @@ namespace crossclr {
 namespace {
 
 constexpr int MM_TN = 128;                    // score tile columns
+constexpr int MM_THREADS = 384;                // TMA warp, MMA warp, TMEM warp, one idle, eight epilogue warps
+constexpr int MM_EPI_THREADS = 256;
 constexpr int MM_VEC_BYTES = 2 * MM_TN * 8;   // per-tile column vector (margin - d_j) and column counts, double-buffered
 
 struct MmSeg { int ib, sb, j0, j1; bool last_of_ib; };
@@ -61,7 +63,7 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 
 // kFmt: 0 = fp16, 1 = bf16 operands.  kGrad: false = forward (hinge sums, counts), true = one direction of the backward.
 template <int kFmt, bool kGrad, bool kResident>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(MM_THREADS, 1)
 mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int B, float margin,
              const float* __restrict__ diag, float* __restrict__ cnt, double* __restrict__ acc, int* __restrict__ rank_row,
              int* __restrict__ rank_col, float* __restrict__ dacc, int dpad, int n_units, int n_slabs, int ncb, int nk,
@@ -96,8 +98,8 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < num_slots; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(pfull_bar(b), EPI_THREADS); }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, EPI_THREADS);
+    for (int b = 0; b < 2; ++b) { mbar_init(sfull_bar(b), 1); mbar_init(pfull_bar(b), MM_EPI_THREADS); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, MM_EPI_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -233,10 +235,12 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
 #pragma unroll
               for (int k16 = 0; k16 < MM_TN / 16; ++k16) {
-                // A = G[:, 16 k16 .. +16) from TMEM (8 columns of packed 16-bit pairs per K = 16 step); B = B_j[16 k16 .. +16,
-                // 64 or 128 d]: MN-major view of the TMA boxes, 16 K rows = 2048 bytes, second 64-wide atom = next slot
+                // A = G[:, 16 k16 .. +16) from TMEM (8 columns of packed 16-bit pairs per K = 16 step; each 64-column half of
+                // the tile is packed into the front of its own half); B = B_j[16 k16 .. +16, 64 or 128 d]: MN-major view of
+                // the TMA boxes, 16 K rows = 2048 bytes, second 64-wide atom = next slot
                 const uint64_t bd = make_smem_desc_sw128(st + k16 * 2048, 1024, CHUNK_BYTES);
-                umma_ts(tmem_acc + c * KC, p_tmem + k16 * 8, bd, dpair ? idesc_g128 : idesc_g64,
+                const uint32_t g_tmem = p_tmem + (k16 < 4 ? k16 * 8 : 64 + (k16 - 4) * 8);
+                umma_ts(tmem_acc + c * KC, g_tmem, bd, dpair ? idesc_g128 : idesc_g64,
                         (j > sg.j0 || k16 > 0) ? 1u : 0u);
               }
               umma_commit(empty_bar(ring.stage));
@@ -257,10 +261,11 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
       ++seg_iter;
     }
   } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - EPI_WARP0;
-    const int r = ew * 32 + lane;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16);
+    // ------------------------------------------------------------------ epilogue: 8 warps, two per TMEM lane quadrant
+    // warp (quadrant qd = warp % 4, half h): rows [32 qd, +32) of the tile, columns [64 h, +64) as two chunks of 32
+    const int qd = warp & 3, h = (warp - EPI_WARP0) >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float ninf = __int_as_float(0xff800000);
     uint32_t seg_iter = 0, p_cnt = 0;
     double tot = 0.0;
@@ -275,12 +280,14 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
       for (int j = sg.j0; j < sg.j1; ++j, ++p_cnt) {
         const int col0 = j * MM_TN;
         const uint32_t buf = p_cnt & 1;
-        const uint32_t tbuf = lane_base + buf * MM_TN;
+        const uint32_t tbuf = lane_base + buf * MM_TN + h * 64;
         float* cv = cvec + buf * MM_TN;
-        cv[r] = (col0 + r < B) ? margin - diag[col0 + r] : ninf;
-        if (!kGrad) ccnt[buf * MM_TN + r] = 0;
-        named_bar_sync(1, EPI_THREADS);
-        if (!kGrad && pend_col0 >= 0) {      // every warp is past the previous tile: flush its column counts
+        if (h == 0) {
+          cv[r] = (col0 + r < B) ? margin - diag[col0 + r] : ninf;
+          if (!kGrad) ccnt[buf * MM_TN + r] = 0;
+        }
+        named_bar_sync(1, MM_EPI_THREADS);
+        if (!kGrad && h == 0 && pend_col0 >= 0) {      // every warp is past the previous tile: flush its column counts
           const int v = ccnt[(buf ^ 1) * MM_TN + r];
           if (v != 0 && pend_col0 + r < B) {
             atomicAdd(&cnt[pend_col0 + r], (float)v);
@@ -293,15 +300,17 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
         tc_fence_after();
         uint32_t va[32], vb[32];
         tmem_ld32(tbuf, va);
-        float local = 0.f;
-        int colc[MM_TN / 32];
+        float loc[4] = {0.f, 0.f, 0.f, 0.f};
+        int rc4[4] = {0, 0, 0, 0};
+        int colc[2];
 #pragma unroll
-        for (int c = 0; c < MM_TN / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
           colc[c] = 0;
           uint32_t (&v)[32] = (c & 1) ? vb : va;
           tmem_ld_wait();
-          if (c + 1 < MM_TN / 32) tmem_ld32(tbuf + (c + 1) * 32, (c & 1) ? va : vb);
-          const float4* cv4 = reinterpret_cast<const float4*>(cv + c * 32);
+          if (c == 0) tmem_ld32(tbuf + 32, vb);
+          const int cb = h * 64 + c * 32;                 // first tile column of this chunk
+          const float4* cv4 = reinterpret_cast<const float4*>(cv + cb);
           if (kGrad) {
             uint32_t packed[16];
 #pragma unroll
@@ -314,7 +323,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               float g2 = (x2 + mi > 0.f ? 1.f : 0.f) + (x2 + cc.z > 0.f ? 1.f : 0.f);
               float g3 = (x3 + mi > 0.f ? 1.f : 0.f) + (x3 + cc.w > 0.f ? 1.f : 0.f);
               if (j == sg.ib) {                        // G_ii is applied by the finishing pass
-                const int cq = c * 32 + q;
+                const int cq = cb + q;
                 if (cq + 0 == r) g0 = 0.f;
                 if (cq + 1 == r) g1 = 0.f;
                 if (cq + 2 == r) g2 = 0.f;
@@ -323,8 +332,8 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               packed[q >> 1] = pack_pair<kFmt>(g0, g1);
               packed[(q >> 1) + 1] = pack_pair<kFmt>(g2, g3);
             }
-            // G(j) columns [32c, 32c+32) -> packed pairs in TMEM columns [16c, 16c+16) of the same buffer (score columns
-            // < 32(c+1) are already in registers, so nothing unread is overwritten)
+            // G(j) columns [64h + 32c, +32) -> packed pairs in TMEM columns [64h + 16c, +16) of the same buffer: inside the
+            // first chunk of this warp's own column half, which is in registers by now -- nothing unread is overwritten
             tmem_st16(tbuf + c * 16, packed);
           } else if (!special) {
 #pragma unroll
@@ -332,11 +341,11 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               const float4 cc = cv4[q >> 2];
               const float cj[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+              for (int e = 0; e < 4; ++e) {            // four independent accumulation chains
                 const float x = __uint_as_float(v[q + e]);
                 const float hs = x + mi, hc = x + cj[e];             // trainer/loss.py:34, :35
-                local += fmaxf(hs, 0.f) + fmaxf(hc, 0.f);
-                rowc += hs > 0.f ? 1 : 0;
+                loc[e] += fmaxf(hs, 0.f) + fmaxf(hc, 0.f);
+                rc4[e] += hs > 0.f ? 1 : 0;
                 const unsigned m = __ballot_sync(0xffffffffu, hc > 0.f);
                 if (lane == q + e) colc[c] = __popc(m);
               }
@@ -344,13 +353,13 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
           } else {
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-              const int gj = col0 + c * 32 + q;
+              const int gj = col0 + cb + q;
               const bool valid = gi < B && gj < B && gi != gj;       // :36-40
               const float x = __uint_as_float(v[q]);
-              const float hs = x + mi, hc = x + cv[c * 32 + q];
+              const float hs = x + mi, hc = x + cv[cb + q];
               if (valid) {
-                local += fmaxf(hs, 0.f) + fmaxf(hc, 0.f);
-                rowc += hs > 0.f ? 1 : 0;
+                loc[q & 3] += fmaxf(hs, 0.f) + fmaxf(hc, 0.f);
+                rc4[q & 3] += hs > 0.f ? 1 : 0;
               }
               const unsigned m = __ballot_sync(0xffffffffu, valid && hc > 0.f);
               if (lane == q) colc[c] = __popc(m);
@@ -361,10 +370,11 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive(pfull_bar(buf));
         if (!kGrad) {
-          tot += (double)local;
+          tot += (double)((loc[0] + loc[1]) + (loc[2] + loc[3]));
+          rowc += (rc4[0] + rc4[1]) + (rc4[2] + rc4[3]);
 #pragma unroll
-          for (int c = 0; c < MM_TN / 32; ++c)
-            if (colc[c] != 0) atomicAdd(&ccnt[buf * MM_TN + c * 32 + lane], colc[c]);
+          for (int c = 0; c < 2; ++c)
+            if (colc[c] != 0) atomicAdd(&ccnt[buf * MM_TN + h * 64 + c * 32 + lane], colc[c]);
           pend_col0 = col0;
         }
       }
@@ -374,7 +384,8 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
           if (rank_row != nullptr) atomicAdd(&rank_row[gi], rowc);
         }
       } else {
-        // slab accumulator -> dacc (fp32); a segment that covers its whole item stores, partial ones add
+        // slab accumulator -> dacc (fp32); a segment that covers its whole item stores, partial ones add.  The two warps of a
+        // lane quadrant take alternate 32-column chunks.
         mbar_wait(acc_full, seg_iter & 1);
         tc_fence_after();
         const int d0 = sg.sb * SLAB;
@@ -382,7 +393,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
         float* out = dacc + (int64_t)gi * dpad + d0;
         const bool whole = (sg.j0 == 0 && sg.j1 == ncb);
 #pragma unroll 1
-        for (int c = 0; c < slab_w / 32; ++c) {
+        for (int c = h; c < slab_w / 32; c += 2) {
           uint32_t v[32];
           tmem_ld32(lane_base + 2 * MM_TN + c * 32, v);
           tmem_ld_wait();
@@ -405,8 +416,8 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
       ++seg_iter;
     }
     if (!kGrad) {
-      named_bar_sync(1, EPI_THREADS);
-      if (pend_col0 >= 0) {
+      named_bar_sync(1, MM_EPI_THREADS);
+      if (h == 0 && pend_col0 >= 0) {
         const int v = ccnt[((p_cnt - 1) & 1) * MM_TN + r];
         if (v != 0 && pend_col0 + r < B) {
           atomicAdd(&cnt[pend_col0 + r], (float)v);
@@ -503,7 +514,7 @@ int mm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, i
   const int grid = std::min(n_units, sm_count());
   auto kern = mm_tc_kernel<kFmt, kGrad, kResident>;
   CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<grid, NUM_THREADS, p.smem, st>>>(ta, tb, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, p.dpad, n_units,
+  kern<<<grid, MM_THREADS, p.smem, st>>>(ta, tb, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, p.dpad, n_units,
                                           kGrad ? p.n_slabs : 1, p.ncb, p.nk, p.slots);
   return check_launch(kGrad ? "mm_tc_kernel<grad>" : "mm_tc_kernel<fwd>");
 }
