@@ -25,6 +25,8 @@ EXPORTS = (
     "crossclr_timing_enable", "crossclr_timing_read", "crossclr_pack2", "crossclr_forward",
     "crossclr_maxmargin_workspace_bytes", "crossclr_maxmargin_fwd", "crossclr_maxmargin_bwd",
     "crossclr_maxmargin_kernel_name", "crossclr_retrieval_ranks",
+    "crossclr_peer_alloc", "crossclr_peer_free", "crossclr_peer_export", "crossclr_peer_import", "crossclr_peer_release",
+    "crossclr_peer_exchange",
     "crossclr_bwd_kernel_name", "crossclr_feature_pitch", "crossclr_segment_rows", "crossclr_bwd_accumulate", "crossclr_bwd_finish", "crossclr_bwd_scale_grad",
 )
 KERNEL_FAMILIES = ("pack", "fwd", "finalize", "bwd", "grad_finish")
@@ -102,6 +104,18 @@ def _declare(lib):
     lib.crossclr_maxmargin_workspace_bytes.argtypes = [c.c_int32, c.c_int32]
     lib.crossclr_maxmargin_kernel_name.restype = c.c_char_p
     lib.crossclr_maxmargin_kernel_name.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32]
+    lib.crossclr_peer_alloc.restype = c.c_int
+    lib.crossclr_peer_alloc.argtypes = [c.c_size_t, c.POINTER(c.c_void_p)]
+    lib.crossclr_peer_free.restype = c.c_int
+    lib.crossclr_peer_free.argtypes = [vp]
+    lib.crossclr_peer_export.restype = c.c_int
+    lib.crossclr_peer_export.argtypes = [vp, vp]
+    lib.crossclr_peer_import.restype = c.c_int
+    lib.crossclr_peer_import.argtypes = [vp, c.POINTER(c.c_void_p)]
+    lib.crossclr_peer_release.restype = c.c_int
+    lib.crossclr_peer_release.argtypes = [vp]
+    lib.crossclr_peer_exchange.restype = c.c_int
+    lib.crossclr_peer_exchange.argtypes = [vp, vp, c.c_int32, c.c_int32, c.c_size_t, c.c_size_t, c.c_int, vp, vp]
     lib.crossclr_retrieval_ranks.restype = c.c_int
     lib.crossclr_retrieval_ranks.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32, vp, c.c_size_t,
                                              vp, vp, vp]

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "simt_kernels.cu", "tc_kernels.cu", "flow_kernels.cu", "maxmargin.cu", "maxmargin_tc.cu"]
+SOURCES = ["api.cu", "simt_kernels.cu", "tc_kernels.cu", "flow_kernels.cu", "maxmargin.cu", "maxmargin_tc.cu", "peer.cu"]
 HEADERS = ["common.cuh", "tc_ptx.cuh", "tc_common.cuh", "finalize.cuh", os.path.join(ROOT, "include", "crossclr_b200.h")]
 LIB = os.path.join(HERE, "libcrossclr_b200.so")
 

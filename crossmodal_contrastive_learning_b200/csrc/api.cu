@@ -362,6 +362,55 @@ int crossclr_retrieval_ranks(const void* im, const void* s, int dtype, int64_t i
                               nullptr, (cudaStream_t)stream);
 }
 
+int crossclr_peer_alloc(size_t bytes, void** ptr_out) {
+  CC_REQUIRE(ptr_out && bytes > 0, "crossclr_peer_alloc: bad argument");
+  void* p = nullptr;
+  CC_CHECK_CUDA(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e != cudaSuccess) { cudaFree(p); (void)cudaGetLastError(); set_error("crossclr_peer_alloc: memset failed: %s", cudaGetErrorString(e)); return CROSSCLR_ECUDA; }
+  *ptr_out = p;
+  return CROSSCLR_OK;
+}
+
+int crossclr_peer_free(void* ptr) {
+  if (ptr != nullptr) CC_CHECK_CUDA(cudaFree(ptr));
+  return CROSSCLR_OK;
+}
+
+int crossclr_peer_export(const void* ptr, void* handle_out) {
+  CC_REQUIRE(ptr && handle_out, "crossclr_peer_export: NULL pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == CROSSCLR_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CC_CHECK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle_out, &h, sizeof(h));
+  return CROSSCLR_OK;
+}
+
+int crossclr_peer_import(const void* handle, void** ptr_out) {
+  CC_REQUIRE(handle && ptr_out, "crossclr_peer_import: NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CC_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr_out = p;
+  return CROSSCLR_OK;
+}
+
+int crossclr_peer_release(void* ptr) {
+  if (ptr != nullptr) CC_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return CROSSCLR_OK;
+}
+
+int crossclr_peer_exchange(void* const* bases, uint32_t* const* flags, int32_t n_ranks, int32_t rank, size_t offset,
+                           size_t bytes, int entry_barrier, uint32_t* state, void* stream) {
+  CC_REQUIRE(bases && flags && state, "crossclr_peer_exchange: NULL pointer");
+  CC_REQUIRE(n_ranks >= 2 && n_ranks <= peer_max_ranks() && rank >= 0 && rank < n_ranks,
+             "crossclr_peer_exchange: %d ranks (rank %d) outside [2, %d]", n_ranks, rank, peer_max_ranks());
+  CC_REQUIRE(offset % 16 == 0 && bytes % 16 == 0, "crossclr_peer_exchange: offset and size must be multiples of 16 bytes");
+  for (int i = 0; i < n_ranks; ++i) CC_REQUIRE(bases[i] && flags[i], "crossclr_peer_exchange: NULL buffer of rank %d", i);
+  return launch_peer_exchange(bases, flags, n_ranks, rank, offset, bytes, entry_barrier, state, (cudaStream_t)stream);
+}
+
 int crossclr_timing_enable(int on) {
   g_timing_on.store(on ? 1 : 0);
   return CROSSCLR_OK;

@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -221,5 +222,10 @@ int launch_maxmargin_tc_bwd(const void* im, int64_t im_stride, const void* s, in
                             float margin, const float* diag, const float* cnt, float* dacc, const double* grad_out,
                             void* d_im, int64_t d_im_stride, void* d_s, int64_t d_s_stride, int out_dtype,
                             cudaStream_t st);
+
+// peer.cu: exchange of row shards through NVLink peer memory (one kernel: peer stores + cross-rank barrier)
+int peer_max_ranks();
+int launch_peer_exchange(void* const* bases, uint32_t* const* flags, int n, int rank, size_t offset, size_t bytes,
+                         int entry_barrier, uint32_t* state, cudaStream_t st);
 
 }  // namespace crossclr

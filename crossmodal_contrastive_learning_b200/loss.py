@@ -146,10 +146,12 @@ def _group_info(group):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
-def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
+def _forward_impl(ops, v, t, temperature, negative_weight, path, group, exchange="nccl"):
     """pack -> [all-gather features] -> row statistics of the owned rows -> [all-gather stats] -> finalize.
 
     Rank r owns stacked rows [2 r B, 2 (r+1) B): its video rows then its text rows (include/crossclr_b200.h).
+    exchange: "nccl" (two `all_gather_into_tensor`) | "peer" (one node: `crossclr_peer_exchange`, peer stores over NVLink +
+    a flag barrier in one kernel per exchange; the stacked matrix and the statistics live in an IPC-mapped buffer, peer.py).
     Returns (loss, prob, code, saved tensors)."""
     B, D = v.shape
     dev = v.device
@@ -158,9 +160,17 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
     code, feat_dtype, pitch = ops.plan(prob, v.dtype, path == "simt", _FORCED.get(path))
     S = ops.seg_rows(code, B)                                   # rows per segment in the path's layout (>= B: zero padding)
     rows = 2 * world * S
-    feat_all = torch.empty((2 * world, S, pitch), dtype=feat_dtype, device=dev)
+    plan = None
+    if world > 1 and exchange == "peer":
+        from . import peer
+        esz = torch.empty((), dtype=feat_dtype).element_size()
+        plan = peer.plan_for(group, dev, 2 * world * S * pitch * esz, rows * 8)
+        feat_all, stats = plan.feat((2 * world, S, pitch), feat_dtype), plan.stats(rows)
+        plan.generation += 1                 # the saved rows are a view of the plan's buffer: a later forward overwrites them
+    else:
+        feat_all = torch.empty((2 * world, S, pitch), dtype=feat_dtype, device=dev)
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
     rnorm = torch.empty(2 * B, dtype=torch.float32, device=dev)
-    stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
     coef = torch.empty((rows, 2), dtype=torch.float32, device=dev)          # separate allocations: the custom op returns
     scal = torch.empty(4, dtype=torch.float32, device=dev)                  # coef and scal, and outputs must not alias
     loss = torch.empty((), dtype=torch.float64, device=dev)
@@ -169,6 +179,18 @@ def _forward_impl(ops, v, t, temperature, negative_weight, path, group):
         return loss, prob, code, (feat_all, rnorm, coef, scal)
     import torch.distributed as dist
     feat_loc = feat_all[2 * rank:2 * rank + 2]
+    if plan is not None:
+        # the entry barrier of the first exchange: no peer stores into this rank's rows before it is done with the previous
+        # step (its backward reads them), and pack below must not run ahead of the peers' previous readers either -- pack
+        # writes LOCAL memory only, which no peer reads, so it may go first
+        ops.pack2(v, t, feat_loc, rnorm, code)
+        fb = feat_loc.numel() * feat_loc.element_size()
+        plan.exchange(rank * fb, fb, True, _stream())
+        ops.fwd(prob, code, feat_all, stats)
+        sb = 2 * S * 8
+        plan.exchange(plan.feat_bytes + rank * sb, sb, False, _stream())
+        ops.finalize(prob, code, stats, coef, loss, scal)
+        return loss, prob, code, (feat_all, rnorm, coef, scal)
     ops.pack2(v, t, feat_loc, rnorm, code)
     # in-place all-gather: rank r's block already sits at its slot of the output
     dist.all_gather_into_tensor(feat_all.view(-1), feat_loc.reshape(-1), group=group)
@@ -209,7 +231,7 @@ class _CrossCLRFunction(torch.autograd.Function):
     effective temperature tau / logit_scale and the Parameter receives d loss / d logit_scale."""
 
     @staticmethod
-    def forward(ctx, video, text, temperature, negative_weight, path, group, grad_scale, logit_scale=None):
+    def forward(ctx, video, text, temperature, negative_weight, path, group, grad_scale, logit_scale=None, exchange="nccl"):
         ops = _ops()
         _check_inputs(video, text)
         in_dtype = video.dtype
@@ -224,7 +246,13 @@ class _CrossCLRFunction(torch.autograd.Function):
             ctx.scale_dtype = logit_scale.dtype
             temperature = float(temperature) / ctx.scale
         with torch.cuda.device(v.device):
-            loss, prob, code, saved = _forward_impl(ops, v, t, temperature, negative_weight, path, group)
+            loss, prob, code, saved = _forward_impl(ops, v, t, temperature, negative_weight, path, group, exchange)
+        ctx.peer_plan = ctx.peer_generation = None
+        if group is not None and exchange == "peer" and _group_info(group)[0] > 1:
+            from . import peer
+            esz = saved[0].element_size()
+            ctx.peer_plan = peer.plan_for(group, v.device, saved[0].numel() * esz, saved[2].shape[0] * 8)
+            ctx.peer_generation = ctx.peer_plan.generation
         ctx.save_for_backward(*saved)
         ctx.prob, ctx.code, ctx.in_dtype, ctx.grad_scale = prob, code, in_dtype, float(grad_scale)
         return loss
@@ -232,6 +260,9 @@ class _CrossCLRFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         saved = ctx.saved_tensors
+        if ctx.peer_plan is not None and ctx.peer_plan.generation != ctx.peer_generation:
+            raise RuntimeError("exchange='peer': this forward's stacked rows were overwritten by a later forward on the same "
+                               "process group (one outstanding forward per group; use exchange='nccl' otherwise)")
         out_dtype = torch.float32 if ctx.in_dtype == torch.float64 else ctx.in_dtype
         with torch.cuda.device(saved[0].device):
             res = _backward_impl(_ops(), ctx.prob, ctx.code, saved, grad_out, ctx.grad_scale, out_dtype, ctx.scale)
@@ -239,7 +270,7 @@ class _CrossCLRFunction(torch.autograd.Function):
         if ctx.in_dtype == torch.float64:
             dv, dt = dv.double(), dt.double()
         ds = res[2].to(ctx.scale_dtype) if ctx.scale is not None else None
-        return dv, dt, None, None, None, None, None, ds
+        return dv, dt, None, None, None, None, None, ds, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -324,10 +355,13 @@ def _op_backward_formula(ctx, g_loss, g_feat, g_rnorm, g_coef, g_scal):
 _op_forward.register_autograd(_op_backward_formula, setup_context=_op_setup_context)
 
 
-def _criterion(video, text, temperature, negative_weight, path, group, grad_scale, logit_scale=None):
+def _criterion(video, text, temperature, negative_weight, path, group, grad_scale, logit_scale=None, exchange="nccl"):
     """Dispatch: custom ops on a single rank (traceable), the autograd.Function with a process group or a learnable scale."""
+    if exchange not in ("nccl", "peer"):
+        raise ValueError("exchange must be 'nccl' or 'peer'")
     if group is not None or logit_scale is not None:
-        return _CrossCLRFunction.apply(video, text, temperature, negative_weight, path, group, grad_scale, logit_scale)
+        return _CrossCLRFunction.apply(video, text, temperature, negative_weight, path, group, grad_scale, logit_scale,
+                                       exchange)
     _check_inputs(video, text)
     if video.dtype == torch.float64:          # kernels compute in fp32; autograd casts the gradients back
         video, text = video.float(), text.float()
@@ -355,6 +389,10 @@ class CrossCLR_onlyIntraModality(nn.Module):
     (defaults reproduce the reference's single-device behaviour):
       process_group  torch.distributed group whose ranks each hold a row shard of the global batch
       grad_scale     multiplies the returned gradients (set to world_size under DDP's gradient averaging)
+      exchange       "nccl" (default): two NCCL all-gathers per step | "peer": ranks of ONE node store their row shard
+                     straight into every rank's stacked matrix over NVLink (CUDA-IPC-mapped buffers, one kernel per exchange
+                     with the cross-rank barrier inside, csrc/peer.cu).  The first step maps the buffers (collective, outside
+                     graph capture); one forward may be outstanding per group (its saved rows live in the shared buffer)
       path           "auto" | "tc" (tcgen05 kernels, fp16 operands) | "split" (tcgen05 kernels, fp32 inputs as fp16 hi + lo
                      pairs) | "simt" (exact-fp32 CUDA-core kernels).  "auto": 16-bit inputs -> "tc"; fp32 inputs -> "split"
                      where it applies (>= 1024 global samples, D <= 1024), else "simt"; temperatures below ~0.0073 and tiny
@@ -368,7 +406,7 @@ class CrossCLR_onlyIntraModality(nn.Module):
     """
 
     def __init__(self, temperature=0.03, negative_weight=0.8, logger=None, *, process_group=None, grad_scale=1.0,
-                 path="auto", learnable_temperature=False):
+                 path="auto", learnable_temperature=False, exchange="nccl"):
         super().__init__()
         self.logit_scale = nn.Parameter(torch.ones([]))            # trainer/loss.py:52 (registered, never used)
         self.criterion = torch.nn.CrossEntropyLoss(reduction='none')  # :53 (registered, never used)
@@ -381,6 +419,9 @@ class CrossCLR_onlyIntraModality(nn.Module):
         self.grad_scale = grad_scale
         self.path = path
         self.learnable_temperature = bool(learnable_temperature)
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange
 
     def forward(self, video_features, text_features):
         """
@@ -392,10 +433,12 @@ class CrossCLR_onlyIntraModality(nn.Module):
         """
         # temperature / negative_w are read per call (trainer/loss.py:90-93, :99-100)
         return _criterion(video_features, text_features, self.temperature, self.negative_w, self.path,
-                          self.process_group, self.grad_scale, self.logit_scale if self.learnable_temperature else None)
+                          self.process_group, self.grad_scale, self.logit_scale if self.learnable_temperature else None,
+                          self.exchange)
 
 
 def crossclr_loss(video_features, text_features, temperature=0.03, negative_weight=0.8, *, process_group=None,
-                  grad_scale=1.0, path="auto"):
+                  grad_scale=1.0, path="auto", exchange="nccl"):
     """Functional form of `CrossCLR_onlyIntraModality.forward`."""
-    return _criterion(video_features, text_features, temperature, negative_weight, path, process_group, grad_scale)
+    return _criterion(video_features, text_features, temperature, negative_weight, path, process_group, grad_scale,
+                      exchange=exchange)

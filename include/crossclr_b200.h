@@ -280,6 +280,29 @@ CROSSCLR_API int crossclr_retrieval_ranks(const void* im, const void* s, int dty
                              int32_t* rank_s2im, void* stream);
 
 /*
+ * Exchange of row shards through NVLink peer memory on one node (SURVEY.md section 8 rows e / f2): what the row-sharded step
+ * uses instead of the two NCCL all-gathers of trainer-side code (the reference itself is single-device; its DDP caller would
+ * all-gather features before trainer/loss.py:79).  Every rank allocates buffers of one size with crossclr_peer_alloc
+ * (cudaMalloc, zeroed), exports a 64-byte handle, and imports the handles of its peers (CUDA IPC, one process per GPU).
+ * crossclr_peer_exchange is ONE kernel: it stores bytes [offset, offset + bytes) of the local buffer bases[rank] to the same
+ * offset of every other bases[p], and its last block runs a cross-rank barrier over `flags` (flags[p] = rank p's array of
+ * 2 n_ranks 32-bit words, peer-mapped like the buffers; zero before the first exchange).  When it completes in stream order,
+ * every rank's slice is in this rank's buffer.  `entry_barrier` != 0 adds a barrier BEFORE the stores: no rank overwrites a
+ * peer's buffer until that peer has reached the same exchange in its own stream (i.e. is done reading the previous contents).
+ * `bases` / `flags` are HOST arrays of n_ranks DEVICE pointers; `state`: four zero-initialised 32-bit words of local device
+ * memory (epochs, ticket).  Collective semantics: every rank issues the same sequence of exchanges.  Capturable in a CUDA
+ * graph.
+ */
+#define CROSSCLR_PEER_HANDLE_BYTES 64
+CROSSCLR_API int crossclr_peer_alloc(size_t bytes, void** ptr_out);
+CROSSCLR_API int crossclr_peer_free(void* ptr);
+CROSSCLR_API int crossclr_peer_export(const void* ptr, void* handle_out);
+CROSSCLR_API int crossclr_peer_import(const void* handle, void** ptr_out);
+CROSSCLR_API int crossclr_peer_release(void* ptr);
+CROSSCLR_API int crossclr_peer_exchange(void* const* bases, uint32_t* const* flags, int32_t n_ranks, int32_t rank, size_t offset,
+                           size_t bytes, int entry_barrier, uint32_t* state, void* stream);
+
+/*
  * Hardware self-test of the tcgen05/TMA building blocks (descriptor encodings, TMEM layouts).
  * `variant` selects the block under test (0: K-major x K-major, 1: swizzled thread-written A x MN-major
  * B with b given as [k][n], 2: A from TMEM, 3: un-swizzled thread-written A, 4: one cta_group::2 MMA stream over

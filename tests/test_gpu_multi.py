@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, B, D, path, out, graphed=False):
+def _worker(rank, world, port, B, D, path, out, graphed=False, exchange="nccl"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
@@ -32,9 +32,9 @@ def _worker(rank, world, port, B, D, path, out, graphed=False):
         bl = B // world
         vl = v[rank * bl:(rank + 1) * bl].float().cuda().requires_grad_()
         tl = t[rank * bl:(rank + 1) * bl].float().cuda().requires_grad_()
-        crit = M.CrossCLR_onlyIntraModality(0.03, 0.8, process_group=dist.group.WORLD, path=path)
+        crit = M.CrossCLR_onlyIntraModality(0.03, 0.8, process_group=dist.group.WORLD, path=path, exchange=exchange)
         step = M.GraphedCrossCLR(crit, bl, D, dtype=torch.float32) if graphed else crit   # graphs capture the all-gathers
-        for _ in range(2):                       # twice: buffers are recycled by the caching allocator / replayed
+        for _ in range(3):                       # repeatedly: buffers are recycled by the caching allocator / replayed / shared
             vl.grad = tl.grad = None
             loss = step(vl, tl)
             loss.backward()
@@ -42,15 +42,18 @@ def _worker(rank, world, port, B, D, path, out, graphed=False):
         out[rank] = (loss.item(), vl.grad.double().cpu().numpy(), tl.grad.double().cpu().numpy())
         dist.barrier()
     finally:
-        if graphed:
+        if graphed or exchange == "peer":
             out[f"done{rank}"] = True
             os._exit(0)                          # tearing NCCL down under live graphs hangs on this stack (see bench.py)
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B,D,path,graphed", [(1024, 256, "tc", False), (512, 512, "tc", False), (1024, 1024, "tc", False),
-                                              (384, 96, "simt", False), (1024, 512, "tc", True)])
-def test_sharded_gpu_matches_global_oracle(B, D, path, graphed):
+@pytest.mark.parametrize("B,D,path,graphed,exchange", [
+    (1024, 256, "tc", False, "nccl"), (512, 512, "tc", False, "nccl"), (1024, 1024, "tc", False, "nccl"),
+    (384, 96, "simt", False, "nccl"), (1024, 512, "tc", True, "nccl"),
+    # exchange="peer": row shards stored into every rank's stacked matrix over NVLink (csrc/peer.cu) instead of NCCL
+    (1024, 256, "tc", False, "peer"), (384, 96, "simt", False, "peer"), (1024, 512, "tc", True, "peer")])
+def test_sharded_gpu_matches_global_oracle(B, D, path, graphed, exchange):
     import torch.multiprocessing as mp
     from oracle import crossclr_oracle as O
     world = min(torch.cuda.device_count(), 4)
@@ -59,7 +62,7 @@ def test_sharded_gpu_matches_global_oracle(B, D, path, graphed):
     if path == "tc" and (B // world) % 128:
         world = 2
     out = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), B, D, path, out, graphed), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), B, D, path, out, graphed, exchange), nprocs=world, join=True)
     g = torch.Generator().manual_seed(77)
     v = torch.randn(B, D, generator=g).to(torch.bfloat16)
     t = (v.float() + 2.0 * torch.randn(B, D, generator=g)).to(torch.bfloat16)
