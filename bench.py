@@ -244,6 +244,9 @@ def synthetic_shard(Bg, D, lo, hi, seed=0):
     return out
 
 
+EXCHANGE = ["nccl"]          # how the ranks of this run exchange row shards (set once by run_b200_arm)
+
+
 def kernel_times_eager(crit, v_dev, t_dev, steps, flush, NAT, torch):
     """Per-kernel device time of eager steps (the library's own stream-ordered cudaEvents, recorded around each launch
     after all host-side preparation)."""
@@ -322,7 +325,7 @@ def run_extra_workload(name, M, NAT, torch, dist, world, rank, dev, group, flush
     v_host, t_host = synthetic_shard(Bg, D, rank * Bl, (rank + 1) * Bl, seed=1)
     v_dev, t_dev = v_host.to(dev), t_host.to(dev)
     del v_host, t_host
-    crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group).to(dev)
+    crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group, exchange=EXCHANGE[0]).to(dev)
 
     def step():
         v, t = v_dev.detach().requires_grad_(), t_dev.detach().requires_grad_()
@@ -583,7 +586,24 @@ def run_b200_arm(args):
     lo, hi = rank * Bl, (rank + 1) * Bl
     v_host, t_host = synthetic_shard(Bg, D, lo, hi)
 
-    crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group).to(dev)
+    # how the ranks exchange their row shards: peer stores over NVLink (csrc/peer.cu) where CUDA IPC works on this box,
+    # else the two NCCL all-gathers; every rank takes the same decision
+    exchange, exchange_note = "nccl", None
+    if world > 1 and args.exchange in ("auto", "peer"):
+        ok = 1
+        try:
+            from crossmodal_contrastive_learning_b200 import peer as PEER
+            PEER.plan_for(group, dev, 4096, 4096)
+        except Exception as exc:
+            ok, exchange_note = 0, f"peer exchange unavailable ({type(exc).__name__}: {str(exc)[:120]})"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            exchange = "peer"
+        elif args.exchange == "peer":
+            raise SystemExit(exchange_note or "peer exchange unavailable on another rank")
+    EXCHANGE[0] = exchange
+    crit = M.CrossCLR_onlyIntraModality(TAU, W, process_group=group, exchange=exchange).to(dev)
     v_dev = v_host.to(dev)
     t_dev = t_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
@@ -771,9 +791,16 @@ def run_b200_arm(args):
                        "temperature": TAU, "negative_weight": W,
                        "l2": "value: flushed between steps (256 MiB write); e2e: each step's inputs arrive by H2D copy",
                        "launch": ("one CUDA graph launch per step (HostFedCrossCLR: pack + forward + backward"
-                                  + (", NCCL all-gathers captured" if world > 1 else "") + ")" if use_graph
+                                  + ((", peer-store exchanges captured" if exchange == "peer" else ", NCCL all-gathers captured")
+                                     if world > 1 else "") + ")" if use_graph
                                   else "eager module calls" + (f"; {graph_note}" if graph_note else "")),
-                       "parallelism": f"row-sharded x{world}, NCCL all-gather of features + row stats" if world > 1 else "single GPU",
+                       "parallelism": (f"row-sharded x{world}, " + ("row shards and row statistics stored into every rank's buffers over "
+                                       "NVLink peer memory (crossclr_peer_exchange: stores + flag barrier in one kernel, twice per step)"
+                                       if exchange == "peer" else "NCCL all-gather of features + row stats")
+                                       + (f"; {exchange_note}" if exchange_note else "")) if world > 1 else "single GPU",
+                       "exchange": exchange if world > 1 else None,
+                       "nvlink_bytes_stored_per_rank_per_step": ((world - 1) * (2 * Bl * (D + 64) * 2 + 2 * Bl * 8)
+                                                                 if (world > 1 and exchange == "peer") else None),
                        "loss": loss_val},
             "e2e": {"value": Bg / (e2e_ms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 2 * Bl * D * 2, "d2h_bytes_per_step": 8,
@@ -829,6 +856,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how ranks exchange row shards (auto: NVLink peer stores where CUDA IPC works, else NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="time eager module calls instead of CUDA-graph replays")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (c3 / c4 / c5 records)")
     ap.add_argument("--no-parity", action="store_true", help="skip the per-rank oracle check of the headline workload")

@@ -277,14 +277,17 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
       const int gi = row0 + r;
       const float mi = gi < B ? margin - diag[gi] : ninf;      // rows past the edge: every comparison false
       int rowc = 0;
+      // d_j of the tile's columns, fetched one tile ahead (a global load right in front of the barrier costs its latency per tile)
+      float dj_next = (h == 0 && sg.j0 * MM_TN + r < B) ? diag[sg.j0 * MM_TN + r] : 0.f;
       for (int j = sg.j0; j < sg.j1; ++j, ++p_cnt) {
         const int col0 = j * MM_TN;
         const uint32_t buf = p_cnt & 1;
         const uint32_t tbuf = lane_base + buf * MM_TN + h * 64;
         float* cv = cvec + buf * MM_TN;
         if (h == 0) {
-          cv[r] = (col0 + r < B) ? margin - diag[col0 + r] : ninf;
+          cv[r] = (col0 + r < B) ? margin - dj_next : ninf;
           if (!kGrad) ccnt[buf * MM_TN + r] = 0;
+          if (j + 1 < sg.j1 && col0 + MM_TN + r < B) dj_next = diag[col0 + MM_TN + r];
         }
         named_bar_sync(1, MM_EPI_THREADS);
         if (!kGrad && h == 0 && pend_col0 >= 0) {      // every warp is past the previous tile: flush its column counts
