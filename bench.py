@@ -481,7 +481,7 @@ def run_next_rows(M, NAT, torch, dev, flush, reps=10):
         if B == 4096:
             rl, rda, rdb = maxmargin_loss_and_grads(im.float().numpy(), s.float().numpy(), 0.1)
             af = im.float().to(dev).bfloat16()
-            ws_n = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
+            ws_n = int(lib.crossclr_maxmargin_workspace_bytes(B, D, code))
             ws = torch.empty(ws_n, dtype=torch.uint8, device=dev)
             loss64 = torch.empty((), dtype=torch.float64, device=dev)
             da = torch.empty(B, D, dtype=torch.float32, device=dev)

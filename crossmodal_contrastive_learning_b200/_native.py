@@ -101,7 +101,7 @@ def _declare(lib):
     lib.crossclr_selftest.restype = c.c_int
     lib.crossclr_selftest.argtypes = [c.c_int, vp, vp, vp, c.c_int32, c.c_int32]
     lib.crossclr_maxmargin_workspace_bytes.restype = c.c_size_t
-    lib.crossclr_maxmargin_workspace_bytes.argtypes = [c.c_int32, c.c_int32]
+    lib.crossclr_maxmargin_workspace_bytes.argtypes = [c.c_int32, c.c_int32, c.c_int]
     lib.crossclr_maxmargin_kernel_name.restype = c.c_char_p
     lib.crossclr_maxmargin_kernel_name.argtypes = [vp, vp, c.c_int, c.c_int64, c.c_int64, c.c_int32, c.c_int32]
     lib.crossclr_peer_alloc.restype = c.c_int

@@ -309,8 +309,8 @@ int crossclr_bwd(const crossclr_problem_t* p, int path, const void* feat, const 
                              out_dtype, workspace, stream);
 }
 
-size_t crossclr_maxmargin_workspace_bytes(int32_t batch, int32_t dim) {
-  return (batch >= 1 && dim >= 1) ? maxmargin_workspace_bytes(batch, dim) : 0;
+size_t crossclr_maxmargin_workspace_bytes(int32_t batch, int32_t dim, int dtype) {
+  return (batch >= 1 && dim >= 1) ? maxmargin_workspace_bytes(batch, dim, dtype) : 0;
 }
 
 const char* crossclr_maxmargin_kernel_name(const void* im, const void* s, int dtype, int64_t im_row_stride,
@@ -318,13 +318,13 @@ const char* crossclr_maxmargin_kernel_name(const void* im, const void* s, int dt
   return maxmargin_kernel_name(im, im_row_stride, s, s_row_stride, dtype, batch, dim);
 }
 
-static int maxmargin_check(const char* who, const void* im, const void* s, int64_t im_row_stride, int64_t s_row_stride,
-                           int32_t batch, int32_t dim, const void* workspace, size_t workspace_bytes) {
+static int maxmargin_check(const char* who, const void* im, const void* s, int dtype, int64_t im_row_stride,
+                           int64_t s_row_stride, int32_t batch, int32_t dim, const void* workspace, size_t workspace_bytes) {
   CC_REQUIRE(im && s && workspace, "%s: NULL pointer", who);
   CC_REQUIRE(batch >= 1 && dim >= 1 && im_row_stride >= dim && s_row_stride >= dim, "%s: bad shape/stride", who);
   CC_REQUIRE((int64_t)batch * batch < ((int64_t)1 << 40), "%s: batch too large", who);
-  if (workspace_bytes < maxmargin_workspace_bytes(batch, dim)) {
-    set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, maxmargin_workspace_bytes(batch, dim));
+  if (workspace_bytes < maxmargin_workspace_bytes(batch, dim, dtype)) {
+    set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, maxmargin_workspace_bytes(batch, dim, dtype));
     return CROSSCLR_EWORKSPACE;
   }
   return CROSSCLR_OK;
@@ -334,7 +334,7 @@ int crossclr_maxmargin_fwd(const void* im, const void* s, int dtype, int64_t im_
                            int32_t batch, int32_t dim, float margin, void* workspace, size_t workspace_bytes,
                            double* loss_out, void* stream) {
   CC_REQUIRE(loss_out, "crossclr_maxmargin_fwd: NULL pointer");
-  int rc = maxmargin_check("crossclr_maxmargin_fwd", im, s, im_row_stride, s_row_stride, batch, dim, workspace, workspace_bytes);
+  int rc = maxmargin_check("crossclr_maxmargin_fwd", im, s, dtype, im_row_stride, s_row_stride, batch, dim, workspace, workspace_bytes);
   if (rc) return rc;
   return launch_maxmargin_fwd(im, im_row_stride, s, s_row_stride, dtype, batch, dim, margin, workspace, nullptr, nullptr,
                               loss_out, (cudaStream_t)stream);
@@ -346,7 +346,7 @@ int crossclr_maxmargin_bwd(const void* im, const void* s, int dtype, int64_t im_
                            int out_dtype, void* stream) {
   CC_REQUIRE(d_im && d_s, "crossclr_maxmargin_bwd: NULL pointer");
   CC_REQUIRE(d_im_row_stride >= dim && d_s_row_stride >= dim, "crossclr_maxmargin_bwd: bad shape/stride");
-  int rc = maxmargin_check("crossclr_maxmargin_bwd", im, s, im_row_stride, s_row_stride, batch, dim, workspace, workspace_bytes);
+  int rc = maxmargin_check("crossclr_maxmargin_bwd", im, s, dtype, im_row_stride, s_row_stride, batch, dim, workspace, workspace_bytes);
   if (rc) return rc;
   return launch_maxmargin_bwd(im, im_row_stride, s, s_row_stride, dtype, batch, dim, margin, workspace, grad_out, d_im,
                               d_im_row_stride, d_s, d_s_row_stride, out_dtype, (cudaStream_t)stream);
@@ -356,7 +356,7 @@ int crossclr_retrieval_ranks(const void* im, const void* s, int dtype, int64_t i
                              int32_t batch, int32_t dim, void* workspace, size_t workspace_bytes, int32_t* rank_im2s,
                              int32_t* rank_s2im, void* stream) {
   CC_REQUIRE(rank_im2s && rank_s2im, "crossclr_retrieval_ranks: NULL pointer");
-  int rc = maxmargin_check("crossclr_retrieval_ranks", im, s, im_row_stride, s_row_stride, batch, dim, workspace, workspace_bytes);
+  int rc = maxmargin_check("crossclr_retrieval_ranks", im, s, dtype, im_row_stride, s_row_stride, batch, dim, workspace, workspace_bytes);
   if (rc) return rc;
   return launch_maxmargin_fwd(im, im_row_stride, s, s_row_stride, dtype, batch, dim, 0.0f, workspace, rank_im2s, rank_s2im,
                               nullptr, (cudaStream_t)stream);

@@ -204,7 +204,7 @@ int launch_bwd_flow(const Geometry& g, const void* feat_f16, const float* coef, 
 int run_selftest(int variant, const uint16_t* a, const uint16_t* b, float* out, int n, int k);
 
 // maxmargin.cu (MaxMargin_coot, trainer/loss.py:17-41; retrieval ranks = the same forward at margin 0)
-size_t maxmargin_workspace_bytes(int B, int D);
+size_t maxmargin_workspace_bytes(int B, int D, int dtype);
 const char* maxmargin_kernel_name(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D);
 // rank_row / rank_col (optional, int[B]): #{j != i : m + s_ij - s_ii > 0} and #{i != j : m + s_ij - s_jj > 0}; loss optional
 int launch_maxmargin_fwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
@@ -215,13 +215,14 @@ int launch_maxmargin_bwd(const void* im, int64_t im_stride, const void* s, int64
 // maxmargin_tc.cu: tcgen05 score tiles with a hinge epilogue (16-bit inputs, TMA straight from the caller's tensors)
 bool maxmargin_tc_applies(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D);
 size_t maxmargin_tc_dacc_bytes(int B, int D);
+size_t maxmargin_tc_stage_bytes(int B, int D, int dtype);   // fp32 inputs: staged fp16 [hi | lo] rows + scales, else 0
 int launch_maxmargin_tc_fwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
-                            float margin, float* diag, float* cnt, double* acc, int* rank_row, int* rank_col, double* loss,
-                            cudaStream_t st);
+                            float margin, float* diag, float* cnt, double* acc, void* stage, int* rank_row, int* rank_col,
+                            double* loss, cudaStream_t st);
 int launch_maxmargin_tc_bwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
-                            float margin, const float* diag, const float* cnt, float* dacc, const double* grad_out,
-                            void* d_im, int64_t d_im_stride, void* d_s, int64_t d_s_stride, int out_dtype,
-                            cudaStream_t st);
+                            float margin, const float* diag, const float* cnt, float* dacc, void* stage,
+                            const double* grad_out, void* d_im, int64_t d_im_stride, void* d_s, int64_t d_s_stride,
+                            int out_dtype, cudaStream_t st);
 
 // peer.cu: exchange of row shards through NVLink peer memory (one kernel: peer stores + cross-rank barrier)
 int peer_max_ranks();

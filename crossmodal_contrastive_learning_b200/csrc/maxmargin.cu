@@ -216,15 +216,17 @@ int maxmargin_path_override() {
   return 0;
 }
 
-// workspace layout: double acc | pad | float diag[B] | float cnt[B] | (256-byte aligned) float dacc[ceil128(B)][ceil64(D)]
+// workspace layout: double acc | pad | float diag[B] | float cnt[B] | (256-byte aligned) float dacc[ceil128(B)][ceil64(D)] |
+// (fp32 inputs) the staged fp16 [hi | lo] rows of both tensors
 size_t mm_dacc_offset(int B) { return (16 + 2 * (size_t)B * sizeof(float) + 255) / 256 * 256; }
+size_t mm_stage_offset(int B, int D) { return mm_dacc_offset(B) + (maxmargin_tc_dacc_bytes(B, D) + 255) / 256 * 256; }
 
 // *use_tc: which kernels serve this problem; an explicit "tc" request for a problem they do not take is an error
 int mm_choose(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D, bool* use_tc) {
   const int ov = maxmargin_path_override();
   const bool can = maxmargin_tc_applies(im, im_stride, s, s_stride, dtype, B, D);
   if (ov == 2 && !can) {
-    set_error("CROSSCLR_MAXMARGIN_PATH=tc: the tensor-core kernels need fp16 / bf16 inputs, batch >= 256, dim >= 64, "
+    set_error("CROSSCLR_MAXMARGIN_PATH=tc: the tensor-core kernels need batch >= 256, dim >= 64 and, for fp16 / bf16 inputs, "
               "16-byte aligned rows (got dtype %d, batch %d, dim %d)", dtype, B, D);
     return CROSSCLR_EINVAL;
   }
@@ -234,7 +236,9 @@ int mm_choose(const void* im, int64_t im_stride, const void* s, int64_t s_stride
 
 }  // namespace
 
-size_t maxmargin_workspace_bytes(int B, int D) { return mm_dacc_offset(B) + maxmargin_tc_dacc_bytes(B, D); }
+size_t maxmargin_workspace_bytes(int B, int D, int dtype) {
+  return mm_stage_offset(B, D) + maxmargin_tc_stage_bytes(B, D, dtype);
+}
 
 const char* maxmargin_kernel_name(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D) {
   bool tc = false;
@@ -251,7 +255,8 @@ int launch_maxmargin_fwd(const void* im, int64_t im_stride, const void* s, int64
   int rc = mm_choose(im, im_stride, s, s_stride, dtype, B, D, &tc);
   if (rc) return rc;
   if (tc)
-    return launch_maxmargin_tc_fwd(im, im_stride, s, s_stride, dtype, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
+    return launch_maxmargin_tc_fwd(im, im_stride, s, s_stride, dtype, B, D, margin, diag, cnt, acc,
+                                   (char*)workspace + mm_stage_offset(B, D), rank_row, rank_col, loss, st);
   switch (dtype) {
     case CROSSCLR_F32: return fwd_t<float>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
     case CROSSCLR_F16: return fwd_t<__half>(im, im_stride, s, s_stride, B, D, margin, diag, cnt, acc, rank_row, rank_col, loss, st);
@@ -271,8 +276,8 @@ int launch_maxmargin_bwd(const void* im, int64_t im_stride, const void* s, int64
   if (rc) return rc;
   if (tc)
     return launch_maxmargin_tc_bwd(im, im_stride, s, s_stride, dtype, B, D, margin, diag, cnt,
-                                   (float*)((char*)workspace + mm_dacc_offset(B)), grad_out, d_im, d_im_stride, d_s,
-                                   d_s_stride, out_dtype, st);
+                                   (float*)((char*)workspace + mm_dacc_offset(B)), (char*)workspace + mm_stage_offset(B, D),
+                                   grad_out, d_im, d_im_stride, d_s, d_s_stride, out_dtype, st);
   if ((size_t)D * MT * sizeof(float) > 200 * 1024) {
     set_error("crossclr_maxmargin_bwd: dim %d too large for the CUDA-core path", D);
     return CROSSCLR_EINVAL;

@@ -17,7 +17,9 @@
 // exact in fp16 and bf16) is written IN PLACE over the score tile in TMEM (tcgen05.st) and is the A operand of
 // dA[128 x 256] += G(j) B_j[:, slab], B read MN-major from the same kind of boxes the score product uses; the diagonal
 // entry is applied by the finishing pass (-cnt_i B_i), where it is exact whatever the count.
-// fp32 inputs stay on the CUDA-core path (maxmargin.cu), like small problems.
+// fp32 inputs (the reference multiplies them in fp32) are staged as fp16 hi + lo pairs after a power-of-two scale per tensor and
+// the score product runs over K = 3 D (hi.hi + lo.hi + hi.lo, a column map in the TMA producer): scores to ~2^-22 relative,
+// the dropped lo.lo term included -- the precision of an fp32 dot product.  Small problems stay on the CUDA cores (maxmargin.cu).
 #include "tc_common.cuh"
 
 namespace crossclr {
@@ -67,7 +69,12 @@ __global__ void __launch_bounds__(MM_THREADS, 1)
 mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int B, float margin,
              const float* __restrict__ diag, float* __restrict__ cnt, double* __restrict__ acc, int* __restrict__ rank_row,
              int* __restrict__ rank_col, float* __restrict__ dacc, int dpad, int n_units, int n_slabs, int ncb, int nk,
-             int num_slots) {
+             int num_slots, int split, const float* __restrict__ scales) {
+  // split (fp32 inputs staged as fp16 [hi | lo] rows, lo at column dpad): nk = 3 dpad / 64 score chunks with the column maps
+  // A = [hi | lo | hi], B = [hi | hi | lo] (tc_common.cuh), the gradient operand is hi + lo (two MMAs per box position), and
+  // the staged rows carry a power-of-two scale per tensor: true score = accumulator * scales[0] * scales[1]
+  const int nkd = dpad / KC;
+  const int nparts = split ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
@@ -144,8 +151,8 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               tma_load_2d(st, &tmapB, full_bar(ring.stage), kc * KC, col0);
             } else {
               mbar_arrive_expect_tx(full_bar(ring.stage), 2 * CHUNK_BYTES);
-              tma_load_2d(st, &tmapA, full_bar(ring.stage), kc * KC, row0);
-              tma_load_2d(st + CHUNK_BYTES, &tmapB, full_bar(ring.stage), kc * KC, col0);
+              tma_load_2d(st, &tmapA, full_bar(ring.stage), split ? a_kcol(kc, nkd) : kc * KC, row0);
+              tma_load_2d(st + CHUNK_BYTES, &tmapB, full_bar(ring.stage), split ? b_kcol(kc, nkd) : kc * KC, col0);
               mbar_arrive(full_bar(ring.stage + 1));
             }
           }
@@ -157,18 +164,21 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
       auto load_dA = [&](int j) {          // B operand of dA(j): B_j[:, slab] as [128 j][64 d] boxes
         const int col0 = j * MM_TN;
         for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
-          mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
-          if (dadv2) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
-          if (elect_one()) {
-            const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
-            mbar_arrive_expect_tx(full_bar(ring.stage), dpair ? 2 * CHUNK_BYTES : CHUNK_BYTES);
-            tma_load_2d(st, &tmapB, full_bar(ring.stage), d0 + c * KC, col0);
-            if (dpair) tma_load_2d(st + CHUNK_BYTES, &tmapB, full_bar(ring.stage), d0 + (c + 1) * KC, col0);
-            if (dadv2) mbar_arrive(full_bar(ring.stage + 1));   // keep the skipped slot's barriers in phase
+          for (int part = 0; part < nparts; ++part) {          // hi, then lo (split rows)
+            const int dc = part * dpad + d0 + c * KC;
+            mbar_wait(empty_bar(ring.stage), ring.phase ^ 1);
+            if (dadv2) mbar_wait(empty_bar(ring.stage + 1), ring.phase ^ 1);
+            if (elect_one()) {
+              const uint32_t st = ring_base + ring.stage * CHUNK_BYTES;
+              mbar_arrive_expect_tx(full_bar(ring.stage), dpair ? 2 * CHUNK_BYTES : CHUNK_BYTES);
+              tma_load_2d(st, &tmapB, full_bar(ring.stage), dc, col0);
+              if (dpair) tma_load_2d(st + CHUNK_BYTES, &tmapB, full_bar(ring.stage), dc + KC, col0);
+              if (dadv2) mbar_arrive(full_bar(ring.stage + 1));   // keep the skipped slot's barriers in phase
+            }
+            __syncwarp();
+            ring.advance();
+            if (dadv2) ring.advance();
           }
-          __syncwarp();
-          ring.advance();
-          if (dadv2) ring.advance();
         }
       };
       load_S(sg.j0);
@@ -228,7 +238,8 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
         tc_fence_after();
         if (kGrad) {
           const uint32_t p_tmem = tmem_base + buf * MM_TN;
-          for (int c = 0; c < nsc; c += (dpair ? 2 : 1)) {
+          for (int c = 0; c < nsc; c += (dpair ? 2 : 1))
+          for (int part = 0; part < nparts; ++part) {
             mbar_wait(full_bar(ring.stage), ring.phase);
             tc_fence_after();
             if (elect_one()) {
@@ -241,7 +252,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
                 const uint64_t bd = make_smem_desc_sw128(st + k16 * 2048, 1024, CHUNK_BYTES);
                 const uint32_t g_tmem = p_tmem + (k16 < 4 ? k16 * 8 : 64 + (k16 - 4) * 8);
                 umma_ts(tmem_acc + c * KC, g_tmem, bd, dpair ? idesc_g128 : idesc_g64,
-                        (j > sg.j0 || k16 > 0) ? 1u : 0u);
+                        (j > sg.j0 || k16 > 0 || part > 0) ? 1u : 0u);
               }
               umma_commit(empty_bar(ring.stage));
               if (dadv2) umma_commit(empty_bar(ring.stage + 1));
@@ -267,6 +278,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
     const int r = qd * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float ninf = __int_as_float(0xff800000);
+    const float sc = scales != nullptr ? scales[0] * scales[1] : 1.0f;      // both powers of two: exact
     uint32_t seg_iter = 0, p_cnt = 0;
     double tot = 0.0;
     int pend_col0 = -1;                      // forward: column block whose counts sit in ccnt[(p_cnt - 1) & 1]
@@ -321,10 +333,10 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               const float4 cc = cv4[q >> 2];
               const float x0 = __uint_as_float(v[q]), x1 = __uint_as_float(v[q + 1]);
               const float x2 = __uint_as_float(v[q + 2]), x3 = __uint_as_float(v[q + 3]);
-              float g0 = (x0 + mi > 0.f ? 1.f : 0.f) + (x0 + cc.x > 0.f ? 1.f : 0.f);
-              float g1 = (x1 + mi > 0.f ? 1.f : 0.f) + (x1 + cc.y > 0.f ? 1.f : 0.f);
-              float g2 = (x2 + mi > 0.f ? 1.f : 0.f) + (x2 + cc.z > 0.f ? 1.f : 0.f);
-              float g3 = (x3 + mi > 0.f ? 1.f : 0.f) + (x3 + cc.w > 0.f ? 1.f : 0.f);
+              float g0 = (fmaf(x0, sc, mi) > 0.f ? 1.f : 0.f) + (fmaf(x0, sc, cc.x) > 0.f ? 1.f : 0.f);
+              float g1 = (fmaf(x1, sc, mi) > 0.f ? 1.f : 0.f) + (fmaf(x1, sc, cc.y) > 0.f ? 1.f : 0.f);
+              float g2 = (fmaf(x2, sc, mi) > 0.f ? 1.f : 0.f) + (fmaf(x2, sc, cc.z) > 0.f ? 1.f : 0.f);
+              float g3 = (fmaf(x3, sc, mi) > 0.f ? 1.f : 0.f) + (fmaf(x3, sc, cc.w) > 0.f ? 1.f : 0.f);
               if (j == sg.ib) {                        // G_ii is applied by the finishing pass
                 const int cq = cb + q;
                 if (cq + 0 == r) g0 = 0.f;
@@ -346,7 +358,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 4; ++e) {            // four independent accumulation chains
                 const float x = __uint_as_float(v[q + e]);
-                const float hs = x + mi, hc = x + cj[e];             // trainer/loss.py:34, :35
+                const float hs = fmaf(x, sc, mi), hc = fmaf(x, sc, cj[e]);   // trainer/loss.py:34, :35
                 loc[e] += fmaxf(hs, 0.f) + fmaxf(hc, 0.f);
                 rc4[e] += hs > 0.f ? 1 : 0;
                 const unsigned m = __ballot_sync(0xffffffffu, hc > 0.f);
@@ -359,7 +371,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
               const int gj = col0 + cb + q;
               const bool valid = gi < B && gj < B && gi != gj;       // :36-40
               const float x = __uint_as_float(v[q]);
-              const float hs = x + mi, hc = x + cv[cb + q];
+              const float hs = fmaf(x, sc, mi), hc = fmaf(x, sc, cv[cb + q]);
               if (valid) {
                 loc[q & 3] += fmaxf(hs, 0.f) + fmaxf(hc, 0.f);
                 rc4[q & 3] += hs > 0.f ? 1 : 0;
@@ -438,8 +450,9 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// d_i = im_i . s_i in fp32 (one warp per row, 16-bit inputs), and the per-call state zeroed: counts, ranks, the loss sum
-template <typename T>
+// d_i = im_i . s_i in fp32 (one warp per row, the caller's own tensors), and the per-call state zeroed: counts, ranks, the
+// loss sum.  kVec: rows are 16-byte aligned (16-byte loads); fp32 rows of the split path may have any alignment.
+template <typename T, bool kVec>
 __global__ void __launch_bounds__(256) mm_tc_diag_kernel(const T* __restrict__ im, int64_t im_stride, const T* __restrict__ s,
                                                         int64_t s_stride, int B, int D, float* __restrict__ diag,
                                                         float* __restrict__ cnt, int* __restrict__ rank_row,
@@ -448,16 +461,19 @@ __global__ void __launch_bounds__(256) mm_tc_diag_kernel(const T* __restrict__ i
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) acc[0] = 0.0;
   if (row >= B) return;
-  const T* a = im + (int64_t)row * im_stride;          // 16-byte aligned rows (maxmargin_tc_applies)
+  const T* a = im + (int64_t)row * im_stride;
   const T* b = s + (int64_t)row * s_stride;
+  constexpr int E = 16 / (int)sizeof(T);
   float dot = 0.f;
-  const int dv = D & ~7;
-  for (int d = lane * 8; d < dv; d += 256) {
-    const uint4 ua = *reinterpret_cast<const uint4*>(a + d), ub = *reinterpret_cast<const uint4*>(b + d);
-    const T* pa = reinterpret_cast<const T*>(&ua);
-    const T* pb = reinterpret_cast<const T*>(&ub);
+  const int dv = kVec ? (D / E) * E : 0;
+  if (kVec) {
+    for (int d = lane * E; d < dv; d += 32 * E) {
+      const uint4 ua = *reinterpret_cast<const uint4*>(a + d), ub = *reinterpret_cast<const uint4*>(b + d);
+      const T* pa = reinterpret_cast<const T*>(&ua);
+      const T* pb = reinterpret_cast<const T*>(&ub);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dot = fmaf(to_float<T>(pa[e]), to_float<T>(pb[e]), dot);
+      for (int e = 0; e < E; ++e) dot = fmaf(to_float<T>(pa[e]), to_float<T>(pb[e]), dot);
+    }
   }
   for (int d = dv + lane; d < D; d += 32) dot = fmaf(to_float<T>(a[d]), to_float<T>(b[d]), dot);
   dot = warp_sum(dot);
@@ -469,38 +485,79 @@ __global__ void __launch_bounds__(256) mm_tc_diag_kernel(const T* __restrict__ i
   }
 }
 
+// ---- fp32 inputs: rows staged as fp16 [hi | lo] pairs after a power-of-two scale per tensor ----------------------------------
+// max |x| of a tensor as the bit pattern of a non-negative float (ordered like unsigned integers); out[0] zeroed by the caller
+__global__ void __launch_bounds__(256) mm_absmax_kernel(const float* __restrict__ x, int64_t stride, int B, int D,
+                                                       unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < B; row += gridDim.x * (blockDim.x >> 5))
+    for (int d = threadIdx.x & 31; d < D; d += 32) m = fmaxf(m, fabsf(x[(int64_t)row * stride + d]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// x' = x 2^-e with max |x'| in [2^13, 2^14) (the top of the fp16 range, so that hi keeps 11 bits for 27 binades below the
+// maximum and hi + lo 22 bits for 16); hi = fp16(x'), lo = fp16(x' - hi); out row = [hi (dpad) | lo (dpad)], zero padded.
+// scale_out[0] = 2^e: true score = (staged score) * scale_a * scale_b.
+__global__ void __launch_bounds__(256) mm_split_kernel(const float* __restrict__ x, int64_t stride, int B, int D, int dpad,
+                                                      const unsigned int* __restrict__ absmax, __half* __restrict__ out,
+                                                      float* __restrict__ scale_out) {
+  const float mx = __uint_as_float(absmax[0]);
+  int e = 0;
+  if (mx > 0.f && mx < __int_as_float(0x7f800000)) e = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127 - 13;
+  e = max(-126, min(126, e));                     // 2^e and 2^-e both normal floats, built from their bit patterns
+  const float down = __int_as_float((127 - e) << 23);
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale_out[0] = __int_as_float((127 + e) << 23);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  __half* o = out + (int64_t)row * 2 * dpad;
+  for (int d = lane * 2; d < dpad; d += 64) {
+    const float v0 = d < D ? x[(int64_t)row * stride + d] * down : 0.f;
+    const float v1 = d + 1 < D ? x[(int64_t)row * stride + d + 1] * down : 0.f;
+    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+    *reinterpret_cast<__half2*>(o + d) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(o + dpad + d) =
+        __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+  }
+}
+
 __global__ void mm_tc_loss_kernel(const double* __restrict__ acc, int B, double* __restrict__ loss) {
   loss[0] = acc[0] / ((double)B * (double)B);                              // trainer/loss.py:41
 }
 
-// out[a, :] = (c / B^2) (dacc[a, :] - cnt_a Bm[a, :]); one warp per row
+// out[a, :] = (c / B^2) (dacc[a, :] acc_scale - cnt_a Bm[a, :]); one warp per row.  acc_scale: the power-of-two scale of the
+// staged gradient operand (split path), Bm the caller's own rows.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) mm_tc_finish_kernel(const float* __restrict__ dacc, int dpad, const T* __restrict__ Bm,
                                                           int64_t b_stride, const float* __restrict__ cnt,
                                                           const double* __restrict__ grad_out, int B, int D,
-                                                          TO* __restrict__ out, int64_t out_stride) {
+                                                          TO* __restrict__ out, int64_t out_stride,
+                                                          const float* __restrict__ acc_scale) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   double c = 1.0 / ((double)B * (double)B);
   if (grad_out != nullptr) c *= grad_out[0];
   const float cf = (float)c, ca = cnt[row];
+  const float as = acc_scale != nullptr ? acc_scale[0] : 1.0f;
   for (int d = lane; d < D; d += 32) {
-    const float v = dacc[(int64_t)row * dpad + d] - ca * to_float<T>(Bm[(int64_t)row * b_stride + d]);
+    const float v = dacc[(int64_t)row * dpad + d] * as - ca * to_float<T>(Bm[(int64_t)row * b_stride + d]);
     out[(int64_t)row * out_stride + d] = from_float<TO>(cf * v);
   }
 }
 
-struct MmPlan { int nk, dpad, ncb, nrb, n_slabs, slots; bool resident; size_t smem; };
+struct MmPlan { int nk, dpad, ncb, nrb, n_slabs, slots, split; bool resident; size_t smem; };
 
-MmPlan mm_plan(int B, int D) {
+MmPlan mm_plan(int B, int D, bool split) {
   MmPlan p;
-  p.nk = (D + KC - 1) / KC;
-  p.dpad = p.nk * KC;
+  p.split = split ? 1 : 0;
+  p.dpad = (D + KC - 1) / KC * KC;
+  p.nk = p.dpad / KC * (split ? 3 : 1);             // score chunks: hi.hi + lo.hi + hi.lo on split rows
   p.ncb = (B + MM_TN - 1) / MM_TN;
   p.nrb = (B + TM - 1) / TM;
   p.n_slabs = (p.dpad + SLAB - 1) / SLAB;
-  p.resident = p.nk <= MAX_RES_CHUNKS;
+  p.resident = !split && p.nk <= MAX_RES_CHUNKS;    // split rows always stream A beside B
   const size_t a_bytes = p.resident ? (size_t)p.nk * CHUNK_BYTES : 0;
   const size_t avail = kMaxSmem - 1024 - MM_VEC_BYTES - kBarBytes - a_bytes;
   p.slots = std::min((int)(avail / CHUNK_BYTES) & ~1, MAX_SLOTS);
@@ -510,7 +567,7 @@ MmPlan mm_plan(int B, int D) {
 
 template <int kFmt, bool kGrad, bool kResident>
 int mm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, int B, float margin, const float* diag,
-                float* cnt, double* acc, int* rank_row, int* rank_col, float* dacc, cudaStream_t st) {
+                float* cnt, double* acc, int* rank_row, int* rank_col, float* dacc, const float* scales, cudaStream_t st) {
   const long long n_units_ll = (long long)p.nrb * (kGrad ? p.n_slabs : 1) * p.ncb;
   if (n_units_ll > 0x7fffffffLL) { set_error("maxmargin: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
   const int n_units = (int)n_units_ll;
@@ -518,18 +575,19 @@ int mm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, i
   auto kern = mm_tc_kernel<kFmt, kGrad, kResident>;
   CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   kern<<<grid, MM_THREADS, p.smem, st>>>(ta, tb, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, p.dpad, n_units,
-                                          kGrad ? p.n_slabs : 1, p.ncb, p.nk, p.slots);
+                                          kGrad ? p.n_slabs : 1, p.ncb, p.nk, p.slots, p.split, scales);
   return check_launch(kGrad ? "mm_tc_kernel<grad>" : "mm_tc_kernel<fwd>");
 }
 
 template <bool kGrad>
 int mm_launch(int dtype, const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, int B, float margin, const float* diag,
-              float* cnt, double* acc, int* rank_row, int* rank_col, float* dacc, cudaStream_t st) {
-  if (dtype == CROSSCLR_F16)
-    return p.resident ? mm_launch_t<0, kGrad, true>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, st)
-                      : mm_launch_t<0, kGrad, false>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, st);
-  return p.resident ? mm_launch_t<1, kGrad, true>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, st)
-                    : mm_launch_t<1, kGrad, false>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, st);
+              float* cnt, double* acc, int* rank_row, int* rank_col, float* dacc, const float* scales, cudaStream_t st) {
+  if (dtype == CROSSCLR_BF16)
+    return p.resident ? mm_launch_t<1, kGrad, true>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st)
+                      : mm_launch_t<1, kGrad, false>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
+  // fp16 rows: the caller's, or the staged [hi | lo] rows of fp32 inputs
+  return p.resident ? mm_launch_t<0, kGrad, true>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st)
+                    : mm_launch_t<0, kGrad, false>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
 }
 
 int mm_tmaps(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D, CUtensorMap* ta,
@@ -542,82 +600,135 @@ int mm_tmaps(const void* im, int64_t im_stride, const void* s, int64_t s_stride,
 
 template <typename T, typename TO>
 int mm_finish_t(const float* dacc, int dpad, const void* Bm, int64_t bs, const float* cnt, const double* go, int B, int D,
-                void* out, int64_t os, cudaStream_t st) {
-  mm_tc_finish_kernel<T, TO><<<(B + 7) / 8, 256, 0, st>>>(dacc, dpad, (const T*)Bm, bs, cnt, go, B, D, (TO*)out, os);
+                void* out, int64_t os, const float* acc_scale, cudaStream_t st) {
+  mm_tc_finish_kernel<T, TO><<<(B + 7) / 8, 256, 0, st>>>(dacc, dpad, (const T*)Bm, bs, cnt, go, B, D, (TO*)out, os, acc_scale);
   return check_launch("mm_tc_finish_kernel");
 }
 
 template <typename T>
 int mm_finish(const float* dacc, int dpad, const void* Bm, int64_t bs, const float* cnt, const double* go, int B, int D,
-              void* out, int64_t os, int out_dtype, cudaStream_t st) {
+              void* out, int64_t os, int out_dtype, const float* acc_scale, cudaStream_t st) {
   switch (out_dtype) {
-    case CROSSCLR_F32: return mm_finish_t<T, float>(dacc, dpad, Bm, bs, cnt, go, B, D, out, os, st);
-    case CROSSCLR_F16: return mm_finish_t<T, __half>(dacc, dpad, Bm, bs, cnt, go, B, D, out, os, st);
-    case CROSSCLR_BF16: return mm_finish_t<T, __nv_bfloat16>(dacc, dpad, Bm, bs, cnt, go, B, D, out, os, st);
+    case CROSSCLR_F32: return mm_finish_t<T, float>(dacc, dpad, Bm, bs, cnt, go, B, D, out, os, acc_scale, st);
+    case CROSSCLR_F16: return mm_finish_t<T, __half>(dacc, dpad, Bm, bs, cnt, go, B, D, out, os, acc_scale, st);
+    case CROSSCLR_BF16: return mm_finish_t<T, __nv_bfloat16>(dacc, dpad, Bm, bs, cnt, go, B, D, out, os, acc_scale, st);
     default: set_error("crossclr_maxmargin_bwd: unsupported output dtype %d", out_dtype); return CROSSCLR_EINVAL;
   }
 }
 
+// Stage block of the split path inside the workspace: unsigned absmax[2] | float scale[2] | pad to 256 | half im[B][2 dpad] |
+// half s[B][2 dpad]
+struct MmStage { unsigned int* absmax; float* scales; __half* a; __half* b; };
+MmStage mm_stage(void* stage, int B, int D) {
+  const int dpad = (D + KC - 1) / KC * KC;
+  MmStage m;
+  m.absmax = (unsigned int*)stage;
+  m.scales = (float*)((char*)stage + 8);
+  m.a = (__half*)((char*)stage + 256);
+  m.b = m.a + (size_t)B * 2 * dpad;
+  return m;
+}
+
 }  // namespace
 
-// The tensor maps address the caller's tensors directly: 16-bit elements, 16-byte aligned rows; below one tile of rows or one
-// K chunk of columns the CUDA-core kernels are the better fit.
+// 16-bit inputs: the tensor maps address the caller's tensors directly (16-byte aligned rows).  fp32 inputs: staged as fp16
+// [hi | lo] rows in the workspace (any alignment).  Below one tile of rows or one K chunk of columns the CUDA-core kernels
+// are the better fit.
 bool maxmargin_tc_applies(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D) {
-  if (dtype != CROSSCLR_F16 && dtype != CROSSCLR_BF16) return false;
   if (B < 2 * TM || D < KC) return false;
+  if (dtype == CROSSCLR_F32) return true;
+  if (dtype != CROSSCLR_F16 && dtype != CROSSCLR_BF16) return false;
   if ((reinterpret_cast<uintptr_t>(im) | reinterpret_cast<uintptr_t>(s)) & 15u) return false;
   if ((im_stride | s_stride) & 7) return false;
   return true;
 }
 
 size_t maxmargin_tc_dacc_bytes(int B, int D) {
-  const MmPlan p = mm_plan(B, D);
+  const MmPlan p = mm_plan(B, D, false);
   return (size_t)p.nrb * TM * p.dpad * sizeof(float);
 }
 
+size_t maxmargin_tc_stage_bytes(int B, int D, int dtype) {
+  if (dtype != CROSSCLR_F32) return 0;
+  const int dpad = (D + KC - 1) / KC * KC;
+  return 256 + 2 * (size_t)B * 2 * dpad * sizeof(__half);
+}
+
 int launch_maxmargin_tc_fwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
-                            float margin, float* diag, float* cnt, double* acc, int* rank_row, int* rank_col, double* loss,
-                            cudaStream_t st) {
+                            float margin, float* diag, float* cnt, double* acc, void* stage, int* rank_row, int* rank_col,
+                            double* loss, cudaStream_t st) {
   CUtensorMap ta, tb;
-  int rc = mm_tmaps(im, im_stride, s, s_stride, dtype, B, D, &ta, &tb);
-  if (rc) return rc;
-  if (dtype == CROSSCLR_F16)
-    mm_tc_diag_kernel<__half><<<(B + 7) / 8, 256, 0, st>>>((const __half*)im, im_stride, (const __half*)s, s_stride, B, D,
-                                                          diag, cnt, rank_row, rank_col, acc);
-  else
-    mm_tc_diag_kernel<__nv_bfloat16><<<(B + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)im, im_stride,
-                                                                 (const __nv_bfloat16*)s, s_stride, B, D, diag, cnt,
-                                                                 rank_row, rank_col, acc);
+  const bool split = dtype == CROSSCLR_F32;
+  const MmPlan p = mm_plan(B, D, split);
+  const float* scales = nullptr;
+  int rc;
+  if (split) {
+    const MmStage m = mm_stage(stage, B, D);
+    CC_CHECK_CUDA(cudaMemsetAsync(m.absmax, 0, 8, st));
+    const int grid = std::min((B + 7) / 8, 4 * sm_count());
+    mm_absmax_kernel<<<grid, 256, 0, st>>>((const float*)im, im_stride, B, D, m.absmax);
+    mm_absmax_kernel<<<grid, 256, 0, st>>>((const float*)s, s_stride, B, D, m.absmax + 1);
+    mm_split_kernel<<<(B + 7) / 8, 256, 0, st>>>((const float*)im, im_stride, B, D, p.dpad, m.absmax, m.a, m.scales);
+    mm_split_kernel<<<(B + 7) / 8, 256, 0, st>>>((const float*)s, s_stride, B, D, p.dpad, m.absmax + 1, m.b, m.scales + 1);
+    rc = check_launch("mm_split_kernel");
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    if (rc) return rc;
+    rc = mm_tmaps(m.a, 2 * p.dpad, m.b, 2 * p.dpad, CROSSCLR_F16, B, 2 * p.dpad, &ta, &tb);
+    scales = m.scales;
+    if (rc) return rc;
+    mm_tc_diag_kernel<float, false><<<(B + 7) / 8, 256, 0, st>>>((const float*)im, im_stride, (const float*)s, s_stride, B, D,
+                                                                 diag, cnt, rank_row, rank_col, acc);
+  } else {
+    rc = mm_tmaps(im, im_stride, s, s_stride, dtype, B, D, &ta, &tb);
+    if (rc) return rc;
+    if (dtype == CROSSCLR_F16)
+      mm_tc_diag_kernel<__half, true><<<(B + 7) / 8, 256, 0, st>>>((const __half*)im, im_stride, (const __half*)s, s_stride, B,
+                                                                   D, diag, cnt, rank_row, rank_col, acc);
+    else
+      mm_tc_diag_kernel<__nv_bfloat16, true><<<(B + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)im, im_stride,
+                                                                          (const __nv_bfloat16*)s, s_stride, B, D, diag, cnt,
+                                                                          rank_row, rank_col, acc);
+  }
   rc = check_launch("mm_tc_diag_kernel");
   if (rc) return rc;
-  const MmPlan p = mm_plan(B, D);
-  rc = mm_launch<false>(dtype, ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, nullptr, st);
+  rc = mm_launch<false>(dtype, ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, nullptr, scales, st);
   if (rc || loss == nullptr) return rc;
   mm_tc_loss_kernel<<<1, 1, 0, st>>>(acc, B, loss);
   return check_launch("mm_tc_loss_kernel");
 }
 
 int launch_maxmargin_tc_bwd(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D,
-                            float margin, const float* diag, const float* cnt, float* dacc, const double* grad_out,
-                            void* d_im, int64_t d_im_stride, void* d_s, int64_t d_s_stride, int out_dtype,
-                            cudaStream_t st) {
+                            float margin, const float* diag, const float* cnt, float* dacc, void* stage,
+                            const double* grad_out, void* d_im, int64_t d_im_stride, void* d_s, int64_t d_s_stride,
+                            int out_dtype, cudaStream_t st) {
   CUtensorMap ta, tb;
-  int rc = mm_tmaps(im, im_stride, s, s_stride, dtype, B, D, &ta, &tb);
+  const bool split = dtype == CROSSCLR_F32;
+  const MmPlan p = mm_plan(B, D, split);
+  const float* scales = nullptr;
+  int rc;
+  if (split) {                     // the forward staged the rows (same inputs, same workspace)
+    const MmStage m = mm_stage(stage, B, D);
+    rc = mm_tmaps(m.a, 2 * p.dpad, m.b, 2 * p.dpad, CROSSCLR_F16, B, 2 * p.dpad, &ta, &tb);
+    scales = m.scales;
+  } else {
+    rc = mm_tmaps(im, im_stride, s, s_stride, dtype, B, D, &ta, &tb);
+  }
   if (rc) return rc;
-  const MmPlan p = mm_plan(B, D);
   const size_t dacc_bytes = maxmargin_tc_dacc_bytes(B, D);
   for (int dir = 0; dir < 2 && !rc; ++dir) {
     // dir 0: dL/dim = G s (rows of im against rows of s); dir 1: dL/ds = G^T im -- the same tile formula, operands exchanged
     CC_CHECK_CUDA(cudaMemsetAsync(dacc, 0, dacc_bytes, st));
     rc = mm_launch<true>(dtype, dir ? tb : ta, dir ? ta : tb, p, B, margin, diag, const_cast<float*>(cnt), nullptr, nullptr,
-                         nullptr, dacc, st);
+                         nullptr, dacc, scales, st);
     if (rc) break;
     const void* Bm = dir ? im : s;
     const int64_t bs = dir ? im_stride : s_stride;
     void* out = dir ? d_s : d_im;
     const int64_t os = dir ? d_s_stride : d_im_stride;
-    rc = dtype == CROSSCLR_F16 ? mm_finish<__half>(dacc, p.dpad, Bm, bs, cnt, grad_out, B, D, out, os, out_dtype, st)
-                               : mm_finish<__nv_bfloat16>(dacc, p.dpad, Bm, bs, cnt, grad_out, B, D, out, os, out_dtype, st);
+    const float* as = split ? scales + (dir ? 0 : 1) : nullptr;        // the scale of the gradient operand's tensor
+    if (dtype == CROSSCLR_F32) rc = mm_finish<float>(dacc, p.dpad, Bm, bs, cnt, grad_out, B, D, out, os, out_dtype, as, st);
+    else if (dtype == CROSSCLR_F16) rc = mm_finish<__half>(dacc, p.dpad, Bm, bs, cnt, grad_out, B, D, out, os, out_dtype, as, st);
+    else rc = mm_finish<__nv_bfloat16>(dacc, p.dpad, Bm, bs, cnt, grad_out, B, D, out, os, out_dtype, as, st);
   }
   return rc;
 }

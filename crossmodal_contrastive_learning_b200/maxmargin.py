@@ -41,7 +41,7 @@ class _MaxMarginFunction(torch.autograd.Function):
         a, b = _rowmajor(im.detach()), _rowmajor(s.detach())
         B, D = a.shape
         with torch.cuda.device(a.device):
-            ws_bytes = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
+            ws_bytes = int(lib.crossclr_maxmargin_workspace_bytes(B, D, _DTYPE_CODE[a.dtype]))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
             loss = torch.empty((), dtype=torch.float64, device=a.device)
             N.check(lib.crossclr_maxmargin_fwd(_ptr(a), _ptr(b), _DTYPE_CODE[a.dtype], a.stride(0), b.stride(0), B, D,

@@ -28,7 +28,7 @@ def retrieval_ranks(im: torch.Tensor, s: torch.Tensor):
     a, b = _rowmajor(im.detach()), _rowmajor(s.detach())
     B, D = a.shape
     with torch.cuda.device(a.device):
-        ws_bytes = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
+        ws_bytes = int(lib.crossclr_maxmargin_workspace_bytes(B, D, _DTYPE_CODE[a.dtype]))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
         r_a = torch.empty(B, dtype=torch.int32, device=a.device)
         r_b = torch.empty(B, dtype=torch.int32, device=a.device)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CROSSCLR_VERSION 130          /* 0.1.3 */
+#define CROSSCLR_VERSION 140          /* 0.1.4 */
 
 /* error codes */
 #define CROSSCLR_OK            0
@@ -246,17 +246,18 @@ CROSSCLR_API int crossclr_timing_read(int kernel, double* total_ms, int64_t* lau
  * MaxMargin_coot (trainer/loss.py:17-41; SURVEY.md section 8 row f1 -- beside the CrossCLR hot path).  No batch x batch
  * array is stored.
  *   loss_out[0] (double) = (1/B^2) sum_{i != j} [max(0, m + s_ij - s_ii) + max(0, m + s_ij - s_jj)],  s = im s^T
- * `im`, `s`: [batch][dim] device arrays of `dtype`, row strides in elements.  fp16 / bf16 inputs with batch >= 256,
- * dim >= 64 and 16-byte aligned rows (base pointers and row strides) run on the tensor cores -- tcgen05 score tiles whose
- * TMA boxes come straight out of the caller's tensors, a hinge epilogue, and for the backward the 0/1/2 indicator tile as the
- * A operand of the gradient product; everything else (fp32 inputs: the reference multiplies them in fp32) on exact fp32
- * CUDA-core kernels (dim <= 1600 there).  crossclr_maxmargin_kernel_name reports which (CROSSCLR_MAXMARGIN_PATH=simt|tc
- * overrides).  The forward leaves the diagonal and the hinge counts in `workspace`
- * (crossclr_maxmargin_workspace_bytes(batch, dim) bytes), which the backward reads and extends; `grad_out` is a DEVICE
- * pointer to the upstream scalar gradient (double) or NULL for 1.0.
+ * `im`, `s`: [batch][dim] device arrays of `dtype`, row strides in elements.  batch >= 256 and dim >= 64 run on the tensor
+ * cores -- tcgen05 score tiles, a hinge epilogue, and for the backward the 0/1/2 indicator tile as the A operand of the
+ * gradient product.  fp16 / bf16 inputs (16-byte aligned base pointers and row strides) are read by TMA straight out of the
+ * caller's tensors; fp32 inputs (the reference multiplies them in fp32) are staged in the workspace as fp16 hi + lo pairs after a
+ * power-of-two scale per tensor and the score product runs over K = 3 dim (hi.hi + lo.hi + hi.lo): fp32-grade scores.
+ * Everything else runs on exact fp32 CUDA-core kernels (dim <= 1600 there).  crossclr_maxmargin_kernel_name reports which
+ * (CROSSCLR_MAXMARGIN_PATH=simt|tc overrides).  The forward leaves the diagonal, the hinge counts and (fp32) the staged
+ * rows in `workspace` (crossclr_maxmargin_workspace_bytes(batch, dim, dtype) bytes), which the backward reads and
+ * extends; `grad_out` is a DEVICE pointer to the upstream scalar gradient (double) or NULL for 1.0.
  * Replaces: trainer/loss.py:29-41 (forward) and its autograd backward.
  */
-CROSSCLR_API size_t crossclr_maxmargin_workspace_bytes(int32_t batch, int32_t dim);
+CROSSCLR_API size_t crossclr_maxmargin_workspace_bytes(int32_t batch, int32_t dim, int dtype);
 CROSSCLR_API const char* crossclr_maxmargin_kernel_name(const void* im, const void* s, int dtype, int64_t im_row_stride,
                                            int64_t s_row_stride, int32_t batch, int32_t dim);
 CROSSCLR_API int crossclr_maxmargin_fwd(const void* im, const void* s, int dtype, int64_t im_row_stride, int64_t s_row_stride,

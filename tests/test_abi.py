@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(N.EXPORTS) == names           # the ctypes binding covers exactly the header
-    assert lib.crossclr_version() == 130
+    assert lib.crossclr_version() == 140
 
 
 def test_planning_and_validation_without_a_device():

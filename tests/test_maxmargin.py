@@ -103,7 +103,7 @@ def _mm_raw(a, b, margin, grad_out=None):
     B, D = a.shape
     code = _DTYPE_CODE[a.dtype]
     name = lib.crossclr_maxmargin_kernel_name(_ptr(a), _ptr(b), code, a.stride(0), b.stride(0), B, D).decode()
-    nb = int(lib.crossclr_maxmargin_workspace_bytes(B, D))
+    nb = int(lib.crossclr_maxmargin_workspace_bytes(B, D, code))
     ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
     loss = torch.empty((), dtype=torch.float64, device=a.device)
     N.check(lib.crossclr_maxmargin_fwd(_ptr(a), _ptr(b), code, a.stride(0), b.stride(0), B, D, float(margin), _ptr(ws), nb,
@@ -118,7 +118,9 @@ def _mm_raw(a, b, margin, grad_out=None):
 
 
 TC_SHAPES = [(512, 512, torch.bfloat16), (4096, 512, torch.bfloat16), (1000, 200, torch.float16),
-             (300, 72, torch.float16), (2048, 1024, torch.bfloat16), (1100, 640, torch.bfloat16), (256, 64, torch.float16)]
+             (300, 72, torch.float16), (2048, 1024, torch.bfloat16), (1100, 640, torch.bfloat16), (256, 64, torch.float16),
+             # fp32 inputs: staged as fp16 hi + lo pairs, score product over K = 3 D
+             (512, 512, torch.float32), (1000, 200, torch.float32), (333, 77, torch.float32), (2048, 1024, torch.float32)]
 
 
 @pytest.mark.gpu
@@ -128,12 +130,18 @@ def test_tensor_core_path_against_oracle(B, D, dtype):
     im, s = _paired(B, D, seed=B + D)
     if dtype == torch.float16:
         im, s = im.half().float(), s.half().float()
+    if dtype == torch.float32:                                 # values that need the lo halves (not 16-bit representable)
+        g = torch.Generator().manual_seed(1)
+        im = im * (1.0 + 1e-3 * torch.randn(B, D, generator=g))
+        s = s * (1.0 + 1e-3 * torch.randn(B, D, generator=g))
     rloss, rdim, rds = maxmargin_loss_and_grads(im.numpy(), s.numpy(), 0.1, grad_out=0.5)
     assert rloss > 1e-3                                        # the case exercises active hinges
     loss, da, db, name = _mm_raw(im.to(dtype).cuda(), s.to(dtype).cuda(), 0.1, grad_out=0.5)
     assert name == "mm_tc_kernel"
-    # exact products, fp32 accumulation: the loss to rounding; a hinge within rounding of 0 may flip one 1/B^2 entry
-    assert abs(loss - rloss) <= 2e-6 * abs(rloss)
+    # exact products, fp32 accumulation: the loss to rounding; a hinge within rounding of 0 may flip one 1/B^2 entry.  fp32
+    # inputs: hi + lo products are 22-bit and the tensor cores' accumulation truncates them, a one-sided 2^-22-of-|a||b| error per
+    # score that does not average out over the hinges (measured 3e-6 of the loss)
+    assert abs(loss - rloss) <= (1e-5 if dtype == torch.float32 else 2e-6) * abs(rloss)
     for got, ref in ((da, rdim), (db, rds)):
         assert np.linalg.norm(got - ref) <= 1e-3 * np.linalg.norm(ref)
 
@@ -149,15 +157,44 @@ def test_tensor_core_and_cuda_core_paths_agree(monkeypatch):
     assert (n0, n1) == ("mm_fwd_kernel", "mm_tc_kernel")
     assert abs(l0 - l1) <= 2e-6 * abs(l0)
     assert np.linalg.norm(da0 - da1) <= 1e-3 * np.linalg.norm(da0) and np.linalg.norm(db0 - db1) <= 1e-3 * np.linalg.norm(db0)
-    # fp32 inputs are never rounded to 16 bits; asking for the tensor cores there is an error, not a silent downgrade
+    # fp32 inputs: hi + lo operands on the tensor cores against the exact CUDA-core kernels
+    l3, da3, db3, n3 = _mm_raw(im.cuda(), s.cuda(), 0.2)
+    monkeypatch.setenv("CROSSCLR_MAXMARGIN_PATH", "simt")
+    l2, da2, db2, n2 = _mm_raw(im.cuda(), s.cuda(), 0.2)
+    assert (n2, n3) == ("mm_fwd_kernel", "mm_tc_kernel")
+    assert abs(l2 - l3) <= 1e-5 * abs(l2) and np.linalg.norm(da2 - da3) <= 1e-3 * np.linalg.norm(da2)
+    # asking for the tensor cores on a problem they do not take is an error, not a silent downgrade
+    monkeypatch.setenv("CROSSCLR_MAXMARGIN_PATH", "tc")
     with pytest.raises(RuntimeError, match="tensor-core kernels need"):
-        _mm_raw(im.cuda(), s.cuda(), 0.2)
+        _mm_raw(a[:100], b[:100], 0.2)
     monkeypatch.delenv("CROSSCLR_MAXMARGIN_PATH")
-    assert _mm_raw(im.cuda(), s.cuda(), 0.2)[3] == "mm_fwd_kernel"
-    # a row pitch that breaks the 16-byte alignment of the TMA boxes falls back to the CUDA cores
+    # a row pitch that breaks the 16-byte alignment of the TMA boxes falls back to the CUDA cores (16-bit inputs are not staged)
     wide = torch.zeros(768, 260, dtype=torch.bfloat16, device="cuda")
     wide[:, :256] = a
     assert _mm_raw(wide[:, :256], b, 0.2)[3] == "mm_fwd_kernel"
+    # fp32 rows are staged, so any pitch rides the tensor cores
+    widef = torch.zeros(768, 259, dtype=torch.float32, device="cuda")
+    widef[:, :256] = im.cuda()
+    l4, da4, _, n4 = _mm_raw(widef[:, :256], s.cuda(), 0.2)
+    assert n4 == "mm_tc_kernel" and abs(l4 - l3) <= 1e-9 * abs(l3) and np.array_equal(da4, da3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [300.0, 1.0 / 64, 1e-6])
+def test_tensor_core_fp32_inputs_at_any_magnitude(scale):
+    """The staged fp16 pairs carry a power-of-two scale per tensor: unnormalised embeddings far outside the fp16 range (or deep
+    inside its subnormals) keep fp32-grade scores."""
+    from oracle.maxmargin_oracle import maxmargin_loss_and_grads
+    im, s = _paired(640, 192, seed=11)
+    g = torch.Generator().manual_seed(2)
+    im = im * (1.0 + 1e-3 * torch.randn(640, 192, generator=g)) * scale
+    s = s * (1.0 + 1e-3 * torch.randn(640, 192, generator=g)) * (scale * 4.0)
+    m = 0.1 * scale * scale * 4.0
+    rloss, rdim, rds = maxmargin_loss_and_grads(im.numpy(), s.numpy(), m)
+    loss, da, db, name = _mm_raw(im.cuda(), s.cuda(), m)
+    assert name == "mm_tc_kernel"
+    assert abs(loss - rloss) <= 1e-5 * abs(rloss)
+    assert np.linalg.norm(da - rdim) <= 1e-3 * np.linalg.norm(rdim) and np.linalg.norm(db - rds) <= 1e-3 * np.linalg.norm(rds)
 
 
 @pytest.mark.gpu
