@@ -176,7 +176,8 @@ def test_tensor_core_and_cuda_core_paths_agree(monkeypatch):
     widef = torch.zeros(768, 259, dtype=torch.float32, device="cuda")
     widef[:, :256] = im.cuda()
     l4, da4, _, n4 = _mm_raw(widef[:, :256], s.cuda(), 0.2)
-    assert n4 == "mm_tc_kernel" and abs(l4 - l3) <= 1e-9 * abs(l3) and np.array_equal(da4, da3)
+    # (partial row-block sums meet through fp32 atomics: equal to rounding, not bit for bit)
+    assert n4 == "mm_tc_kernel" and abs(l4 - l3) <= 1e-9 * abs(l3) and np.linalg.norm(da4 - da3) <= 1e-5 * np.linalg.norm(da3)
 
 
 @pytest.mark.gpu
