@@ -493,6 +493,18 @@ def run_next_rows(M, NAT, torch, dev, flush, reps=10):
             NAT.check(lib.crossclr_maxmargin_bwd(af.data_ptr(), bd.data_ptr(), code, D, D, B, D, 0.1, ws.data_ptr(), ws_n, None,
                                                  da.data_ptr(), D, db.data_ptr(), D, NAT.F32, st), "crossclr_maxmargin_bwd")
             torch.cuda.synchronize()
+            # the same values as fp32 tensors: fp16 hi + lo operands, K = 3 D
+            a32 = im.float().to(dev).requires_grad_()
+            b32 = s.float().to(dev).requires_grad_()
+
+            def step32():
+                a32.grad = b32.grad = None
+                crit(a32, b32).backward()
+
+            rec["fp32_inputs"] = {"step_ms": timed(step32), "parity_dim_rel": float(np.linalg.norm(a32.grad.double().cpu().numpy() - rda)
+                                                                                     / np.linalg.norm(rda)),
+                                  "kernel": lib.crossclr_maxmargin_kernel_name(a32.data_ptr(), b32.data_ptr(), NAT.F32, D, D, B, D).decode(),
+                                  "what": "fp32 embeddings staged as fp16 hi + lo pairs (per-tensor power-of-two scale)"}
             ra, rb, _ = oracle_ranks(im.float().numpy(), s.float().numpy())
             ga, gb = M.retrieval_ranks(a.detach(), bd)
             rec["parity"] = {"loss_rel": abs(loss64.item() - rl) / abs(rl),
