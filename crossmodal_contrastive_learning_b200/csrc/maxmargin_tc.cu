@@ -573,7 +573,13 @@ int mm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, i
   const int n_units = (int)n_units_ll;
   const int grid = std::min(n_units, sm_count());
   auto kern = mm_tc_kernel<kFmt, kGrad, kResident>;
-  CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  // opt-in shared memory: once per device and instantiation (the largest plan's size covers every other)
+  static std::atomic<int> smem_set[64];
+  const int slot = current_device_slot();
+  if (smem_set[slot].load(std::memory_order_relaxed) < (int)p.smem) {
+    CC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    smem_set[slot].store((int)p.smem, std::memory_order_relaxed);
+  }
   kern<<<grid, MM_THREADS, p.smem, st>>>(ta, tb, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, p.dpad, n_units,
                                           kGrad ? p.n_slabs : 1, p.ncb, p.nk, p.slots, p.split, scales);
   return check_launch(kGrad ? "mm_tc_kernel<grad>" : "mm_tc_kernel<fwd>");
