@@ -64,17 +64,21 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 }
 
 // kFmt: 0 = fp16, 1 = bf16 operands.  kGrad: false = forward (hinge sums, counts), true = one direction of the backward.
-template <int kFmt, bool kGrad, bool kResident>
+// kVar: 0 = row block streamed beside the column blocks, 1 = row block resident in shared memory (D <= 512), 2 = split rows
+// (fp32 inputs as fp16 [hi | lo], streamed) -- compile-time, so that the 16-bit kernels carry none of the split bookkeeping.
+template <int kFmt, bool kGrad, int kVar>
 __global__ void __launch_bounds__(MM_THREADS, 1)
 mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int B, float margin,
              const float* __restrict__ diag, float* __restrict__ cnt, double* __restrict__ acc, int* __restrict__ rank_row,
              int* __restrict__ rank_col, float* __restrict__ dacc, int dpad, int n_units, int n_slabs, int ncb, int nk,
-             int num_slots, int split, const float* __restrict__ scales) {
+             int num_slots, const float* __restrict__ scales) {
+  constexpr bool kResident = kVar == 1;
+  constexpr bool split = kVar == 2;
   // split (fp32 inputs staged as fp16 [hi | lo] rows, lo at column dpad): nk = 3 dpad / 64 score chunks with the column maps
   // A = [hi | lo | hi], B = [hi | hi | lo] (tc_common.cuh), the gradient operand is hi + lo (two MMAs per box position), and
   // the staged rows carry a power-of-two scale per tensor: true score = accumulator * scales[0] * scales[1]
   const int nkd = dpad / KC;
-  const int nparts = split ? 2 : 1;
+  constexpr int nparts = split ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_region = base;
@@ -278,7 +282,7 @@ mm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ 
     const int r = qd * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
     const float ninf = __int_as_float(0xff800000);
-    const float sc = scales != nullptr ? scales[0] * scales[1] : 1.0f;      // both powers of two: exact
+    const float sc = split ? scales[0] * scales[1] : 1.0f;      // both powers of two: exact (16-bit inputs: folds away)
     uint32_t seg_iter = 0, p_cnt = 0;
     double tot = 0.0;
     int pend_col0 = -1;                      // forward: column block whose counts sit in ccnt[(p_cnt - 1) & 1]
@@ -565,14 +569,14 @@ MmPlan mm_plan(int B, int D, bool split) {
   return p;
 }
 
-template <int kFmt, bool kGrad, bool kResident>
+template <int kFmt, bool kGrad, int kVar>
 int mm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, int B, float margin, const float* diag,
                 float* cnt, double* acc, int* rank_row, int* rank_col, float* dacc, const float* scales, cudaStream_t st) {
   const long long n_units_ll = (long long)p.nrb * (kGrad ? p.n_slabs : 1) * p.ncb;
   if (n_units_ll > 0x7fffffffLL) { set_error("maxmargin: problem too large (%lld work units)", n_units_ll); return CROSSCLR_EINVAL; }
   const int n_units = (int)n_units_ll;
   const int grid = std::min(n_units, sm_count());
-  auto kern = mm_tc_kernel<kFmt, kGrad, kResident>;
+  auto kern = mm_tc_kernel<kFmt, kGrad, kVar>;
   // opt-in shared memory: once per device and instantiation (the largest plan's size covers every other)
   static std::atomic<int> smem_set[64];
   const int slot = current_device_slot();
@@ -581,19 +585,20 @@ int mm_launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, i
     smem_set[slot].store((int)p.smem, std::memory_order_relaxed);
   }
   kern<<<grid, MM_THREADS, p.smem, st>>>(ta, tb, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, p.dpad, n_units,
-                                          kGrad ? p.n_slabs : 1, p.ncb, p.nk, p.slots, p.split, scales);
+                                          kGrad ? p.n_slabs : 1, p.ncb, p.nk, p.slots, scales);
   return check_launch(kGrad ? "mm_tc_kernel<grad>" : "mm_tc_kernel<fwd>");
 }
 
 template <bool kGrad>
 int mm_launch(int dtype, const CUtensorMap& ta, const CUtensorMap& tb, const MmPlan& p, int B, float margin, const float* diag,
               float* cnt, double* acc, int* rank_row, int* rank_col, float* dacc, const float* scales, cudaStream_t st) {
+  if (p.split)          // fp32 inputs: staged fp16 [hi | lo] rows
+    return mm_launch_t<0, kGrad, 2>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
   if (dtype == CROSSCLR_BF16)
-    return p.resident ? mm_launch_t<1, kGrad, true>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st)
-                      : mm_launch_t<1, kGrad, false>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
-  // fp16 rows: the caller's, or the staged [hi | lo] rows of fp32 inputs
-  return p.resident ? mm_launch_t<0, kGrad, true>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st)
-                    : mm_launch_t<0, kGrad, false>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
+    return p.resident ? mm_launch_t<1, kGrad, 1>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st)
+                      : mm_launch_t<1, kGrad, 0>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
+  return p.resident ? mm_launch_t<0, kGrad, 1>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st)
+                    : mm_launch_t<0, kGrad, 0>(ta, tb, p, B, margin, diag, cnt, acc, rank_row, rank_col, dacc, scales, st);
 }
 
 int mm_tmaps(const void* im, int64_t im_stride, const void* s, int64_t s_stride, int dtype, int B, int D, CUtensorMap* ta,
