@@ -77,6 +77,51 @@ def test_planning_and_validation_without_a_device():
     assert lib.crossclr_timing_read(99, ctypes.byref(tot), ctypes.byref(n)) == -1
 
 
+def test_maxmargin_and_peer_planning_without_a_device(monkeypatch):
+    """The MaxMargin / retrieval path rule, its workspace size and the peer exchange's argument checks are pure host logic."""
+    from crossmodal_contrastive_learning_b200 import _native as N
+    lib = N.load()
+    monkeypatch.delenv("CROSSCLR_MAXMARGIN_PATH", raising=False)
+    name = lambda a, b, dt, sa, sb, B, D: lib.crossclr_maxmargin_kernel_name(a, b, dt, sa, sb, B, D).decode()
+    assert name(0x1000, 0x2000, N.BF16, 512, 512, 4096, 512) == "mm_tc_kernel"      # 16-bit rows read in place by TMA
+    assert name(0x1000, 0x2000, N.F16, 520, 512, 300, 72) == "mm_tc_kernel"
+    assert name(0x1002, 0x2000, N.BF16, 512, 512, 4096, 512) == "mm_fwd_kernel"     # rows not 16-byte aligned
+    assert name(0x1000, 0x2000, N.BF16, 516, 512, 4096, 512) == "mm_fwd_kernel"     # pitch not a multiple of 16 bytes
+    assert name(0x1004, 0x2004, N.F32, 513, 777, 4096, 512) == "mm_tc_kernel"       # fp32 rows are staged: any alignment
+    assert name(0x1000, 0x2000, N.BF16, 512, 512, 128, 512) == "mm_fwd_kernel"      # below two tiles of rows
+    assert name(0x1000, 0x2000, N.BF16, 32, 32, 4096, 32) == "mm_fwd_kernel"        # below one K chunk
+    monkeypatch.setenv("CROSSCLR_MAXMARGIN_PATH", "simt")
+    assert name(0x1000, 0x2000, N.BF16, 512, 512, 4096, 512) == "mm_fwd_kernel"
+    monkeypatch.setenv("CROSSCLR_MAXMARGIN_PATH", "tc")
+    assert name(0x1000, 0x2000, N.BF16, 512, 512, 128, 512) == "invalid"            # an error, never a silent downgrade
+    monkeypatch.delenv("CROSSCLR_MAXMARGIN_PATH")
+    ws16 = lib.crossclr_maxmargin_workspace_bytes(4096, 512, N.BF16)
+    ws32 = lib.crossclr_maxmargin_workspace_bytes(4096, 512, N.F32)
+    assert ws16 >= 16 + 2 * 4096 * 4 + 4096 * 512 * 4                               # state + a direction's fp32 accumulator
+    assert ws32 - ws16 == 256 + 2 * 4096 * 2 * 512 * 2                              # + the staged fp16 [hi | lo] rows
+    assert lib.crossclr_maxmargin_workspace_bytes(1000, 200, N.F16) >= 1024 * 256 * 4       # padded to 128 rows / 64 columns
+    assert lib.crossclr_maxmargin_workspace_bytes(0, 512, N.BF16) == 0
+    # workspace too small / bad shapes are refused before anything is launched
+    one = ctypes.c_void_p(0x1000)
+    assert lib.crossclr_maxmargin_fwd(one, one, N.BF16, 512, 512, 4096, 512, 0.1, one, 64, one, None) == -3      # EWORKSPACE
+    assert b"workspace too small" in lib.crossclr_last_error()
+    assert lib.crossclr_maxmargin_fwd(one, one, N.BF16, 100, 512, 4096, 512, 0.1, one, ws16, one, None) == -1    # stride < dim
+    assert lib.crossclr_retrieval_ranks(one, one, N.BF16, 512, 512, 4096, 512, one, ws16, None, one, None) == -1
+    # peer exchange: collective geometry and alignment are checked on the host
+    bases = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    flags = (ctypes.c_void_p * 2)(0x3000, 0x4000)
+    assert lib.crossclr_peer_exchange(bases, flags, 1, 0, 0, 256, 0, one, None) == -1        # a single rank exchanges nothing
+    assert lib.crossclr_peer_exchange(bases, flags, 2, 2, 0, 256, 0, one, None) == -1        # rank outside the group
+    assert lib.crossclr_peer_exchange(bases, flags, 2, 0, 8, 256, 0, one, None) == -1        # offset not a multiple of 16
+    assert lib.crossclr_peer_exchange(bases, flags, 17, 0, 0, 256, 0, one, None) == -1       # more ranks than one node holds
+    holes = (ctypes.c_void_p * 2)(0x1000, None)
+    assert lib.crossclr_peer_exchange(holes, flags, 2, 0, 0, 256, 0, one, None) == -1 and b"rank 1" in lib.crossclr_last_error()
+    import crossmodal_contrastive_learning_b200 as M
+    with pytest.raises(ValueError):
+        M.CrossCLR_onlyIntraModality(exchange="mpi")
+    assert M.CrossCLR_onlyIntraModality(exchange="peer").exchange == "peer"
+
+
 def test_module_surface_on_cpu():
     import crossmodal_contrastive_learning_b200 as M
     from trainer.loss import CrossCLR_onlyIntraModality
