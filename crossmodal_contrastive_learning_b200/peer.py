@@ -34,20 +34,39 @@ class PeerPlan:
         self.stats_bytes = (stats_bytes + 255) // 256 * 256
         self.generation = 0
         total = self.feat_bytes + self.stats_bytes
+        # Every step below is taken by EVERY rank, whatever fails locally: a rank that left the sequence early would leave the
+        # others waiting in a collective.  The closing all-reduce is both the agreement on success and the barrier "every rank
+        # has mapped every buffer" that must precede the first store.
+        err, mine = None, None
+        self._local = self._ctrl = None
+        self._peers, bases, flags = [], [], []
         with torch.cuda.device(device):
-            self._local = self._alloc(total)
-            self._ctrl = self._alloc(_CTRL_BYTES)
+            try:
+                self._local = self._alloc(total)
+                self._ctrl = self._alloc(_CTRL_BYTES)
+                mine = (self._export(self._local), self._export(self._ctrl))
+            except Exception as exc:             # noqa: BLE001 -- reported to every rank below
+                err = exc
             handles = [None] * self.world
-            dist.all_gather_object(handles, (self._export(self._local), self._export(self._ctrl)), group=group)
-            self._peers, bases, flags = [], [], []
-            for r, (hb, hc) in enumerate(handles):
-                if r == self.rank:
-                    bases.append(self._local); flags.append(self._ctrl)
-                else:
-                    pb, pc = self._import(hb), self._import(hc)
-                    self._peers += [pb, pc]
-                    bases.append(pb); flags.append(pc)
-            dist.barrier(group=group)            # every rank has mapped every buffer before anyone stores into them
+            dist.all_gather_object(handles, mine, group=group)
+            if err is None and any(h is None for h in handles):
+                err = RuntimeError("a peer rank could not allocate or export its buffers")
+            if err is None:
+                try:
+                    for r, (hb, hc) in enumerate(handles):
+                        if r == self.rank:
+                            bases.append(self._local); flags.append(self._ctrl)
+                        else:
+                            pb, pc = self._import(hb), self._import(hc)
+                            self._peers += [pb, pc]
+                            bases.append(pb); flags.append(pc)
+                except Exception as exc:         # noqa: BLE001
+                    err = exc
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                raise RuntimeError(f"exchange='peer': the peer buffers could not be mapped on every rank "
+                                   f"({'this rank: ' + str(err) if err is not None else 'another rank failed'})")
         self._bases = (ctypes.c_void_p * self.world)(*bases)
         self._flags = (ctypes.c_void_p * self.world)(*flags)
         self._state = self._ctrl + 512
