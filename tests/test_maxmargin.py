@@ -246,3 +246,61 @@ def test_retrieval_ranks_against_oracle(B, D, dtype):
     m = M.retrieval_metrics(im.to(dtype).cuda(), s.to(dtype).cuda())
     assert abs(m["im2s_R@10"] - recall_at_k(ra)[10]) <= 2.0 / B and abs(m["s2im_R@1"] - recall_at_k(rb)[1]) <= 2.0 / B
     assert m["im2s_MedR"] >= 1.0
+
+
+# ---- CPU: properties of the checkers and of the staged fp32 representation (no GPU) ----------------------------------------
+def test_oracle_symmetry_and_rank_definition():
+    """Swapping the two blocks transposes the score matrix: same loss, gradients exchanged, rank arrays exchanged; the ranks
+    equal the position of the partner in a stable descending sort when there are no ties."""
+    from oracle.maxmargin_oracle import maxmargin_loss_and_grads
+    from oracle.retrieval_oracle import retrieval_ranks
+    rng = np.random.default_rng(3)
+    im, s = rng.standard_normal((37, 11)), rng.standard_normal((37, 11))
+    l0, da0, db0 = maxmargin_loss_and_grads(im, s, 0.3)
+    l1, da1, db1 = maxmargin_loss_and_grads(s, im, 0.3)
+    assert abs(l0 - l1) < 1e-12 and np.allclose(da0, db1) and np.allclose(db0, da1)
+    ra, rb, _ = retrieval_ranks(im, s)
+    rb2, ra2, _ = retrieval_ranks(s, im)
+    assert (ra == ra2).all() and (rb == rb2).all()
+    scores = im @ s.T
+    order = np.argsort(-scores, axis=1, kind="stable")
+    assert (ra == np.array([int(np.where(order[i] == i)[0][0]) for i in range(37)])).all()
+    # the hinge indicators at margin 0 are the rank indicators (what lets one kernel serve both): with orthonormal s the diagonal
+    # coefficient of the gradient, -(active hinges in row i + in column i) / B^2, reads off as (dL/dim_i . s_i)
+    q, _ = np.linalg.qr(rng.standard_normal((16, 16)))
+    im2 = rng.standard_normal((16, 16))
+    _, da, _ = maxmargin_loss_and_grads(im2, q, 0.0)
+    ra2, rb2, _ = retrieval_ranks(im2, q)
+    coef = da @ q.T * 16 * 16                      # G (rows of s orthonormal): off-diagonal indicators, diagonal -(counts)
+    assert np.allclose(-np.diag(coef), ra2 + rb2)
+
+
+@pytest.mark.parametrize("scale", [1.0, 300.0, 1e-6, 3e4])
+def test_staged_fp16_pairs_keep_fp32_grade_scores(scale):
+    """numpy restatement of mm_absmax_kernel / mm_split_kernel (csrc/maxmargin_tc.cu): x 2^-e with the tensor's largest magnitude
+    in [2^13, 2^14), hi = fp16, lo = fp16(rest); score = (hi.hi + lo.hi + hi.lo) 2^(e_a + e_b).  The representation error of a
+    score stays ~2^-22 of |a||b| whatever the inputs' magnitude -- without the scale fp16 would overflow or flush."""
+    rng = np.random.default_rng(5)
+    a = (rng.standard_normal((64, 256)) * scale).astype(np.float32)
+    b = (rng.standard_normal((64, 256)) * scale * 4).astype(np.float32)
+
+    def stage(x):
+        mx = np.abs(x).max()
+        e = int(np.floor(np.log2(mx))) - 13
+        e = max(-126, min(126, e))
+        xs = (x.astype(np.float64) * 2.0 ** -e).astype(np.float32)
+        assert 2.0 ** 13 <= np.abs(xs).max() < 2.0 ** 14
+        hi = xs.astype(np.float16)
+        lo = (xs - hi.astype(np.float32)).astype(np.float16)
+        assert np.isfinite(hi).all()
+        return hi.astype(np.float64), lo.astype(np.float64), 2.0 ** e
+
+    ha, la, ca = stage(a)
+    hb, lb, cb = stage(b)
+    staged = (ha @ hb.T + la @ hb.T + ha @ lb.T) * ca * cb
+    exact = a.astype(np.float64) @ b.astype(np.float64).T
+    bound = np.linalg.norm(a.astype(np.float64), axis=1)[:, None] * np.linalg.norm(b.astype(np.float64), axis=1)[None, :]
+    assert (np.abs(staged - exact) / bound).max() < 2.0 ** -21
+    # a single fp16 rounding of the same rows is ~2^-11 per element: three orders of magnitude worse on the scores
+    single = (ha @ hb.T) * ca * cb
+    assert (np.abs(single - exact) / bound).max() > 50 * (np.abs(staged - exact) / bound).max()
