@@ -158,9 +158,10 @@ def test_header_is_plain_c_and_the_c_host_example_links():
     from crossmodal_contrastive_learning_b200 import _native as N
     N.load()                                               # make sure the library is built
     with tempfile.TemporaryDirectory() as tmp:
-        cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
-               os.path.join(root, "examples", "c_host.c"), "-L", os.path.join(root, "crossmodal_contrastive_learning_b200"),
-               "-lcrossclr_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,--allow-shlib-undefined",
-               "-o", os.path.join(tmp, "c_host")]
-        p = subprocess.run(cmd, capture_output=True, text=True)
-        assert p.returncode == 0, p.stderr
+        for example in ("c_host", "retrieval_host"):        # the CrossCLR step; MaxMargin_coot + retrieval ranks
+            cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                   os.path.join(root, "examples", example + ".c"), "-L", os.path.join(root, "crossmodal_contrastive_learning_b200"),
+                   "-lcrossclr_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-Wl,--allow-shlib-undefined",
+                   "-o", os.path.join(tmp, example)]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
